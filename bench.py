@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the CodeFormer hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = one CodeFormer.forward(x, w=0.5, adain=True) over one batch of 32 synthetic 512x512 faces per
+GPU (BASELINE.json configs[1]; N GPUs = configs[4], 32 faces/GPU, weak scaling) followed -- for N>1 -- by
+the one NCCL all-gather of `out`.  Random-init weights of the reference architecture
+(no checkpoints offline) and synthetic inputs; both stated in the JSON line.
+
+Printed (rank 0, ONE line): metric/value/unit/... per the driver contract, plus
+  e2e          same metric through the public nn.Module API with pinned HOST input -> H2D -> forward -> D2H of out
+  roofline     dominant kernel (the 128->128 3x3 conv at 256^2, 13 of the 128 convs) timed alone with CUDA events
+  cpu_baseline the oracle port timed on this box's host cores on a bounded sample (N=1 only)
+  clocks       nvidia-smi samples taken during the timed region
+`--impl reference` times the reference's CPU algorithm (oracle port; torch CPU fp32 = the reference's own math
+backend) on the same config with all host threads, each step a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'faces_per_sec_512x512_batch32'
+UNIT = 'faces/s'
+GFLOP_PER_FACE = 809.77          # CodeFormer.forward, w>0, 4 connects
+FALLBACK_PEAKS = {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}   # B200_PROFILING.md
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return {k: float(d[k]) for k in FALLBACK_PEAKS}, 'measured'
+        except Exception:
+            pass
+    return dict(FALLBACK_PEAKS), 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '200', '-i', str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(nme)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def synthetic_batch(batch, seed):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(batch, 3, 512, 512, generator=g).clamp_(-1, 1)     # SURVEY.md §8d config 5 inputs
+
+
+def config_dict(n_gpus, batch):
+    return {'workload': 'CodeFormer.forward(w=0.5, adain=True) on 512x512 aligned faces, batch 32 per GPU '
+                        '(BASELINE.json configs[1]; N GPUs -> configs[4] weak scaling, one NCCL all-gather of out)',
+            'batch_per_gpu': batch, 'global_batch': batch * n_gpus, 'w': 0.5, 'adain': True,
+            'weights': 'random-init (seed 1) of the reference architecture, 94.1 M params fp32',
+            'gflop_per_face': GFLOP_PER_FACE,
+            'l2': 'timed iterations rotate over 2 input batches (201 MB > 126 MB L2); activations ~10 GB per step',
+            'parallelism': f'dp{n_gpus}'}
+
+
+def time_oracle(batch, passes, seed=0):
+    """faces/s of the oracle port (torch CPU fp32, all host threads)."""
+    import torch
+    from codeformer_b200 import spec as S
+    from oracle import codeformer_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = S.random_state_dict(S.codeformer_spec(), 1)
+    x = synthetic_batch(batch, seed)
+    times = []
+    with torch.no_grad():
+        for _ in range(passes):
+            t = time.perf_counter()
+            O.codeformer_forward(sd, x, w=0.5, adain_on=True)
+            times.append(time.perf_counter() - t)
+    return times, torch.get_num_threads()
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port) on the host cores."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    batch = 1 if (args.steps + args.warmup) > 6 else 2      # bounded sample per step: whole run stays within minutes
+    times, cores = time_oracle(batch, args.warmup + args.steps)
+    timed = times[args.warmup:]
+    total = sum(timed)
+    value = batch * len(timed) / total
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(timed), 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config_dict(args.gpus, 32),
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                             'sample': f'{batch} face(s) per step (bounded sample of the batch-32 workload), '
+                                       f'{len(timed)} timed steps, torch CPU fp32 oneDNN'},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+def dominant_kernel_roofline(torch, cb, batch, peaks, peak_kind):
+    """Time the dominant conv (ResBlock 128->128 3x3 at 256^2: 13 launches of 19.33 GFLOP/face, Appendix A)
+    alone through the C ABI with CUDA events on the launching stream."""
+    import ctypes
+    from codeformer_b200 import _lib
+    lib = _lib.load()
+    N, H, C = batch, 256, 128
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(N, H, H, C, generator=g).cuda()
+    w = (torch.randn(C, C, 3, 3, generator=g) / (9 * C) ** 0.5).cuda()
+    b = torch.zeros(C).cuda()
+    out = torch.empty(N, H, H, C, device='cuda')
+    wsb = lib.cfb_conv2d_workspace_bytes(N, H, H, C, C, 3, 0)
+    ws = torch.empty(int(wsb), dtype=torch.uint8, device='cuda')
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def launch():
+        _lib.check(lib.cfb_conv2d_nhwc(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(out), N, H, H, C, C, 3, 0, None, None,
+                                       0, None, 0, 0, _lib.ptr(ws), wsb, st), 'conv')
+    for _ in range(3):
+        launch()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        launch()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    flops = 2.0 * N * H * H * C * C * 9
+    achieved = flops / (ms * 1e-3) / 1e12
+    return {'bound': 'tensor', 'kernel': 'conv 3x3 128->128 @256^2 (implicit GEMM, operand prep + weight split included)',
+            'achieved': achieved, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s', 'frac': achieved / peaks['bf16_tflops'],
+            'peak_kind': f'{peak_kind} bf16 burst (MEASURED_PEAKS.json)', 'ms_per_launch': ms,
+            'algorithmic_gflop_per_launch': flops / 1e9, 'traffic': None}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import codeformer_b200 as cb
+    from codeformer_b200 import spec as S
+
+    torch.set_grad_enabled(False)
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.gpus > 1 and world != args.gpus:
+        raise SystemExit(f'--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    batch = args.batch
+    net = cb.ARCH_REGISTRY.get('CodeFormer')(dim_embd=512, codebook_size=1024, n_head=8, n_layers=9,
+                                            connect_list=['32', '64', '128', '256']).to(dev).eval()
+    net.load_state_dict(S.random_state_dict(S.codeformer_spec(), 1), strict=True)
+    xs_host = [synthetic_batch(batch, 100 + rank * 2 + i).pin_memory() for i in range(2)]
+    xs = [x.to(dev) for x in xs_host]
+    gathered = torch.empty((world * batch, 3, 512, 512), device=dev) if world > 1 else None
+
+    def step(i):
+        out = net(xs[i % 2], w=0.5, adain=True)[0]
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)          # the one collective of the path (§8e)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    launches = net.last_launch_count * args.steps
+    clocks = sampler.stop() if sampler else None
+    ms_total = float(ms.item())
+    value = world * batch * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: public API with host buffers, H2D + D2H inside the timed region
+    out_host = torch.empty((batch, 3, 512, 512), dtype=torch.float32, pin_memory=True)
+
+    def step_e2e(i):
+        x = xs_host[i % 2].to(dev, non_blocking=True)
+        out = net(x, w=0.5, adain=True)[0]
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)
+        out_host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()               # the caller reads the result (tensor2img .cpu())
+    e_steps = max(2, min(args.steps, 5))
+    step_e2e(0)
+    barrier()
+    e0.record()
+    for i in range(e_steps):
+        step_e2e(i)
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = world * batch * e_steps / (float(ms2.item()) * 1e-3)
+    img_bytes = batch * 3 * 512 * 512 * 4
+
+    if rank == 0:
+        peaks, peak_kind = load_peaks()
+        roof = dominant_kernel_roofline(torch, cb, batch, peaks, peak_kind)
+        step_tflops = value / world * GFLOP_PER_FACE / 1e3
+        roof['step_algorithmic_tflops_per_gpu'] = step_tflops
+        roof['step_frac_of_sustained_peak'] = step_tflops / peaks['bf16_tflops_sustained']
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+                'warmup': max(args.warmup, 3), 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
+                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (split-fp16 operands on tensor cores, fp32 accumulate)',
+                'data': 'synthetic', 'config': config_dict(world, batch),
+                'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': img_bytes, 'd2h_bytes_per_step': img_bytes,
+                        'steps': e_steps},
+                'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof}
+        if world == 1 and not args.no_cpu_baseline:
+            times, cores = time_oracle(2, 3)
+            best = min(times[1:])
+            line['cpu_baseline'] = {'value': 2 / best, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                                    'sample': '2 faces per pass (bounded sample of the batch-32 workload), best of 2 after '
+                                              '1 warm-up, torch CPU fp32 oneDNN'}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=32, help='faces per GPU (the metric is quoted at 32)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,460 @@
+"""Drop-in ``nn.Module`` mirrors of the reference networks, executing on libcfb200 (sm_100a).
+
+Same constructor signatures, ``state_dict`` keys/shapes and ``forward`` return tuples as
+
+    CodeFormer      /root/reference/basicsr/archs/codeformer_arch.py:160-280
+    VQAutoEncoder   /root/reference/basicsr/archs/vqgan_arch.py:326-389
+    VectorQuantizer /root/reference/basicsr/archs/vqgan_arch.py:24-84
+
+so ``net = ARCH_REGISTRY.get('CodeFormer')(...).to(device); net.load_state_dict(ckpt['params_ema']);
+net.eval(); net(x, w=w, adain=True)[0]`` (inference_codeformer.py:135-143, 204-206) works unchanged.
+
+PyTorch is plumbing here: the modules only *hold* parameters (so ``.to()``, ``load_state_dict`` and
+``named_parameters`` behave like the reference) and allocate output / workspace tensors.  All
+arithmetic is in the CUDA library behind the C ABI of ``include/cfb200.h``; there is no eager-PyTorch
+or CPU fallback -- a missing library, a CPU tensor or a failing kernel raises ``RuntimeError``.
+Inference only (the reference's callers run under ``torch.no_grad()``); autograd is not provided.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import threading
+from typing import Dict, Optional
+
+import torch
+from torch import nn
+
+from . import _lib
+from . import spec as S
+from .registry import ARCH_REGISTRY
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter holders: same attribute names and default initialisation as the torch layers the
+# reference instantiates, but no forward -- they are containers, the math is in libcfb200.
+# ------------------------------------------------------------------------------------------------
+class _ParamsOnly(nn.Module):
+    def forward(self, *a, **k):
+        raise RuntimeError(f'{type(self).__name__} is a parameter holder of codeformer_b200; the arithmetic runs '
+                           'inside libcfb200 through the owning network\'s forward')
+
+
+class _Conv(_ParamsOnly):
+    """Parameters of nn.Conv2d(cin, cout, k) (weight OIHW + bias), default init of torch."""
+
+    def __init__(self, cin, cout, k):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(cout, cin, k, k))
+        self.bias = nn.Parameter(torch.empty(cout))
+        bound = 1.0 / math.sqrt(cin * k * k)
+        nn.init.uniform_(self.weight, -bound, bound)
+        nn.init.uniform_(self.bias, -bound, bound)
+
+
+class _Linear(_ParamsOnly):
+    def __init__(self, cin, cout, bias=True):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(cout, cin))
+        bound = 1.0 / math.sqrt(cin)
+        nn.init.uniform_(self.weight, -bound, bound)
+        if bias:
+            self.bias = nn.Parameter(torch.empty(cout))
+            nn.init.uniform_(self.bias, -bound, bound)
+        else:
+            self.register_parameter('bias', None)
+
+
+class _Norm(_ParamsOnly):
+    """Parameters of GroupNorm(32, C, eps=1e-6) (vqgan_arch.py:14-15) or LayerNorm(C)."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(c))
+        self.bias = nn.Parameter(torch.zeros(c))
+
+
+class _ResBlock(_ParamsOnly):
+    """vqgan_arch.py:141-151"""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.in_channels, self.out_channels = cin, cout
+        self.norm1 = _Norm(cin)
+        self.conv1 = _Conv(cin, cout, 3)
+        self.norm2 = _Norm(cout)
+        self.conv2 = _Conv(cout, cout, 3)
+        if cin != cout:
+            self.conv_out = _Conv(cin, cout, 1)
+
+
+class _AttnBlock(_ParamsOnly):
+    """vqgan_arch.py:167-200"""
+
+    def __init__(self, c):
+        super().__init__()
+        self.in_channels = c
+        self.norm = _Norm(c)
+        self.q = _Conv(c, c, 1)
+        self.k = _Conv(c, c, 1)
+        self.v = _Conv(c, c, 1)
+        self.proj_out = _Conv(c, c, 1)
+
+
+class _Resample(_ParamsOnly):
+    """Downsample / Upsample (vqgan_arch.py:117-138): one 3x3 conv named ``conv``."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.conv = _Conv(c, c, 3)
+
+
+class _BlockStack(_ParamsOnly):
+    """Encoder / Generator (vqgan_arch.py:229-323): ``blocks`` ModuleList with the reference's order."""
+
+    def __init__(self, plan):
+        super().__init__()
+        blocks = []
+        for kind, cin, cout, _ in plan:
+            if kind == 'conv':
+                blocks.append(_Conv(cin, cout, 3))
+            elif kind == 'res':
+                blocks.append(_ResBlock(cin, cout))
+            elif kind == 'attn':
+                blocks.append(_AttnBlock(cin))
+            elif kind in ('down', 'up'):
+                blocks.append(_Resample(cin))
+            elif kind == 'norm':
+                blocks.append(_Norm(cin))
+        self.blocks = nn.ModuleList(blocks)
+
+
+class _Embedding(_ParamsOnly):
+    def __init__(self, k, d):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(k, d))
+        nn.init.uniform_(self.weight, -1.0 / k, 1.0 / k)          # vqgan_arch.py:31
+
+
+def _stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _require_cuda(x, what):
+    if not (torch.is_tensor(x) and x.is_cuda):
+        raise RuntimeError(f'{what}: codeformer_b200 runs on a CUDA device only (got {getattr(x, "device", type(x))}); '
+                           'there is no CPU fallback')
+    if x.dtype != torch.float32:
+        raise RuntimeError(f'{what}: expected float32, got {x.dtype}')
+
+
+class VectorQuantizer(nn.Module):
+    """``VectorQuantizer`` of vqgan_arch.py:24-84 on libcfb200 (``cfb_vq_nearest`` / ``cfb_codebook_lookup``)."""
+
+    def __init__(self, codebook_size, emb_dim, beta):
+        super().__init__()
+        self.codebook_size = codebook_size
+        self.emb_dim = emb_dim
+        self.beta = beta
+        self.embedding = _Embedding(codebook_size, emb_dim)
+
+    def forward(self, z, return_min_encodings=True):
+        _require_cuda(z, 'VectorQuantizer.forward')
+        lib = _lib.load()
+        z = z.contiguous()
+        B, D, H, W = z.shape
+        if D != self.emb_dim:
+            raise RuntimeError(f'VectorQuantizer: expected {self.emb_dim} channels, got {D}')
+        E = self.embedding.weight.detach().contiguous()
+        with torch.cuda.device(z.device):
+            zq = torch.empty_like(z)
+            idx = torch.empty((B * H * W, 1), dtype=torch.int64, device=z.device)
+            stats = torch.empty(4, dtype=torch.float32, device=z.device)
+            onehot = torch.empty((B * H * W, self.codebook_size), dtype=torch.float32, device=z.device) \
+                if return_min_encodings else None
+            wsb = lib.cfb_vq_workspace_bytes(B, H * W, D, self.codebook_size)
+            ws = torch.empty(int(wsb), dtype=torch.uint8, device=z.device)
+            _lib.check(lib.cfb_vq_nearest(_lib.ptr(z), _lib.ptr(E), B, H, W, D, self.codebook_size, float(self.beta),
+                                          _lib.ptr(zq), _lib.ptr(idx), _lib.ptr(stats), _lib.ptr(onehot),
+                                          _lib.ptr(ws), wsb, _stream_ptr(z.device)), 'cfb_vq_nearest')
+        return zq, stats[0], {'perplexity': stats[1], 'min_encodings': onehot,
+                              'min_encoding_indices': idx, 'mean_distance': stats[2]}
+
+    def get_codebook_feat(self, indices, shape):
+        """vqgan_arch.py:72-84: indices -> codebook rows; ``shape`` = [B,H,W,C] gives an NCHW result."""
+        if not indices.is_cuda:
+            raise RuntimeError('get_codebook_feat: CUDA tensors only')
+        lib = _lib.load()
+        idx = indices.reshape(-1).to(torch.int64).contiguous()
+        E = self.embedding.weight.detach().contiguous()
+        if shape is None:
+            B, H, W = idx.numel(), 1, 1
+        else:
+            B, H, W, C = shape
+            if C != self.emb_dim or B * H * W != idx.numel():
+                raise RuntimeError('get_codebook_feat: shape does not match the indices')
+        with torch.cuda.device(idx.device):
+            out = torch.empty((B, self.emb_dim, H, W), dtype=torch.float32, device=idx.device)
+            _lib.check(lib.cfb_codebook_lookup(_lib.ptr(idx), _lib.ptr(E), B, H, W, self.emb_dim, self.codebook_size,
+                                               _lib.ptr(out), _stream_ptr(idx.device)), 'cfb_codebook_lookup')
+        return out.view(B, self.emb_dim) if shape is None else out
+
+
+@ARCH_REGISTRY.register()
+class VQAutoEncoder(nn.Module):
+    """Mirror of ``VQAutoEncoder`` (vqgan_arch.py:326-389), quantizer='nearest'."""
+
+    _KIND = 0
+
+    def __init__(self, img_size, nf, ch_mult, quantizer='nearest', res_blocks=2, attn_resolutions=[16],
+                 codebook_size=1024, emb_dim=256, beta=0.25, gumbel_straight_through=False, gumbel_kl_weight=1e-8,
+                 model_path=None):
+        super().__init__()
+        if quantizer != 'nearest':
+            raise NotImplementedError("codeformer_b200 builds the 'nearest' quantizer only (the Gumbel quantizer is "
+                                      'training-only in the reference, SURVEY.md §2.1)')
+        self.in_channels = 3
+        self.nf = nf
+        self.n_blocks = res_blocks
+        self.codebook_size = codebook_size
+        self.embed_dim = emb_dim
+        self.ch_mult = list(ch_mult)
+        self.resolution = img_size
+        self.attn_resolutions = list(attn_resolutions)
+        self.quantizer_type = quantizer
+        self.encoder = _BlockStack(S.encoder_plan(nf, ch_mult, res_blocks, img_size, attn_resolutions, 3, emb_dim))
+        self.beta = beta
+        self.quantize = VectorQuantizer(codebook_size, emb_dim, beta)
+        self.generator = _BlockStack(S.generator_plan(nf, ch_mult, res_blocks, img_size, attn_resolutions, emb_dim))
+        self._cfb_init()
+        if model_path is not None:                                   # vqgan_arch.py:373-382
+            chkpt = torch.load(model_path, map_location='cpu')
+            if 'params_ema' in chkpt:
+                self.load_state_dict(chkpt['params_ema'])
+            elif 'params' in chkpt:
+                self.load_state_dict(chkpt['params'])
+            else:
+                raise ValueError('Wrong params!')
+
+    # ---- native handle management -------------------------------------------------------------
+    def _cfb_init(self):
+        object.__setattr__(self, '_cfb_lock', threading.Lock())
+        object.__setattr__(self, '_cfb_net', None)
+        object.__setattr__(self, '_cfb_sig', None)
+        object.__setattr__(self, '_cfb_keep', None)
+        object.__setattr__(self, '_cfb_ws', {})
+
+    def _cfb_config(self) -> '_lib.CfbConfig':
+        c = _lib.CfbConfig()
+        c.kind = self._KIND
+        c.img_size, c.nf, c.n_ch_mult = self.resolution, self.nf, len(self.ch_mult)
+        for i, m in enumerate(self.ch_mult):
+            c.ch_mult[i] = m
+        c.res_blocks = self.n_blocks
+        c.n_attn_res = len(self.attn_resolutions)
+        for i, r in enumerate(self.attn_resolutions):
+            c.attn_res[i] = r
+        c.codebook_size, c.emb_dim, c.beta = self.codebook_size, self.embed_dim, float(self.beta)
+        return c
+
+    def _cfb_prepare(self, device):
+        """(Re)build the native weight copies when parameters were loaded, moved or modified."""
+        lib = _lib.load()
+        params = list(self.state_dict(keep_vars=True).items())
+        sig = tuple((k, v.data_ptr(), v._version, str(v.device)) for k, v in params)
+        if self._cfb_net is not None and sig == self._cfb_sig:
+            return
+        if self._cfb_net is None:
+            cfg = self._cfb_config()
+            h = lib.cfb_net_create(ctypes.byref(cfg))
+            if not h:
+                _lib.check(1, 'cfb_net_create')
+            object.__setattr__(self, '_cfb_net', ctypes.c_void_p(h))
+        keep = []
+        for k, v in params:
+            if v.device != device:
+                raise RuntimeError(f'parameter {k} is on {v.device} but the input is on {device}; call net.to(device)')
+            t = v.detach()
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.float().contiguous()
+            keep.append(t)
+            _lib.check(lib.cfb_net_set_param(self._cfb_net, k.encode(), _lib.ptr(t), t.numel()), 'cfb_net_set_param')
+        _lib.check(lib.cfb_net_prepare(self._cfb_net, _stream_ptr(device)), 'cfb_net_prepare')
+        object.__setattr__(self, '_cfb_sig', sig)
+        object.__setattr__(self, '_cfb_keep', keep)
+
+    def _cfb_workspace(self, device, batch):
+        lib = _lib.load()
+        key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+        need = lib.cfb_workspace_bytes(self._cfb_net, batch)
+        if need < 0:
+            _lib.check(1, 'cfb_workspace_bytes')
+        ws = self._cfb_ws.get(key)
+        if ws is None or ws.numel() < need:
+            self._cfb_ws.pop(key, None)
+            ws = torch.empty(int(need), dtype=torch.uint8, device=device)   # owned by the module (the caller may
+            self._cfb_ws[key] = ws                                          # empty_cache() after every face)
+        return ws
+
+    def __del__(self):
+        try:
+            if getattr(self, '_cfb_net', None) is not None:
+                _lib.load().cfb_net_destroy(self._cfb_net)
+        except Exception:
+            pass
+
+    def _check_input(self, x):
+        _require_cuda(x, type(self).__name__ + '.forward')
+        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != self.resolution or x.shape[3] != self.resolution:
+            raise RuntimeError(f'expected input [B,3,{self.resolution},{self.resolution}], got {tuple(x.shape)}')
+        return x.contiguous()
+
+    @property
+    def last_launch_count(self) -> int:
+        return 0 if self._cfb_net is None else int(_lib.load().cfb_last_launch_count(self._cfb_net))
+
+    # ---- VQAutoEncoder.forward  vqgan_arch.py:385-389 -------------------------------------------
+    def forward(self, x, return_min_encodings=False):
+        """-> (x_hat [B,3,H,W], codebook_loss, {perplexity, min_encodings, min_encoding_indices, mean_distance}).
+        ``min_encodings`` (the [B*256, K] one-hot, 4 MB per face) is materialised only on request."""
+        x = self._check_input(x)
+        lib = _lib.load()
+        B = x.shape[0]
+        dev = x.device
+        with self._cfb_lock, torch.cuda.device(dev):
+            self._cfb_prepare(dev)
+            ws = self._cfb_workspace(dev, B)
+            out = torch.empty_like(x)
+            n_tok = B * (self.resolution >> (len(self.ch_mult) - 1)) ** 2
+            idx = torch.empty((n_tok, 1), dtype=torch.int64, device=dev)
+            stats = torch.empty(4, dtype=torch.float32, device=dev)
+            onehot = torch.empty((n_tok, self.codebook_size), dtype=torch.float32, device=dev) \
+                if return_min_encodings else None
+            _lib.check(lib.cfb_vqae_forward(self._cfb_net, _lib.ptr(x), _lib.ptr(out), _lib.ptr(idx), _lib.ptr(stats),
+                                            _lib.ptr(onehot), B, _lib.ptr(ws), ws.numel(), _stream_ptr(dev)),
+                       'cfb_vqae_forward')
+        return out, stats[0], {'perplexity': stats[1], 'min_encodings': onehot,
+                               'min_encoding_indices': idx, 'mean_distance': stats[2]}
+
+
+class _MHA(_ParamsOnly):
+    """Parameters of nn.MultiheadAttention(E, heads) (codeformer_arch.py:102)."""
+
+    def __init__(self, e):
+        super().__init__()
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * e, e))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * e))
+        self.out_proj = _Linear(e, e)
+        nn.init.xavier_uniform_(self.in_proj_weight)
+        nn.init.zeros_(self.out_proj.bias)
+
+
+class _TransformerSALayer(_ParamsOnly):
+    """codeformer_arch.py:99-113"""
+
+    def __init__(self, e, dim_mlp):
+        super().__init__()
+        self.self_attn = _MHA(e)
+        self.linear1 = _Linear(e, dim_mlp)
+        self.linear2 = _Linear(dim_mlp, e)
+        self.norm1 = _Norm(e)
+        self.norm2 = _Norm(e)
+
+
+class _FuseSft(_ParamsOnly):
+    """codeformer_arch.py:136-149"""
+
+    def __init__(self, c):
+        super().__init__()
+        self.encode_enc = _ResBlock(2 * c, c)
+        self.scale = nn.ModuleDict({'0': _Conv(c, c, 3), '2': _Conv(c, c, 3)})
+        self.shift = nn.ModuleDict({'0': _Conv(c, c, 3), '2': _Conv(c, c, 3)})
+
+
+@ARCH_REGISTRY.register()
+class CodeFormer(VQAutoEncoder):
+    """Mirror of ``CodeFormer`` (codeformer_arch.py:160-280)."""
+
+    _KIND = 1
+
+    def __init__(self, dim_embd=512, n_head=8, n_layers=9, codebook_size=1024, latent_size=256,
+                 connect_list=['32', '64', '128', '256'], fix_modules=['quantize', 'generator'], vqgan_path=None):
+        super().__init__(512, 64, [1, 2, 2, 4, 4, 8], 'nearest', 2, [16], codebook_size)
+        if vqgan_path is not None:                                  # codeformer_arch.py:168-170
+            self.load_state_dict(torch.load(vqgan_path, map_location='cpu')['params_ema'])
+        if fix_modules is not None:                                 # :172-175
+            for module in fix_modules:
+                for param in getattr(self, module).parameters():
+                    param.requires_grad = False
+        self.connect_list = list(connect_list)
+        self.n_layers = n_layers
+        self.n_head = n_head
+        self.dim_embd = dim_embd
+        self.dim_mlp = dim_embd * 2
+        self.latent_size = latent_size
+        self.position_emb = nn.Parameter(torch.zeros(latent_size, dim_embd))
+        self.feat_emb = _Linear(256, dim_embd)
+        self.ft_layers = nn.Sequential(*[_TransformerSALayer(dim_embd, self.dim_mlp) for _ in range(n_layers)])
+        self.idx_pred_layer = nn.Sequential(_Norm(dim_embd), _Linear(dim_embd, codebook_size, bias=False))
+        self.channels = dict(S.FUSE_CHANNELS)
+        self.fuse_encoder_block = dict(S.FUSE_ENCODER_BLOCK)
+        self.fuse_generator_block = dict(S.FUSE_GENERATOR_BLOCK)
+        self.fuse_convs_dict = nn.ModuleDict()
+        for f_size in self.connect_list:
+            self.fuse_convs_dict[f_size] = _FuseSft(self.channels[f_size])
+
+    def _cfb_config(self):
+        c = super()._cfb_config()
+        c.dim_embd, c.n_head, c.n_layers, c.latent_size = self.dim_embd, self.n_head, self.n_layers, self.latent_size
+        c.n_connect = len(self.connect_list)
+        for i, s in enumerate(self.connect_list):
+            c.connect[i] = int(s)
+        return c
+
+    def forward(self, x, w=0, detach_16=True, code_only=False, adain=False):
+        """-> (out [B,3,512,512], logits [B,256,K], lq_feat [B,256,16,16]); ``code_only`` -> (logits, lq_feat).
+        ``detach_16`` only affects autograd in the reference (:263-264) and is accepted for signature parity."""
+        x = self._check_input(x)
+        lib = _lib.load()
+        B = x.shape[0]
+        dev = x.device
+        with self._cfb_lock, torch.cuda.device(dev):
+            self._cfb_prepare(dev)
+            ws = self._cfb_workspace(dev, B)
+            logits = torch.empty((B, self.latent_size, self.codebook_size), dtype=torch.float32, device=dev)
+            lq_feat = torch.empty((B, 256, 16, 16), dtype=torch.float32, device=dev)
+            out = None if code_only else torch.empty_like(x)
+            _lib.check(lib.cfb_codeformer_forward(self._cfb_net, _lib.ptr(x), _lib.ptr(out), _lib.ptr(logits),
+                                                  _lib.ptr(lq_feat), None, B, float(w), int(bool(adain)),
+                                                  int(bool(code_only)), _lib.ptr(ws), ws.numel(), _stream_ptr(dev)),
+                       'cfb_codeformer_forward')
+        if code_only:
+            return logits, lq_feat
+        return out, logits, lq_feat
+
+    def forward_host(self, x_host, w=0, adain=False, device=None):
+        """End-to-end call with HOST tensors (``cfb_codeformer_forward_host``): pinned x -> H2D -> forward ->
+        D2H of out/logits/lq_feat -> one stream sync.  Returns pinned host tensors."""
+        lib = _lib.load()
+        if x_host.is_cuda or x_host.dtype != torch.float32:
+            raise RuntimeError('forward_host expects a float32 CPU tensor')
+        dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        x_host = x_host.contiguous()
+        B = x_host.shape[0]
+        with self._cfb_lock, torch.cuda.device(dev):
+            self._cfb_prepare(dev)
+            ws = self._cfb_workspace(dev, B)
+            iob = lib.cfb_host_io_bytes(self._cfb_net, B)
+            key = ('io', dev.index)
+            io = self._cfb_ws.get(key)
+            if io is None or io.numel() < iob:
+                io = torch.empty(int(iob), dtype=torch.uint8, device=dev)
+                self._cfb_ws[key] = io
+            out = torch.empty(x_host.shape, dtype=torch.float32, pin_memory=True)
+            logits = torch.empty((B, self.latent_size, self.codebook_size), dtype=torch.float32, pin_memory=True)
+            lq = torch.empty((B, 256, 16, 16), dtype=torch.float32, pin_memory=True)
+            _lib.check(lib.cfb_codeformer_forward_host(self._cfb_net, _lib.ptr(x_host), _lib.ptr(out), _lib.ptr(logits),
+                                                       _lib.ptr(lq), B, float(w), int(bool(adain)), _lib.ptr(io),
+                                                       io.numel(), _lib.ptr(ws), ws.numel(), _stream_ptr(dev)),
+                       'cfb_codeformer_forward_host')
+        return out, logits, lq

@@ -1,0 +1,49 @@
+"""Build libcfb200.so in-tree with nvcc for sm_100a (SASS only: tcgen05 needs the arch-specific target)."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+LIB = os.path.join(HERE, 'libcfb200.so')
+SOURCES = ['simt_kernels.cu', 'conv_tc.cu', 'runtime.cu']
+NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
+         '-Xcompiler', '-fPIC', '--use_fast_math=false' if False else '-Xptxas', '-v' if os.environ.get('CFB_PTXAS_V') else '-O3']
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, '..', 'include', 'cfb200.h'), __file__]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    objs = []
+    procs = []
+    for s in SOURCES:
+        o = os.path.join(CSRC, s.replace('.cu', '.o'))
+        cmd = [NVCC] + FLAGS + ['-c', os.path.join(CSRC, s), '-o', o]
+        if verbose:
+            print(' '.join(cmd), flush=True)
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(o)
+    fail = False
+    for s, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0 or verbose or os.environ.get('CFB_PTXAS_V'):
+            print(out)
+        fail = fail or p.returncode != 0
+    if fail:
+        raise RuntimeError('nvcc failed')
+    cmd = [NVCC, '-shared', '-o', LIB] + objs + ['-lcudart']
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose=True))

@@ -1,0 +1,14 @@
+// tcgen05 (5th-gen tensor core) implicit-GEMM convolution engine: interface.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "kernels.cuh"
+
+namespace cfb {
+// OIHW fp32 -> [taps][Cout][Cin] fp16 hi / lo with hi = fp16(w), lo = fp16(w - hi)
+int tc_split_weights(const float* oihw, __half* hi, __half* lo, int Cout, int Cin, int k, cudaStream_t st);
+bool tc_supported(const ConvArgs& a);
+size_t tc_scratch_bytes(const ConvArgs& a);   // operand (hi/lo fp16 activation planes) staging
+int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st);
+}  // namespace cfb

@@ -1,0 +1,113 @@
+// Internal launcher interface between the host runtime (runtime.cu / capi.cu) and the kernels.
+// Every launcher enqueues on `st` and returns the launch status; none synchronises.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+namespace cfb {
+
+// ---- error plumbing --------------------------------------------------------------------------
+void set_error(const std::string& msg);
+#define CFB_CUDA(expr)                                                                            \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      ::cfb::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " @" + __FILE__ + ":" + \
+                       std::to_string(__LINE__));                                                 \
+      return 1;                                                                                   \
+    }                                                                                             \
+  } while (0)
+#define CFB_LAUNCH_CHECK()                                                                        \
+  do {                                                                                            \
+    cudaError_t _e = cudaGetLastError();                                                          \
+    if (_e != cudaSuccess) {                                                                      \
+      ::cfb::set_error(std::string("kernel launch failed: ") + cudaGetErrorString(_e) + " @" +    \
+                       __FILE__ + ":" + std::to_string(__LINE__));                                \
+      return 1;                                                                                   \
+    }                                                                                             \
+    ::cfb::count_launch();                                                                        \
+  } while (0)
+#define CFB_CHECK(x)                                                                              \
+  do {                                                                                            \
+    if ((x) != 0) return 1;                                                                       \
+  } while (0)
+#define CFB_REQUIRE(cond, msg)                                                                    \
+  do {                                                                                            \
+    if (!(cond)) {                                                                                \
+      ::cfb::set_error(std::string(msg) + " [" #cond "] @" + __FILE__ + ":" + std::to_string(__LINE__)); \
+      return 1;                                                                                   \
+    }                                                                                             \
+  } while (0)
+
+void count_launch();
+int64_t launch_count();
+void reset_launch_count();
+
+enum InAct { IN_NONE = 0, IN_SILU = 1 };
+enum OutAct { OUT_NONE = 0, OUT_LRELU = 1, OUT_GELU = 2 };
+enum ConvMode { CONV_SAME = 0, CONV_DOWN = 1, CONV_UP = 2 };
+
+// Convolution / linear layer as an implicit GEMM over NHWC fp32 activations.
+//   M = N*Ho*Wo output pixels (tokens), N = Cout, K = taps*Cin.
+struct ConvArgs {
+  const float* in = nullptr;        // [N,H,W,Cin]  (H,W are the stored dims; CONV_UP reads (y>>1,x>>1))
+  int N = 0, H = 0, W = 0, Cin = 0;
+  int Ho = 0, Wo = 0, Cout = 0;
+  int ksize = 3;                    // 1 | 3
+  int mode = CONV_SAME;
+  const float* wgt_f32 = nullptr;   // [taps][Cin][Cout] fp32 (CUDA-core engine)
+  const void* wgt_hi = nullptr;     // [taps][Cout][Cin] fp16 hi   (tensor-core engine)
+  const void* wgt_lo = nullptr;     // [taps][Cout][Cin] fp16 lo
+  const float* bias = nullptr;      // [Cout] | null
+  const float* in_scale = nullptr;  // [N,Cin] fused per-sample affine (GroupNorm folded) | null
+  const float* in_shift = nullptr;
+  int in_act = IN_NONE;
+  const float* residual = nullptr;  // [N,Ho,Wo,Cout] | null
+  int out_act = OUT_NONE;
+  // SFT epilogue (codeformer_arch.py:155-156): out = dec + w*(dec*scale + conv)
+  const float* sft_dec = nullptr;
+  const float* sft_scale = nullptr;
+  float sft_w = 0.f;
+  float* out = nullptr;             // [N,Ho,Wo,Cout]
+};
+
+int conv_f32(const ConvArgs& a, cudaStream_t st);                       // CUDA-core fp32 implicit GEMM
+// first conv: x NCHW [N,3,H,W] -> NHWC [N,H,W,Cout], 3x3 p1; weight [27][Cout] (tap-major, then cin)
+int conv_first(const float* x_nchw, const float* wgt, const float* bias, float* out, int N, int H, int W, int Cout,
+               cudaStream_t st);
+// last conv: NHWC [N,H,W,Cin] (+ fused affine) -> NCHW [N,3,H,W], 3x3 p1; weight [9][Cin][3]
+int conv_last(const float* in, const float* in_scale, const float* in_shift, const float* wgt, const float* bias,
+              float* out_nchw, int N, int H, int W, int Cin, cudaStream_t st);
+
+// weight re-layout: OIHW -> [taps][Cin][Cout]
+int relayout_oihw_to_tck(const float* oihw, float* out, int Cout, int Cin, int k, cudaStream_t st);
+
+// GroupNorm statistics -> per-(n,c) scale/shift.  partials: workspace of gn_partial_count() doubles
+size_t gn_workspace_bytes(int N, int HW, int C);
+int gn_coef(const float* x, const float* gamma, const float* beta, float* scale, float* shift, int N, int HW, int C,
+            int groups, float eps, void* ws, cudaStream_t st);
+int affine_act(const float* x, const float* scale, const float* shift, float* y, int N, int HW, int C, int act,
+               cudaStream_t st);
+
+int attention(const float* q, const float* k, const float* v, float* out, int B, int S, int heads, int d, int q_pitch,
+              int k_pitch, int v_pitch, int o_pitch, float scale, cudaStream_t st);
+int layer_norm(const float* x, const float* gamma, const float* beta, float* y, float* y2, const float* pos,
+               int pos_rows, int rows, int C, cudaStream_t st);
+int add_pos(const float* x, const float* pos, float* y, int rows, int pos_rows, int C, cudaStream_t st);
+// logits [T,K] -> idx [T] (first max), quant [T,D] = E[idx]
+int argmax_gather(const float* logits, const float* codebook, int64_t* idx, float* quant, int T, int K, int D,
+                  cudaStream_t st);
+int gather_rows(const int64_t* idx, const float* codebook, float* out, int T, int K, int D, cudaStream_t st);
+int adain_nhwc(const float* content, const float* style, float* out, int B, int HW, int C, cudaStream_t st);
+int nchw_to_nhwc(const float* in, float* out, int N, int C, int HW, cudaStream_t st);
+int nhwc_to_nchw(const float* in, float* out, int N, int C, int HW, cudaStream_t st);
+int concat_channels(const float* a, const float* b, float* out, int64_t pixels, int Ca, int Cb, cudaStream_t st);
+
+// VectorQuantizer.forward core on token-major z [T,D] (NHWC); writes idx, zq_st = z + (E[idx]-z) [T,D],
+// stats = {loss, perplexity, mean_distance, 0}; onehot optional [T,K]
+size_t vq_workspace_bytes(int T, int D, int K);
+int vq_nearest(const float* z, const float* codebook, int T, int D, int K, float beta, int64_t* idx, float* zq,
+               float* stats, float* onehot, void* ws, cudaStream_t st);
+
+}  // namespace cfb

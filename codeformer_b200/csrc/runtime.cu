@@ -1,0 +1,1000 @@
+// Host runtime of libcfb200: the network plan (block lists of the reference constructors), weight
+// preparation, the stream-ordered workspace arena, and the forward passes that enqueue the kernels.
+//
+// Mirrors, block for block:
+//   Encoder / Generator block lists      /root/reference/basicsr/archs/vqgan_arch.py:229-323
+//   VQAutoEncoder.forward                vqgan_arch.py:385-389
+//   CodeFormer.forward                   /root/reference/basicsr/archs/codeformer_arch.py:223-280
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <array>
+#include <atomic>
+#include <cmath>
+#include <map>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/cfb200.h"
+#include "kernels.cuh"
+#include "conv_tc.cuh"
+
+namespace cfb {
+
+// ---- error / counters --------------------------------------------------------------------------
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+const std::string& last_error() { return g_err; }
+static std::atomic<int64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+int64_t launch_count() { return g_launches.load(); }
+void reset_launch_count() { g_launches.store(0); }
+
+// ---- stream-ordered arena over the caller's workspace ---------------------------------------------
+// All work of one forward is enqueued on one stream, so a block can be handed out again as soon as the
+// host has *enqueued* its last reader.  First-fit with coalescing; `dry` mode only tracks the high-water mark.
+class Arena {
+ public:
+  void reset(void* base, size_t cap, bool dry) {
+    base_ = (char*)base; cap_ = cap; dry_ = dry; high_ = 0; free_.clear(); used_.clear();
+    if (dry) { base_ = (char*)(uintptr_t)0x10000; cap_ = (size_t)1 << 46; }
+    free_[0] = cap_;
+  }
+  void* alloc(size_t bytes) {
+    bytes = (bytes + 1023) / 1024 * 1024;   // 1 KiB granularity keeps every tensor TMA/float4 aligned
+    if (bytes == 0) bytes = 1024;
+    for (auto it = free_.begin(); it != free_.end(); ++it) {
+      if (it->second >= bytes) {
+        const size_t off = it->first, sz = it->second;
+        free_.erase(it);
+        if (sz > bytes) free_[off + bytes] = sz - bytes;
+        used_[off] = bytes;
+        if (off + bytes > high_) high_ = off + bytes;
+        return base_ + off;
+      }
+    }
+    return nullptr;
+  }
+  void release(void* p) {
+    if (!p) return;
+    const size_t off = (size_t)((char*)p - base_);
+    auto u = used_.find(off);
+    if (u == used_.end()) return;
+    size_t sz = u->second;
+    used_.erase(u);
+    auto nxt = free_.lower_bound(off);
+    if (nxt != free_.end() && off + sz == nxt->first) { sz += nxt->second; nxt = free_.erase(nxt); }
+    if (nxt != free_.begin()) {
+      auto prv = std::prev(nxt);
+      if (prv->first + prv->second == off) { prv->second += sz; return; }
+    }
+    free_[off] = sz;
+  }
+  size_t high() const { return high_; }
+  bool dry() const { return dry_; }
+
+ private:
+  char* base_ = nullptr;
+  size_t cap_ = 0, high_ = 0;
+  bool dry_ = false;
+  std::map<size_t, size_t> free_, used_;
+};
+
+struct Tensor {
+  float* p = nullptr;
+  int N = 0, H = 0, W = 0, C = 0;
+  bool owned = true;  // false: caller memory or kept-alive tap
+  int64_t numel() const { return (int64_t)N * H * W * C; }
+};
+
+struct ConvW {
+  std::string name;
+  int cin = 0, cout = 0, k = 0;
+  bool has_bias = true;
+  const float* src_w = nullptr;  // reference-layout source (row offset into a larger OIHW tensor allowed)
+  const float* src_b = nullptr;
+  float* w_f32 = nullptr;        // [taps][cin][cout]
+  __half* w_hi = nullptr;        // [taps][cout][cin]
+  __half* w_lo = nullptr;
+  float* bias = nullptr;
+};
+struct NormW { std::string name; int c = 0; const float* gamma = nullptr; const float* beta = nullptr; };
+struct ResW { NormW n1, n2; ConvW c1, c2, co; bool has_out = false; };
+struct AttnW { NormW n; ConvW qkv, proj; };
+struct FuseW { ResW enc; ConvW s0, s2, h0, h2; };
+struct LayerW { NormW n1, n2; ConvW qk, v, o, l1, l2; };
+struct Block { int kind; int cin, cout, res; ConvW conv; ResW res_w; AttnW attn; NormW norm; };
+enum { B_CONV = 0, B_RES, B_ATTN, B_DOWN, B_UP, B_NORM };
+
+}  // namespace cfb
+
+using namespace cfb;
+
+struct cfb_net {
+  cfb_config cfg;
+  std::mutex mu;
+  std::unordered_map<std::string, std::pair<const float*, int64_t>> raw;
+  std::vector<Block> enc, gen;
+  std::map<int, FuseW> fuse;          // keyed by feature size
+  std::vector<LayerW> layers;
+  ConvW feat_emb, idx_lin;
+  NormW idx_norm;
+  const float* position_emb = nullptr;
+  const float* codebook = nullptr;    // points into slab copy
+  float* slab = nullptr;
+  size_t slab_bytes = 0;
+  bool prepared = false;
+  int64_t last_launches = 0;
+  int sm_count = 148;
+  bool tc_ok = false;                 // device is sm_100 => tcgen05 engine usable
+  Arena arena;
+  cudaStream_t st = nullptr;
+  // small owned copies of norm params etc. live in the slab too
+  std::vector<std::pair<const float**, std::pair<std::string, int64_t>>> vec_params;  // (dst, (name, numel))
+  std::vector<ConvW*> convs;
+};
+
+namespace cfb {
+
+// ---- plan construction (mirrors the reference constructors) -----------------------------------------
+static void mk_conv(cfb_net* n, ConvW& c, const std::string& name, int cin, int cout, int k, bool bias = true) {
+  c.name = name; c.cin = cin; c.cout = cout; c.k = k; c.has_bias = bias;
+  n->convs.push_back(&c);
+}
+static void mk_norm(cfb_net* n, NormW& w, const std::string& name, int c) {
+  w.name = name; w.c = c;
+  n->vec_params.push_back({&w.gamma, {name + ".weight", c}});
+  n->vec_params.push_back({&w.beta, {name + ".bias", c}});
+}
+static void mk_res(cfb_net* n, ResW& r, const std::string& p, int cin, int cout) {
+  mk_norm(n, r.n1, p + ".norm1", cin);
+  mk_conv(n, r.c1, p + ".conv1", cin, cout, 3);
+  mk_norm(n, r.n2, p + ".norm2", cout);
+  mk_conv(n, r.c2, p + ".conv2", cout, cout, 3);
+  r.has_out = cin != cout;
+  if (r.has_out) mk_conv(n, r.co, p + ".conv_out", cin, cout, 1);
+}
+static bool in_list(const int32_t* l, int n, int v) {
+  for (int i = 0; i < n; ++i) if (l[i] == v) return true;
+  return false;
+}
+
+static void build_blocks(cfb_net* n, std::vector<Block>& blocks, const std::string& prefix,
+                         const std::vector<std::array<int, 4>>& plan) {
+  blocks.resize(plan.size());   // resize first: ConvW addresses are registered in n->convs
+  for (size_t i = 0; i < plan.size(); ++i) {
+    Block& b = blocks[i];
+    b.kind = plan[i][0]; b.cin = plan[i][1]; b.cout = plan[i][2]; b.res = plan[i][3];
+    const std::string p = prefix + ".blocks." + std::to_string(i);
+    switch (b.kind) {
+      case B_CONV: mk_conv(n, b.conv, p, b.cin, b.cout, 3); break;
+      case B_RES: mk_res(n, b.res_w, p, b.cin, b.cout); break;
+      case B_ATTN:
+        mk_norm(n, b.attn.n, p + ".norm", b.cin);
+        mk_conv(n, b.attn.qkv, p + ".qkv", b.cin, 3 * b.cin, 1);   // q,k,v fused along Cout (special-cased in prepare)
+        mk_conv(n, b.attn.proj, p + ".proj_out", b.cin, b.cin, 1);
+        break;
+      case B_DOWN: case B_UP: mk_conv(n, b.conv, p + ".conv", b.cin, b.cout, 3); break;
+      case B_NORM: mk_norm(n, b.norm, p, b.cin); break;
+    }
+  }
+}
+
+static int build_plan(cfb_net* n) {
+  const cfb_config& c = n->cfg;
+  CFB_REQUIRE(c.n_ch_mult >= 1 && c.n_ch_mult <= 8, "config: bad ch_mult length");
+  CFB_REQUIRE(c.nf == 64, "config: only nf=64 is built (first/last conv kernels)");
+  // Encoder.__init__  vqgan_arch.py:241-267
+  std::vector<std::array<int, 4>> ep, gp;
+  int curr = c.img_size;
+  ep.push_back({B_CONV, 3, c.nf, curr});
+  int cin = c.nf;
+  for (int i = 0; i < c.n_ch_mult; ++i) {
+    cin = c.nf * (i == 0 ? 1 : c.ch_mult[i - 1]);
+    const int cout = c.nf * c.ch_mult[i];
+    for (int r = 0; r < c.res_blocks; ++r) {
+      ep.push_back({B_RES, cin, cout, curr});
+      cin = cout;
+      if (in_list(c.attn_res, c.n_attn_res, curr)) ep.push_back({B_ATTN, cin, cin, curr});
+    }
+    if (i != c.n_ch_mult - 1) { curr /= 2; ep.push_back({B_DOWN, cin, cin, curr}); }
+  }
+  ep.push_back({B_RES, cin, cin, curr});
+  ep.push_back({B_ATTN, cin, cin, curr});
+  ep.push_back({B_RES, cin, cin, curr});
+  ep.push_back({B_NORM, cin, cin, curr});
+  ep.push_back({B_CONV, cin, c.emb_dim, curr});
+  // Generator.__init__  vqgan_arch.py:287-316
+  cin = c.nf * c.ch_mult[c.n_ch_mult - 1];
+  curr = c.img_size >> (c.n_ch_mult - 1);
+  gp.push_back({B_CONV, c.emb_dim, cin, curr});
+  gp.push_back({B_RES, cin, cin, curr});
+  gp.push_back({B_ATTN, cin, cin, curr});
+  gp.push_back({B_RES, cin, cin, curr});
+  for (int i = c.n_ch_mult - 1; i >= 0; --i) {
+    const int cout = c.nf * c.ch_mult[i];
+    for (int r = 0; r < c.res_blocks; ++r) {
+      gp.push_back({B_RES, cin, cout, curr});
+      cin = cout;
+      if (in_list(c.attn_res, c.n_attn_res, curr)) gp.push_back({B_ATTN, cin, cin, curr});
+    }
+    if (i != 0) { curr *= 2; gp.push_back({B_UP, cin, cin, curr}); }
+  }
+  gp.push_back({B_NORM, cin, cin, curr});
+  gp.push_back({B_CONV, cin, 3, curr});
+  build_blocks(n, n->enc, "encoder", ep);
+  build_blocks(n, n->gen, "generator", gp);
+  if (c.kind == 1) {
+    CFB_REQUIRE(c.img_size == 512 && c.emb_dim == 256, "config: CodeFormer is defined for 512x512 / emb 256");
+    CFB_REQUIRE(c.dim_embd == 512 && c.dim_embd % c.n_head == 0 && c.dim_embd / c.n_head == 64,
+                "config: only dim_embd=512 with 64-wide heads is built");
+    mk_conv(n, n->feat_emb, "feat_emb", c.emb_dim, c.dim_embd, 1);
+    n->layers.resize(c.n_layers);
+    for (int l = 0; l < c.n_layers; ++l) {
+      LayerW& L = n->layers[l];
+      const std::string p = "ft_layers." + std::to_string(l);
+      const int E = c.dim_embd;
+      mk_conv(n, L.qk, p + ".self_attn.in_proj#qk", E, 2 * E, 1);
+      mk_conv(n, L.v, p + ".self_attn.in_proj#v", E, E, 1);
+      mk_conv(n, L.o, p + ".self_attn.out_proj", E, E, 1);
+      mk_conv(n, L.l1, p + ".linear1", E, 2 * E, 1);
+      mk_conv(n, L.l2, p + ".linear2", 2 * E, E, 1);
+      mk_norm(n, L.n1, p + ".norm1", E);
+      mk_norm(n, L.n2, p + ".norm2", E);
+    }
+    mk_norm(n, n->idx_norm, "idx_pred_layer.0", c.dim_embd);
+    mk_conv(n, n->idx_lin, "idx_pred_layer.1", c.dim_embd, c.codebook_size, 1, false);
+    static const int chan_of[6][2] = {{16, 512}, {32, 256}, {64, 256}, {128, 128}, {256, 128}, {512, 64}};
+    for (int i = 0; i < c.n_connect; ++i) {
+      int ch = 0;
+      for (auto& e : chan_of) if (e[0] == c.connect[i]) ch = e[1];
+      CFB_REQUIRE(ch != 0, "config: connect_list entries must be one of 16..512");
+      FuseW& f = n->fuse[c.connect[i]];
+      const std::string p = "fuse_convs_dict." + std::to_string(c.connect[i]);
+      mk_res(n, f.enc, p + ".encode_enc", 2 * ch, ch);
+      mk_conv(n, f.s0, p + ".scale.0", ch, ch, 3);
+      mk_conv(n, f.s2, p + ".scale.2", ch, ch, 3);
+      mk_conv(n, f.h0, p + ".shift.0", ch, ch, 3);
+      mk_conv(n, f.h2, p + ".shift.2", ch, ch, 3);
+    }
+  }
+  return 0;
+}
+
+// ---- weight preparation --------------------------------------------------------------------------------
+static const float* find_param(cfb_net* n, const std::string& name, int64_t numel) {
+  auto it = n->raw.find(name);
+  if (it == n->raw.end()) { set_error("missing parameter '" + name + "'"); return nullptr; }
+  if (it->second.second != numel) {
+    set_error("parameter '" + name + "' has " + std::to_string(it->second.second) + " elements, expected " +
+              std::to_string(numel));
+    return nullptr;
+  }
+  return it->second.first;
+}
+
+static int resolve_conv_sources(cfb_net* n, ConvW& c, float* qkv_scratch_w, float* qkv_scratch_b, cudaStream_t st) {
+  const int64_t wn = (int64_t)c.cout * c.cin * c.k * c.k;
+  const size_t hash = c.name.find('#');
+  if (c.name.size() > 4 && c.name.compare(c.name.size() - 4, 4, ".qkv") == 0) {
+    // AttnBlock q,k,v (vqgan_arch.py:173-193) stacked along Cout so one GEMM feeds the attention core
+    const std::string p = c.name.substr(0, c.name.size() - 4);
+    const int C = c.cin;
+    const char* nm[3] = {".q", ".k", ".v"};
+    for (int i = 0; i < 3; ++i) {
+      const float* w = find_param(n, p + nm[i] + ".weight", (int64_t)C * C);
+      const float* b = find_param(n, p + nm[i] + ".bias", C);
+      if (!w || !b) return 1;
+      CFB_CUDA(cudaMemcpyAsync(qkv_scratch_w + (int64_t)i * C * C, w, (size_t)C * C * 4, cudaMemcpyDeviceToDevice, st));
+      CFB_CUDA(cudaMemcpyAsync(qkv_scratch_b + (int64_t)i * C, b, (size_t)C * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    c.src_w = qkv_scratch_w; c.src_b = qkv_scratch_b;
+    return 0;
+  }
+  if (hash != std::string::npos) {
+    // nn.MultiheadAttention in_proj_weight [3E,E] rows = [Wq;Wk;Wv]  (codeformer_arch.py:102)
+    const std::string base = c.name.substr(0, hash);
+    const std::string part = c.name.substr(hash + 1);
+    const int E = c.cin;
+    const float* w = find_param(n, base + "_weight", (int64_t)3 * E * E);
+    const float* b = find_param(n, base + "_bias", (int64_t)3 * E);
+    if (!w || !b) return 1;
+    const int row0 = part == "qk" ? 0 : 2 * E;
+    c.src_w = w + (int64_t)row0 * E; c.src_b = b + row0;
+    return 0;
+  }
+  c.src_w = find_param(n, c.name + ".weight", wn);
+  if (!c.src_w) return 1;
+  if (c.has_bias) { c.src_b = find_param(n, c.name + ".bias", c.cout); if (!c.src_b) return 1; }
+  return 0;
+}
+
+static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+static int prepare(cfb_net* n, cudaStream_t st) {
+  // slab size
+  size_t total = 0;
+  for (ConvW* c : n->convs) {
+    const size_t wn = (size_t)c->cout * c->cin * c->k * c->k;
+    total += align256(wn * 4) + 2 * align256(wn * 2) + align256((size_t)c->cout * 4);
+  }
+  for (auto& v : n->vec_params) total += align256((size_t)v.second.second * 4);
+  total += align256((size_t)n->cfg.codebook_size * n->cfg.emb_dim * 4);
+  if (n->cfg.kind == 1) total += align256((size_t)n->cfg.latent_size * n->cfg.dim_embd * 4);
+  const size_t scratch = align256((size_t)3 * 512 * 512 * 4) + align256(3 * 512 * 4);
+  total += scratch;
+  if (n->slab_bytes < total) {
+    if (n->slab) cudaFree(n->slab);
+    n->slab = nullptr; n->slab_bytes = 0;
+    CFB_CUDA(cudaMalloc((void**)&n->slab, total));
+    n->slab_bytes = total;
+  }
+  char* p = (char*)n->slab;
+  auto take = [&](size_t bytes) { char* r = p; p += align256(bytes); return r; };
+  float* qkv_w = (float*)take((size_t)3 * 512 * 512 * 4);
+  float* qkv_b = (float*)take(3 * 512 * 4);
+  for (ConvW* c : n->convs) {
+    if (c->name.size() > 4 && c->name.compare(c->name.size() - 4, 4, ".qkv") == 0)
+      CFB_REQUIRE(c->cin <= 512, "AttnBlock wider than 512 channels is not built");
+    CFB_CHECK(resolve_conv_sources(n, *c, qkv_w, qkv_b, st));
+    const size_t wn = (size_t)c->cout * c->cin * c->k * c->k;
+    c->w_f32 = (float*)take(wn * 4);
+    c->w_hi = (__half*)take(wn * 2);
+    c->w_lo = (__half*)take(wn * 2);
+    c->bias = (float*)take((size_t)c->cout * 4);
+    CFB_CHECK(relayout_oihw_to_tck(c->src_w, c->w_f32, c->cout, c->cin, c->k, st));
+    CFB_CHECK(tc_split_weights(c->src_w, c->w_hi, c->w_lo, c->cout, c->cin, c->k, st));
+    if (c->has_bias) CFB_CUDA(cudaMemcpyAsync(c->bias, c->src_b, (size_t)c->cout * 4, cudaMemcpyDeviceToDevice, st));
+    else CFB_CUDA(cudaMemsetAsync(c->bias, 0, (size_t)c->cout * 4, st));
+  }
+  for (auto& v : n->vec_params) {
+    const float* src = find_param(n, v.second.first, v.second.second);
+    if (!src) return 1;
+    float* dst = (float*)take((size_t)v.second.second * 4);
+    CFB_CUDA(cudaMemcpyAsync(dst, src, (size_t)v.second.second * 4, cudaMemcpyDeviceToDevice, st));
+    *v.first = dst;
+  }
+  {
+    const int64_t ne = (int64_t)n->cfg.codebook_size * n->cfg.emb_dim;
+    const float* src = find_param(n, "quantize.embedding.weight", ne);
+    if (!src) return 1;
+    float* dst = (float*)take((size_t)ne * 4);
+    CFB_CUDA(cudaMemcpyAsync(dst, src, (size_t)ne * 4, cudaMemcpyDeviceToDevice, st));
+    n->codebook = dst;
+  }
+  if (n->cfg.kind == 1) {
+    const int64_t ne = (int64_t)n->cfg.latent_size * n->cfg.dim_embd;
+    const float* src = find_param(n, "position_emb", ne);
+    if (!src) return 1;
+    float* dst = (float*)take((size_t)ne * 4);
+    CFB_CUDA(cudaMemcpyAsync(dst, src, (size_t)ne * 4, cudaMemcpyDeviceToDevice, st));
+    n->position_emb = dst;
+  }
+  // the qkv scratch is read by kernels enqueued above: the sources must stay valid until they ran
+  CFB_CUDA(cudaStreamSynchronize(st));
+  n->prepared = true;
+  return 0;
+}
+
+// ---- forward building blocks ----------------------------------------------------------------------------
+struct Fwd {
+  cfb_net* n;
+  cudaStream_t st;
+  Arena& ar;
+  bool dry;
+  int engine;   // 0 auto, 1 f32, 2 tc
+
+  int alloc(Tensor& t, int N, int H, int W, int C) {
+    t.N = N; t.H = H; t.W = W; t.C = C; t.owned = true;
+    t.p = (float*)ar.alloc((size_t)t.numel() * 4);
+    CFB_REQUIRE(t.p != nullptr, "workspace too small (use cfb_workspace_bytes)");
+    return 0;
+  }
+  int alloc_raw(void** p, size_t bytes) {
+    *p = ar.alloc(bytes);
+    CFB_REQUIRE(*p != nullptr, "workspace too small (use cfb_workspace_bytes)");
+    return 0;
+  }
+  void release(Tensor& t) { if (t.owned && t.p) ar.release(t.p); t.p = nullptr; }
+  void release_raw(void* p) { ar.release(p); }
+
+  struct ConvOpt {
+    int mode = CONV_SAME;
+    const float* in_scale = nullptr; const float* in_shift = nullptr; int in_act = IN_NONE;
+    const float* residual = nullptr; int out_act = OUT_NONE;
+    const float* sft_dec = nullptr; const float* sft_scale = nullptr; float sft_w = 0.f;
+    float* out_ptr = nullptr;   // write into caller memory instead of the arena
+  };
+
+  int conv(const ConvW& w, const Tensor& in, Tensor& out, const ConvOpt& o) {
+    CFB_REQUIRE(in.C == w.cin, "conv: channel mismatch for " + w.name);
+    int Ho = in.H, Wo = in.W;
+    if (o.mode == CONV_DOWN) { Ho = in.H / 2; Wo = in.W / 2; }
+    if (o.mode == CONV_UP) { Ho = in.H * 2; Wo = in.W * 2; }
+    if (o.out_ptr) { out.p = o.out_ptr; out.N = in.N; out.H = Ho; out.W = Wo; out.C = w.cout; out.owned = false; }
+    else CFB_CHECK(alloc(out, in.N, Ho, Wo, w.cout));
+    ConvArgs a;
+    a.in = in.p; a.N = in.N; a.H = in.H; a.W = in.W; a.Cin = in.C; a.Ho = Ho; a.Wo = Wo; a.Cout = w.cout;
+    a.ksize = w.k; a.mode = o.mode; a.wgt_f32 = w.w_f32; a.wgt_hi = w.w_hi; a.wgt_lo = w.w_lo; a.bias = w.bias;
+    a.in_scale = o.in_scale; a.in_shift = o.in_shift; a.in_act = o.in_act; a.residual = o.residual;
+    a.out_act = o.out_act; a.sft_dec = o.sft_dec; a.sft_scale = o.sft_scale; a.sft_w = o.sft_w; a.out = out.p;
+    bool use_tc = engine == 2 || (engine == 0 && n->tc_ok && tc_supported(a));
+    if (use_tc) {
+      CFB_REQUIRE(tc_supported(a), "conv: shape not supported by the tcgen05 engine: " + w.name);
+      const size_t sb = tc_scratch_bytes(a);
+      void* scratch = nullptr;
+      CFB_CHECK(alloc_raw(&scratch, sb));
+      if (!dry) CFB_CHECK(conv_tc(a, scratch, n->sm_count, st));
+      release_raw(scratch);
+    } else {
+      if (!dry) CFB_CHECK(conv_f32(a, st));
+    }
+    return 0;
+  }
+
+  // GroupNorm(32, C, 1e-6) statistics -> scale/shift [N,C]
+  int gn(const NormW& w, const Tensor& x, float** scale, float** shift) {
+    CFB_REQUIRE(x.C == w.c, "norm: channel mismatch for " + w.name);
+    CFB_CHECK(alloc_raw((void**)scale, (size_t)x.N * x.C * 4));
+    CFB_CHECK(alloc_raw((void**)shift, (size_t)x.N * x.C * 4));
+    void* ws = nullptr;
+    CFB_CHECK(alloc_raw(&ws, gn_workspace_bytes(x.N, x.H * x.W, x.C)));
+    if (!dry) CFB_CHECK(gn_coef(x.p, w.gamma, w.beta, *scale, *shift, x.N, x.H * x.W, x.C, 32, 1e-6f, ws, st));
+    release_raw(ws);
+    return 0;
+  }
+
+  // ResBlock.forward  vqgan_arch.py:153-164
+  int resblock(const ResW& r, const Tensor& x, Tensor& y) {
+    float *s1, *h1, *s2, *h2;
+    CFB_CHECK(gn(r.n1, x, &s1, &h1));
+    Tensor h;
+    ConvOpt o1; o1.in_scale = s1; o1.in_shift = h1; o1.in_act = IN_SILU;
+    CFB_CHECK(conv(r.c1, x, h, o1));
+    release_raw(s1); release_raw(h1);
+    CFB_CHECK(gn(r.n2, h, &s2, &h2));
+    Tensor skip = x; skip.owned = false;
+    if (r.has_out) { ConvOpt oo; CFB_CHECK(conv(r.co, x, skip, oo)); }
+    ConvOpt o2; o2.in_scale = s2; o2.in_shift = h2; o2.in_act = IN_SILU; o2.residual = skip.p;
+    CFB_CHECK(conv(r.c2, h, y, o2));
+    release_raw(s2); release_raw(h2);
+    release(h);
+    if (r.has_out) release(skip);
+    return 0;
+  }
+
+  // AttnBlock.forward  vqgan_arch.py:202-226
+  int attnblock(const AttnW& w, const Tensor& x, Tensor& y) {
+    CFB_REQUIRE(x.H * x.W == 256, "AttnBlock: built for the 16x16 latent");
+    float *s, *h;
+    CFB_CHECK(gn(w.n, x, &s, &h));
+    Tensor qkv;
+    ConvOpt o; o.in_scale = s; o.in_shift = h;
+    CFB_CHECK(conv(w.qkv, x, qkv, o));
+    release_raw(s); release_raw(h);
+    Tensor a;
+    CFB_CHECK(alloc(a, x.N, x.H, x.W, x.C));
+    const int C = x.C;
+    if (!dry)
+      CFB_CHECK(attention(qkv.p, qkv.p + C, qkv.p + 2 * C, a.p, x.N, 256, 1, C, 3 * C, 3 * C, 3 * C, C,
+                          1.0f / sqrtf((float)C), st));
+    release(qkv);
+    ConvOpt op; op.residual = x.p;
+    CFB_CHECK(conv(w.proj, a, y, op));
+    release(a);
+    return 0;
+  }
+
+  // Fuse_sft_block.forward  codeformer_arch.py:151-157
+  int fuse(const FuseW& f, const Tensor& enc_feat, const Tensor& dec, float wgt, Tensor& y) {
+    Tensor cat;
+    CFB_CHECK(alloc(cat, dec.N, dec.H, dec.W, enc_feat.C + dec.C));
+    if (!dry) CFB_CHECK(concat_channels(enc_feat.p, dec.p, cat.p, (int64_t)dec.N * dec.H * dec.W, enc_feat.C, dec.C, st));
+    Tensor e;
+    CFB_CHECK(resblock(f.enc, cat, e));
+    release(cat);
+    Tensor s0, sc, h0;
+    ConvOpt ol; ol.out_act = OUT_LRELU;
+    CFB_CHECK(conv(f.s0, e, s0, ol));
+    ConvOpt on;
+    CFB_CHECK(conv(f.s2, s0, sc, on));
+    release(s0);
+    CFB_CHECK(conv(f.h0, e, h0, ol));
+    release(e);
+    ConvOpt of; of.sft_dec = dec.p; of.sft_scale = sc.p; of.sft_w = wgt;
+    CFB_CHECK(conv(f.h2, h0, y, of));
+    release(h0); release(sc);
+    return 0;
+  }
+
+  // Encoder.forward (+ the taps of codeformer_arch.py:226-230).  x_nchw is the caller's image.
+  int encoder(const float* x_nchw, int B, Tensor& z, std::map<int, Tensor>* taps, const std::vector<int>& tap_blocks) {
+    const cfb_config& c = n->cfg;
+    Tensor x;
+    CFB_CHECK(alloc(x, B, c.img_size, c.img_size, c.nf));
+    if (!dry) CFB_CHECK(conv_first(x_nchw, n->enc[0].conv.w_f32, n->enc[0].conv.bias, x.p, B, c.img_size, c.img_size, c.nf, st));
+    float *ps = nullptr, *ph = nullptr;   // pending GroupNorm of a 'norm' block
+    for (size_t i = 1; i < n->enc.size(); ++i) {
+      const Block& b = n->enc[i];
+      Tensor y;
+      switch (b.kind) {
+        case B_RES: CFB_CHECK(resblock(b.res_w, x, y)); break;
+        case B_ATTN: CFB_CHECK(attnblock(b.attn, x, y)); break;
+        case B_DOWN: { ConvOpt o; o.mode = CONV_DOWN; CFB_CHECK(conv(b.conv, x, y, o)); break; }
+        case B_NORM: CFB_CHECK(gn(b.norm, x, &ps, &ph)); continue;   // consumed by the next conv
+        case B_CONV: {
+          ConvOpt o; o.in_scale = ps; o.in_shift = ph;
+          CFB_CHECK(conv(b.conv, x, y, o));
+          if (ps) { release_raw(ps); release_raw(ph); ps = ph = nullptr; }
+          break;
+        }
+        default: CFB_REQUIRE(false, "encoder: unexpected block kind");
+      }
+      release(x);
+      x = y;
+      for (int tb : tap_blocks)
+        if ((int)i == tb && taps) { x.owned = false; (*taps)[x.W] = x; (*taps)[x.W].owned = true; }
+    }
+    z = x;
+    return 0;
+  }
+
+  // Generator.forward with the SFT fusion of codeformer_arch.py:272-277; writes NCHW into out_nchw
+  int generator(Tensor x, float* out_nchw, std::map<int, Tensor>* taps, const std::vector<int>& fuse_blocks, float w) {
+    float *ps = nullptr, *ph = nullptr;
+    for (size_t i = 0; i < n->gen.size(); ++i) {
+      const Block& b = n->gen[i];
+      Tensor y;
+      switch (b.kind) {
+        case B_RES: CFB_CHECK(resblock(b.res_w, x, y)); break;
+        case B_ATTN: CFB_CHECK(attnblock(b.attn, x, y)); break;
+        case B_UP: { ConvOpt o; o.mode = CONV_UP; CFB_CHECK(conv(b.conv, x, y, o)); break; }
+        case B_NORM: CFB_CHECK(gn(b.norm, x, &ps, &ph)); continue;
+        case B_CONV:
+          if (i + 1 == n->gen.size()) {
+            if (!dry) CFB_CHECK(conv_last(x.p, ps, ph, b.conv.w_f32, b.conv.bias, out_nchw, x.N, x.H, x.W, x.C, st));
+            if (ps) { release_raw(ps); release_raw(ph); ps = ph = nullptr; }
+            release(x);
+            return 0;
+          } else {
+            ConvOpt o; o.in_scale = ps; o.in_shift = ph;
+            CFB_CHECK(conv(b.conv, x, y, o));
+            if (ps) { release_raw(ps); release_raw(ph); ps = ph = nullptr; }
+          }
+          break;
+        default: CFB_REQUIRE(false, "generator: unexpected block kind");
+      }
+      release(x);
+      x = y;
+      if (taps && w > 0.f)
+        for (int fb : fuse_blocks)
+          if ((int)i == fb) {
+            auto it = taps->find(x.W);
+            CFB_REQUIRE(it != taps->end(), "fusion: encoder feature missing");
+            auto fw = n->fuse.find(x.W);
+            CFB_REQUIRE(fw != n->fuse.end(), "fusion: no Fuse_sft_block for this size");
+            Tensor fz;
+            CFB_CHECK(fuse(fw->second, it->second, x, w, fz));
+            release(x);
+            release(it->second);
+            x = fz;
+          }
+    }
+    CFB_REQUIRE(false, "generator: plan does not end with a conv");
+    return 1;
+  }
+
+  // TransformerSALayer.forward x9 + idx_pred_layer  codeformer_arch.py:235-245
+  int transformer(const Tensor& lq, float* logits_out) {
+    const cfb_config& c = n->cfg;
+    const int B = lq.N, S = lq.H * lq.W, E = c.dim_embd, T = B * S;
+    CFB_REQUIRE(S == c.latent_size, "transformer: token count != latent_size");
+    Tensor tok = lq; tok.owned = false;   // [B,16,16,256] == tokens [T,256]
+    Tensor x;
+    { ConvOpt o; CFB_CHECK(conv(n->feat_emb, tok, x, o)); }
+    for (const LayerW& L : n->layers) {
+      Tensor t2, qkin, qk, v, a, x2, hdn, x3;
+      CFB_CHECK(alloc(t2, B, lq.H, lq.W, E));
+      CFB_CHECK(alloc(qkin, B, lq.H, lq.W, E));
+      if (!dry) CFB_CHECK(layer_norm(x.p, L.n1.gamma, L.n1.beta, t2.p, qkin.p, n->position_emb, S, T, E, st));
+      { ConvOpt o; CFB_CHECK(conv(L.qk, qkin, qk, o)); }
+      { ConvOpt o; CFB_CHECK(conv(L.v, t2, v, o)); }
+      release(qkin); release(t2);
+      CFB_CHECK(alloc(a, B, lq.H, lq.W, E));
+      if (!dry)
+        CFB_CHECK(attention(qk.p, qk.p + E, v.p, a.p, B, S, c.n_head, E / c.n_head, 2 * E, 2 * E, E, E,
+                            sqrtf(1.0f / (float)(E / c.n_head)), st));
+      release(qk); release(v);
+      { ConvOpt o; o.residual = x.p; CFB_CHECK(conv(L.o, a, x2, o)); }
+      release(a); release(x);
+      CFB_CHECK(alloc(t2, B, lq.H, lq.W, E));
+      if (!dry) CFB_CHECK(layer_norm(x2.p, L.n2.gamma, L.n2.beta, t2.p, nullptr, nullptr, 0, T, E, st));
+      { ConvOpt o; o.out_act = OUT_GELU; CFB_CHECK(conv(L.l1, t2, hdn, o)); }
+      release(t2);
+      { ConvOpt o; o.residual = x2.p; CFB_CHECK(conv(L.l2, hdn, x3, o)); }
+      release(hdn); release(x2);
+      x = x3;
+    }
+    Tensor t2, lg;
+    CFB_CHECK(alloc(t2, B, lq.H, lq.W, E));
+    if (!dry) CFB_CHECK(layer_norm(x.p, n->idx_norm.gamma, n->idx_norm.beta, t2.p, nullptr, nullptr, 0, T, E, st));
+    release(x);
+    { ConvOpt o; o.out_ptr = logits_out; CFB_CHECK(conv(n->idx_lin, t2, lg, o)); }
+    release(t2);
+    return 0;
+  }
+};
+
+static std::vector<int> tap_blocks_of(const cfb_config& c, bool encoder) {
+  // fuse_encoder_block / fuse_generator_block  codeformer_arch.py:204-206
+  static const int enc_of[6][2] = {{512, 2}, {256, 5}, {128, 8}, {64, 11}, {32, 14}, {16, 18}};
+  static const int gen_of[6][2] = {{16, 6}, {32, 9}, {64, 12}, {128, 15}, {256, 18}, {512, 21}};
+  std::vector<int> r;
+  for (int i = 0; i < c.n_connect; ++i)
+    for (auto& e : (encoder ? enc_of : gen_of))
+      if (e[0] == c.connect[i]) r.push_back(e[1]);
+  return r;
+}
+
+static int codeformer_forward_impl(cfb_net* n, const float* x, float* out, float* logits, float* lq_feat,
+                                   int64_t* top_idx, int B, float w, int adain, int code_only, void* ws, int64_t ws_bytes,
+                                   cudaStream_t st, bool dry) {
+  CFB_REQUIRE(n->cfg.kind == 1, "net was created as VQAutoEncoder");
+  CFB_REQUIRE(dry || n->prepared, "cfb_net_prepare has not been called");
+  CFB_REQUIRE(B >= 0, "negative batch");
+  if (B == 0) return 0;
+  n->arena.reset(ws, (size_t)ws_bytes, dry);
+  Fwd f{n, st, n->arena, dry, 0};
+  const cfb_config& c = n->cfg;
+  std::map<int, Tensor> taps;
+  Tensor lq;
+  const bool want_taps = (w > 0.f) && !code_only;   // codeformer_arch.py:276 -- features are only consumed when w>0
+  CFB_CHECK(f.encoder(x, B, lq, want_taps ? &taps : nullptr, tap_blocks_of(c, true)));
+  const int T = B * lq.H * lq.W;
+  float* logits_buf = logits;
+  if (!logits_buf) CFB_CHECK(f.alloc_raw((void**)&logits_buf, (size_t)T * c.codebook_size * 4));
+  CFB_CHECK(f.transformer(lq, logits_buf));
+  if (lq_feat && !dry) CFB_CHECK(nhwc_to_nchw(lq.p, lq_feat, B, lq.C, lq.H * lq.W, st));
+  if (code_only) {                                     // codeformer_arch.py:247-249
+    if (top_idx && !dry) CFB_CHECK(argmax_gather(logits_buf, n->codebook, top_idx, nullptr, T, c.codebook_size, c.emb_dim, st));
+    return 0;
+  }
+  CFB_REQUIRE(out != nullptr, "out must not be NULL unless code_only");
+  // softmax -> topk(1) -> get_codebook_feat  (:257-259)
+  Tensor quant;
+  CFB_CHECK(f.alloc(quant, B, lq.H, lq.W, c.emb_dim));
+  if (!dry) CFB_CHECK(argmax_gather(logits_buf, n->codebook, top_idx, quant.p, T, c.codebook_size, c.emb_dim, st));
+  if (adain) {                                         // :265-266
+    Tensor q2;
+    CFB_CHECK(f.alloc(q2, B, lq.H, lq.W, c.emb_dim));
+    if (!dry) CFB_CHECK(adain_nhwc(quant.p, lq.p, q2.p, B, lq.H * lq.W, c.emb_dim, st));
+    f.release(quant);
+    quant = q2;
+  }
+  f.release(lq);
+  CFB_CHECK(f.generator(quant, out, want_taps ? &taps : nullptr, tap_blocks_of(c, false), w));
+  return 0;
+}
+
+static int vqae_forward_impl(cfb_net* n, const float* x, float* out, int64_t* idx, float* stats, float* onehot, int B,
+                             void* ws, int64_t ws_bytes, cudaStream_t st, bool dry) {
+  CFB_REQUIRE(dry || n->prepared, "cfb_net_prepare has not been called");
+  if (B == 0) return 0;
+  n->arena.reset(ws, (size_t)ws_bytes, dry);
+  Fwd f{n, st, n->arena, dry, 0};
+  const cfb_config& c = n->cfg;
+  Tensor z;
+  CFB_CHECK(f.encoder(x, B, z, nullptr, {}));
+  const int T = B * z.H * z.W;
+  Tensor zq;
+  CFB_CHECK(f.alloc(zq, B, z.H, z.W, z.C));
+  void* vws = nullptr;
+  int64_t* idx_buf = idx;
+  float* stats_buf = stats;
+  CFB_CHECK(f.alloc_raw(&vws, vq_workspace_bytes(T, z.C, c.codebook_size)));
+  if (!idx_buf) CFB_CHECK(f.alloc_raw((void**)&idx_buf, (size_t)T * 8));
+  if (!stats_buf) CFB_CHECK(f.alloc_raw((void**)&stats_buf, 16));
+  if (!dry) CFB_CHECK(vq_nearest(z.p, n->codebook, T, z.C, c.codebook_size, c.beta, idx_buf, zq.p, stats_buf, onehot, vws, st));
+  f.release(z);
+  CFB_CHECK(f.generator(zq, out, nullptr, {}, 0.f));
+  return 0;
+}
+
+}  // namespace cfb
+
+// =========================================================================================================
+// C ABI
+// =========================================================================================================
+#define API_BEGIN try {
+#define API_END(ret)                                                             \
+  } catch (const std::exception& e) { cfb::set_error(std::string("exception: ") + e.what()); return ret; } \
+  catch (...) { cfb::set_error("unknown exception"); return ret; }
+
+extern "C" {
+
+int cfb_version(void) { return CFB_VERSION; }
+const char* cfb_last_error(void) { return cfb::last_error().c_str(); }
+
+int cfb_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  API_BEGIN
+  int dev = 0;
+  CFB_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  CFB_CUDA(cudaGetDeviceProperties(&p, dev));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  return 0;
+  API_END(1)
+}
+
+cfb_net* cfb_net_create(const cfb_config* cfg) {
+  API_BEGIN
+  if (!cfg) { cfb::set_error("cfb_net_create: NULL config"); return nullptr; }
+  cfb_net* n = new cfb_net();
+  n->cfg = *cfg;
+  n->convs.reserve(512);
+  if (cfb::build_plan(n) != 0) { delete n; return nullptr; }
+  int dev = 0, major = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) {
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  } else {
+    cudaGetLastError();
+  }
+  n->sm_count = sms > 0 ? sms : 148;
+  n->tc_ok = (major == 10);
+  return n;
+  API_END(nullptr)
+}
+
+void cfb_net_destroy(cfb_net* n) {
+  if (!n) return;
+  if (n->slab) cudaFree(n->slab);
+  delete n;
+}
+
+int cfb_net_set_param(cfb_net* n, const char* name, const float* dev_ptr, int64_t numel) {
+  API_BEGIN
+  CFB_REQUIRE(n && name && dev_ptr, "cfb_net_set_param: NULL argument");
+  std::lock_guard<std::mutex> lk(n->mu);
+  n->raw[name] = {dev_ptr, numel};
+  n->prepared = false;
+  return 0;
+  API_END(1)
+}
+
+int cfb_net_prepare(cfb_net* n, void* stream) {
+  API_BEGIN
+  CFB_REQUIRE(n, "cfb_net_prepare: NULL net");
+  std::lock_guard<std::mutex> lk(n->mu);
+  return cfb::prepare(n, (cudaStream_t)stream);
+  API_END(1)
+}
+
+int64_t cfb_workspace_bytes(cfb_net* n, int32_t batch) {
+  API_BEGIN
+  if (!n) { cfb::set_error("cfb_workspace_bytes: NULL net"); return -1; }
+  std::lock_guard<std::mutex> lk(n->mu);
+  int rc;
+  if (n->cfg.kind == 1)
+    rc = cfb::codeformer_forward_impl(n, (const float*)0x1000, (float*)0x1000, nullptr, (float*)0x1000, nullptr, batch, 1.f, 1,
+                                      0, nullptr, 0, nullptr, true);
+  else
+    rc = cfb::vqae_forward_impl(n, (const float*)0x1000, (float*)0x1000, nullptr, nullptr, nullptr, batch, nullptr, 0, nullptr,
+                                true);
+  if (rc != 0) return -1;
+  return (int64_t)n->arena.high() + 4096;
+  API_END(-1)
+}
+
+int64_t cfb_last_launch_count(cfb_net* n) { return n ? n->last_launches : 0; }
+
+int cfb_codeformer_forward(cfb_net* n, const float* x, float* out, float* logits, float* lq_feat, int64_t* top_idx,
+                           int32_t batch, float w, int32_t adain, int32_t code_only, void* workspace,
+                           int64_t workspace_bytes, void* stream) {
+  API_BEGIN
+  CFB_REQUIRE(n, "cfb_codeformer_forward: NULL net");
+  if (batch == 0) return 0;
+  CFB_REQUIRE(x, "cfb_codeformer_forward: NULL input");
+  std::lock_guard<std::mutex> lk(n->mu);   // two caller threads may share one net (web-demos/hugging_face/app.py:282)
+  const int64_t before = cfb::launch_count();
+  const int rc = cfb::codeformer_forward_impl(n, x, out, logits, lq_feat, top_idx, batch, w, adain, code_only, workspace,
+                                              workspace_bytes, (cudaStream_t)stream, false);
+  n->last_launches = cfb::launch_count() - before;
+  return rc;
+  API_END(1)
+}
+
+int64_t cfb_host_io_bytes(cfb_net* n, int32_t batch) {
+  if (!n) return -1;
+  const cfb_config& c = n->cfg;
+  const int64_t img = (int64_t)batch * 3 * c.img_size * c.img_size * 4;
+  const int64_t lat = (int64_t)batch * c.latent_size;
+  return 2 * (img + 1024) + lat * c.codebook_size * 4 + lat * c.emb_dim * 4 + 4096;
+}
+
+int cfb_codeformer_forward_host(cfb_net* n, const float* x_host, float* out_host, float* logits_host, float* lq_host,
+                                int32_t batch, float w, int32_t adain, void* dev_scratch, int64_t dev_scratch_bytes,
+                                void* workspace, int64_t workspace_bytes, void* stream) {
+  API_BEGIN
+  CFB_REQUIRE(n && x_host && out_host && dev_scratch, "cfb_codeformer_forward_host: NULL argument");
+  CFB_REQUIRE(dev_scratch_bytes >= cfb_host_io_bytes(n, batch), "dev_scratch too small (cfb_host_io_bytes)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const cfb_config& c = n->cfg;
+  const size_t img = (size_t)batch * 3 * c.img_size * c.img_size * 4;
+  const size_t lat = (size_t)batch * c.latent_size;
+  char* p = (char*)dev_scratch;
+  float* dx = (float*)p; p += (img + 1023) / 1024 * 1024;
+  float* dout = (float*)p; p += (img + 1023) / 1024 * 1024;
+  float* dlog = (float*)p; p += lat * c.codebook_size * 4;
+  float* dlq = (float*)p;
+  CFB_CUDA(cudaMemcpyAsync(dx, x_host, img, cudaMemcpyHostToDevice, st));
+  CFB_CHECK(cfb_codeformer_forward(n, dx, dout, dlog, dlq, nullptr, batch, w, adain, 0, workspace, workspace_bytes, stream));
+  CFB_CUDA(cudaMemcpyAsync(out_host, dout, img, cudaMemcpyDeviceToHost, st));
+  if (logits_host) CFB_CUDA(cudaMemcpyAsync(logits_host, dlog, lat * c.codebook_size * 4, cudaMemcpyDeviceToHost, st));
+  if (lq_host) CFB_CUDA(cudaMemcpyAsync(lq_host, dlq, lat * c.emb_dim * 4, cudaMemcpyDeviceToHost, st));
+  CFB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+  API_END(1)
+}
+
+int cfb_vqae_forward(cfb_net* n, const float* x, float* out, int64_t* idx, float* stats, float* min_encodings,
+                     int32_t batch, void* workspace, int64_t workspace_bytes, void* stream) {
+  API_BEGIN
+  CFB_REQUIRE(n, "cfb_vqae_forward: NULL net");
+  if (batch == 0) return 0;
+  CFB_REQUIRE(x && out, "cfb_vqae_forward: NULL argument");
+  std::lock_guard<std::mutex> lk(n->mu);
+  const int64_t before = cfb::launch_count();
+  const int rc = cfb::vqae_forward_impl(n, x, out, idx, stats, min_encodings, batch, workspace, workspace_bytes,
+                                        (cudaStream_t)stream, false);
+  n->last_launches = cfb::launch_count() - before;
+  return rc;
+  API_END(1)
+}
+
+int64_t cfb_vq_workspace_bytes(int32_t batch, int32_t hw, int32_t dim, int32_t codes) {
+  const int64_t T = (int64_t)batch * hw;
+  return (int64_t)cfb::vq_workspace_bytes((int)T, dim, codes) + 2 * ((T * dim * 4 + 1023) / 1024 * 1024) + 4096;
+}
+
+int cfb_vq_nearest(const float* z, const float* codebook, int32_t batch, int32_t h, int32_t w, int32_t dim, int32_t codes,
+                   float beta, float* z_q, int64_t* idx, float* stats, float* min_encodings, void* workspace,
+                   int64_t workspace_bytes, void* stream) {
+  API_BEGIN
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t T = (int64_t)batch * h * w;
+  if (T == 0) return 0;                     // empty batch: nothing to do (stats are left untouched)
+  CFB_REQUIRE(z && codebook && z_q && idx && stats && workspace, "cfb_vq_nearest: NULL argument");
+  CFB_REQUIRE(workspace_bytes >= cfb_vq_workspace_bytes(batch, h * w, dim, codes), "cfb_vq_nearest: workspace too small");
+  const size_t tb = ((size_t)T * dim * 4 + 1023) / 1024 * 1024;
+  char* p = (char*)workspace;
+  float* zt = (float*)p; p += tb;
+  float* zqt = (float*)p; p += tb;
+  CFB_CHECK(cfb::nchw_to_nhwc(z, zt, batch, dim, h * w, st));
+  CFB_CHECK(cfb::vq_nearest(zt, codebook, (int)T, dim, codes, beta, idx, zqt, stats, min_encodings, p, st));
+  CFB_CHECK(cfb::nhwc_to_nchw(zqt, z_q, batch, dim, h * w, st));
+  return 0;
+  API_END(1)
+}
+
+int cfb_codebook_lookup(const int64_t* idx, const float* codebook, int32_t batch, int32_t h, int32_t w, int32_t dim,
+                        int32_t codes, float* z_q, void* stream) {
+  API_BEGIN
+  CFB_REQUIRE(idx && codebook && z_q, "cfb_codebook_lookup: NULL argument");
+  // gather token-major then transpose in place is not possible; gather straight into NCHW order instead
+  // (small: B*256 tokens) via a temporary-free two-step is avoided by a strided gather kernel:
+  cudaStream_t st = (cudaStream_t)stream;
+  const int T = batch * h * w;
+  if (T == 0) return 0;
+  float* tmp = nullptr;
+  CFB_CUDA(cudaMallocAsync((void**)&tmp, (size_t)T * dim * 4, st));
+  int rc = cfb::gather_rows(idx, codebook, tmp, T, codes, dim, st);
+  if (rc == 0) rc = cfb::nhwc_to_nchw(tmp, z_q, batch, dim, h * w, st);
+  cudaFreeAsync(tmp, st);
+  return rc;
+  API_END(1)
+}
+
+int64_t cfb_conv2d_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t cin, int32_t cout, int32_t ksize, int32_t mode) {
+  cfb::ConvArgs a;
+  a.N = n; a.H = h; a.W = w; a.Cin = cin; a.Cout = cout; a.ksize = ksize; a.mode = mode;
+  a.Ho = mode == cfb::CONV_DOWN ? h / 2 : (mode == cfb::CONV_UP ? h * 2 : h);
+  a.Wo = mode == cfb::CONV_DOWN ? w / 2 : (mode == cfb::CONV_UP ? w * 2 : w);
+  const size_t wn = (size_t)cout * cin * ksize * ksize;
+  return (int64_t)(align256(wn * 4) + 2 * align256(wn * 2) + cfb::tc_scratch_bytes(a) + 8192);
+}
+
+int cfb_conv2d_nhwc(const float* in, const float* weight_oihw, const float* bias, float* out, int32_t n, int32_t h,
+                    int32_t w, int32_t cin, int32_t cout, int32_t ksize, int32_t mode, const float* in_scale,
+                    const float* in_shift, int32_t in_act, const float* residual, int32_t out_act, int32_t engine,
+                    void* workspace, int64_t workspace_bytes, void* stream) {
+  API_BEGIN
+  CFB_REQUIRE(in && weight_oihw && out && workspace, "cfb_conv2d_nhwc: NULL argument");
+  CFB_REQUIRE(workspace_bytes >= cfb_conv2d_workspace_bytes(n, h, w, cin, cout, ksize, mode), "cfb_conv2d_nhwc: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  cfb::ConvArgs a;
+  a.in = in; a.N = n; a.H = h; a.W = w; a.Cin = cin; a.Cout = cout; a.ksize = ksize; a.mode = mode;
+  a.Ho = mode == cfb::CONV_DOWN ? h / 2 : (mode == cfb::CONV_UP ? h * 2 : h);
+  a.Wo = mode == cfb::CONV_DOWN ? w / 2 : (mode == cfb::CONV_UP ? w * 2 : w);
+  a.bias = bias; a.in_scale = in_scale; a.in_shift = in_shift; a.in_act = in_act; a.residual = residual;
+  a.out_act = out_act; a.out = out;
+  const size_t wn = (size_t)cout * cin * ksize * ksize;
+  char* p = (char*)workspace;
+  float* wf = (float*)p; p += align256(wn * 4);
+  __half* whi = (__half*)p; p += align256(wn * 2);
+  __half* wlo = (__half*)p; p += align256(wn * 2);
+  p = (char*)(((uintptr_t)p + 1023) / 1024 * 1024);
+  a.wgt_f32 = wf; a.wgt_hi = whi; a.wgt_lo = wlo;
+  bool use_tc = engine == 2;
+  if (engine == 0) {
+    int dev = 0, major = 0;
+    CFB_CUDA(cudaGetDevice(&dev));
+    CFB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    use_tc = major == 10 && cfb::tc_supported(a);
+  }
+  if (use_tc) {
+    CFB_REQUIRE(cfb::tc_supported(a), "cfb_conv2d_nhwc: shape not supported by the tcgen05 engine");
+    int dev = 0, sms = 148;
+    CFB_CUDA(cudaGetDevice(&dev));
+    CFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CFB_CHECK(cfb::tc_split_weights(weight_oihw, whi, wlo, cout, cin, ksize, st));
+    CFB_CHECK(cfb::conv_tc(a, p, sms, st));
+  } else {
+    CFB_CHECK(cfb::relayout_oihw_to_tck(weight_oihw, wf, cout, cin, ksize, st));
+    CFB_CHECK(cfb::conv_f32(a, st));
+  }
+  return 0;
+  API_END(1)
+}
+
+int64_t cfb_gn_workspace_bytes(int32_t n, int32_t hw, int32_t c) { return (int64_t)cfb::gn_workspace_bytes(n, hw, c) + 256; }
+int cfb_group_norm_coef(const float* x, const float* gamma, const float* beta, float* scale, float* shift, int32_t n,
+                        int32_t hw, int32_t c, int32_t groups, float eps, void* workspace, int64_t workspace_bytes,
+                        void* stream) {
+  API_BEGIN
+  CFB_REQUIRE(x && gamma && beta && scale && shift && workspace, "cfb_group_norm_coef: NULL argument");
+  CFB_REQUIRE(workspace_bytes >= (int64_t)cfb::gn_workspace_bytes(n, hw, c), "cfb_group_norm_coef: workspace too small");
+  return cfb::gn_coef(x, gamma, beta, scale, shift, n, hw, c, groups, eps, workspace, (cudaStream_t)stream);
+  API_END(1)
+}
+int cfb_affine_act(const float* x, const float* scale, const float* shift, float* y, int32_t n, int32_t hw, int32_t c,
+                   int32_t act, void* stream) {
+  API_BEGIN
+  return cfb::affine_act(x, scale, shift, y, n, hw, c, act, (cudaStream_t)stream);
+  API_END(1)
+}
+int cfb_attention(const float* q, const float* k, const float* v, float* out, int32_t batch, int32_t tokens, int32_t heads,
+                  int32_t d, int32_t q_pitch, int32_t k_pitch, int32_t v_pitch, int32_t o_pitch, float scale, void* stream) {
+  API_BEGIN
+  return cfb::attention(q, k, v, out, batch, tokens, heads, d, q_pitch, k_pitch, v_pitch, o_pitch, scale, (cudaStream_t)stream);
+  API_END(1)
+}
+int cfb_layer_norm(const float* x, const float* gamma, const float* beta, float* y, float* y2, const float* pos,
+                   int32_t pos_rows, int32_t rows, int32_t c, void* stream) {
+  API_BEGIN
+  return cfb::layer_norm(x, gamma, beta, y, y2, pos, pos_rows, rows, c, (cudaStream_t)stream);
+  API_END(1)
+}
+int cfb_adain_nhwc(const float* content, const float* style, float* out, int32_t batch, int32_t hw, int32_t c, void* stream) {
+  API_BEGIN
+  return cfb::adain_nhwc(content, style, out, batch, hw, c, (cudaStream_t)stream);
+  API_END(1)
+}
+int cfb_nchw_to_nhwc(const float* in, float* out, int32_t n, int32_t c, int32_t hw, void* stream) {
+  API_BEGIN
+  return cfb::nchw_to_nhwc(in, out, n, c, hw, (cudaStream_t)stream);
+  API_END(1)
+}
+int cfb_nhwc_to_nchw(const float* in, float* out, int32_t n, int32_t c, int32_t hw, void* stream) {
+  API_BEGIN
+  return cfb::nhwc_to_nchw(in, out, n, c, hw, (cudaStream_t)stream);
+  API_END(1)
+}
+
+}  // extern "C"

@@ -1,0 +1,149 @@
+/*
+ * cfb200.h -- C ABI of libcfb200.so, the B200-native (sm_100a) replacement of CodeFormer's
+ * core forward pass.
+ *
+ * Drop-in boundary.  The reference has no FFI on this path: the arithmetic is reached
+ * through PyTorch nn.Modules looked up in a registry
+ *   ARCH_REGISTRY.get('CodeFormer') / .get('VQAutoEncoder')   basicsr/utils/registry.py:62-66,79
+ *   CodeFormer.forward(x, w, detach_16, code_only, adain)      basicsr/archs/codeformer_arch.py:223-280
+ *   VQAutoEncoder.forward(x)                                   basicsr/archs/vqgan_arch.py:385-389
+ *   VectorQuantizer.forward(z) / get_codebook_feat             basicsr/archs/vqgan_arch.py:33-84
+ * and the only native-extension convention the reference has is the pybind11 `m.def` modules
+ * of basicsr/ops/{dcn,fused_act,upfirdn2d}/src/*.cpp built by basicsr/setup.py:118-135.
+ * This header is what a maintainer binds instead (ctypes stub in INTEGRATION.md): plain C,
+ * raw device/host pointers + sizes + a cudaStream_t passed as void*, int status returns
+ * (0 = ok; cfb_last_error() gives the message).  No torch types cross this boundary.
+ *
+ * All tensors are fp32 and contiguous.  "NCHW" tensors use the reference's layout; internal
+ * activations are NHWC and never leave the library.  Every call enqueues on `stream` and
+ * returns without synchronising unless stated.
+ */
+#ifndef CFB200_H_
+#define CFB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CFB_VERSION 100
+
+typedef struct cfb_net cfb_net;
+
+/* Constructor arguments of the reference classes.
+ * CodeFormer(dim_embd, n_head, n_layers, codebook_size, latent_size, connect_list)  codeformer_arch.py:162-166
+ * VQAutoEncoder(img_size, nf, ch_mult, 'nearest', res_blocks, attn_resolutions, codebook_size, emb_dim, beta)
+ *                                                                                    vqgan_arch.py:328-329 */
+typedef struct cfb_config {
+  int32_t kind;            /* 0 = VQAutoEncoder, 1 = CodeFormer */
+  int32_t img_size;        /* 512 */
+  int32_t nf;              /* 64 */
+  int32_t n_ch_mult;       /* 6 */
+  int32_t ch_mult[8];      /* 1,2,2,4,4,8 */
+  int32_t res_blocks;      /* 2 */
+  int32_t n_attn_res;      /* 1 */
+  int32_t attn_res[4];     /* 16 */
+  int32_t codebook_size;   /* 1024 */
+  int32_t emb_dim;         /* 256 */
+  float   beta;            /* 0.25 */
+  /* CodeFormer only */
+  int32_t dim_embd;        /* 512 */
+  int32_t n_head;          /* 8 */
+  int32_t n_layers;        /* 9 */
+  int32_t latent_size;     /* 256 */
+  int32_t n_connect;       /* 4 */
+  int32_t connect[6];      /* 32,64,128,256 (feature sizes of connect_list) */
+} cfb_config;
+
+/* ---- library ---- */
+int         cfb_version(void);
+const char* cfb_last_error(void);             /* thread-local message of the last failing call */
+int         cfb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- network life cycle (replaces nn.Module construction + load_state_dict) ---- */
+cfb_net* cfb_net_create(const cfb_config* cfg);                 /* NULL on error */
+void     cfb_net_destroy(cfb_net* net);
+/* Hand one state_dict tensor (reference key name, reference layout e.g. OIHW) as a DEVICE
+ * fp32 pointer; it is copied/re-laid-out at cfb_net_prepare and need not outlive it. */
+int      cfb_net_set_param(cfb_net* net, const char* name, const float* dev_ptr, int64_t numel);
+int      cfb_net_prepare(cfb_net* net, void* stream);          /* errors if any key is missing */
+int64_t  cfb_workspace_bytes(cfb_net* net, int32_t batch);     /* scratch needed for a forward at this batch; <0 on error */
+/* number of kernel launches the last forward on this net enqueued (bench.py "gpu_launches") */
+int64_t  cfb_last_launch_count(cfb_net* net);
+
+/* ---- CodeFormer.forward (codeformer_arch.py:223-280) ----
+ * x [B,3,512,512] NCHW in [-1,1]; out [B,3,512,512] NCHW (unclamped; may be NULL when code_only);
+ * logits [B,256,K]; lq_feat [B,256,16,16] NCHW; top_idx [B,256] int64 (may be NULL).
+ * All DEVICE pointers.  `w` is the fidelity weight (branch w>0, :276). */
+int cfb_codeformer_forward(cfb_net* net, const float* x, float* out, float* logits, float* lq_feat,
+                           int64_t* top_idx, int32_t batch, float w, int32_t adain, int32_t code_only,
+                           void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Same call with HOST buffers (pinned recommended): H2D of x, forward, D2H of out/logits/lq_feat,
+ * all on `stream`, then one stream synchronise.  dev_scratch must hold the device copies:
+ * cfb_host_io_bytes(net,batch) bytes, in addition to the workspace. */
+int64_t cfb_host_io_bytes(cfb_net* net, int32_t batch);
+int cfb_codeformer_forward_host(cfb_net* net, const float* x_host, float* out_host, float* logits_host,
+                                float* lq_feat_host, int32_t batch, float w, int32_t adain,
+                                void* dev_scratch, int64_t dev_scratch_bytes,
+                                void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- VQAutoEncoder.forward (vqgan_arch.py:385-389) ----
+ * out [B,3,512,512]; idx [B*256] int64; stats[4] = {codebook_loss, perplexity, mean_distance, 0};
+ * min_encodings [B*256,K] one-hot fp32 or NULL (materialised only when asked). */
+int cfb_vqae_forward(cfb_net* net, const float* x, float* out, int64_t* idx, float* stats,
+                     float* min_encodings, int32_t batch,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- VectorQuantizer.forward (vqgan_arch.py:33-70), standalone (config 3 microbench) ----
+ * z [B,D,H,W] NCHW, codebook [K,D]; z_q [B,D,H,W] NCHW (= z + (E[idx]-z), :57); idx [B*H*W] int64;
+ * stats[4] as above; min_encodings optional.  workspace >= cfb_vq_workspace_bytes. */
+int64_t cfb_vq_workspace_bytes(int32_t batch, int32_t hw, int32_t dim, int32_t codes);
+int cfb_vq_nearest(const float* z, const float* codebook, int32_t batch, int32_t h, int32_t w,
+                   int32_t dim, int32_t codes, float beta, float* z_q, int64_t* idx, float* stats,
+                   float* min_encodings, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- VectorQuantizer.get_codebook_feat (vqgan_arch.py:72-84) ---- idx [n] int64 -> z_q [B,D,H,W] NCHW */
+int cfb_codebook_lookup(const int64_t* idx, const float* codebook, int32_t batch, int32_t h, int32_t w,
+                        int32_t dim, int32_t codes, float* z_q, void* stream);
+
+/* ---- per-kernel entry points (unit-parity tests; NHWC fp32 device tensors) ---- */
+/* conv2d: in [N,H,W,Cin] NHWC, weight OIHW [Cout,Cin,k,k] (reference layout), bias [Cout] or NULL.
+ * mode: 0 = 'same' k=1|3 stride 1 (nn.Conv2d padding=k/2); 1 = Downsample (pad right/bottom 1, 3x3 s2 p0,
+ * vqgan_arch.py:122-126); 2 = Upsample (nearest x2 then 3x3 p1, vqgan_arch.py:134-138).
+ * in_scale/in_shift [N,Cin] optional fused per-sample affine (GroupNorm), in_act 0|1(SiLU);
+ * residual [N,Ho,Wo,Cout] optional; out_act 0 | 1 LeakyReLU(0.2) | 2 GELU(erf).
+ * engine: 0 = auto, 1 = fp32 CUDA-core implicit GEMM, 2 = tcgen05 split-fp16 tensor-core implicit GEMM. */
+int cfb_conv2d_nhwc(const float* in, const float* weight_oihw, const float* bias, float* out,
+                    int32_t n, int32_t h, int32_t w, int32_t cin, int32_t cout, int32_t ksize, int32_t mode,
+                    const float* in_scale, const float* in_shift, int32_t in_act,
+                    const float* residual, int32_t out_act, int32_t engine,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+int64_t cfb_conv2d_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t cin, int32_t cout, int32_t ksize, int32_t mode);
+/* GroupNorm(32,C,eps) statistics folded with the affine: scale[n,c] = rstd*gamma, shift[n,c] = beta - mean*rstd*gamma
+ * (vqgan_arch.py:14-15).  x [N,HW,C] NHWC.  workspace >= cfb_gn_workspace_bytes. */
+int64_t cfb_gn_workspace_bytes(int32_t n, int32_t hw, int32_t c);
+int cfb_group_norm_coef(const float* x, const float* gamma, const float* beta, float* scale, float* shift,
+                        int32_t n, int32_t hw, int32_t c, int32_t groups, float eps,
+                        void* workspace, int64_t workspace_bytes, void* stream);
+/* y = act(x*scale[n,c]+shift[n,c]) materialised (NHWC) */
+int cfb_affine_act(const float* x, const float* scale, const float* shift, float* y,
+                   int32_t n, int32_t hw, int32_t c, int32_t act, void* stream);
+/* softmax(q k^T * scale) v for `heads` heads of width d packed in rows of pitch (in floats); S tokens per batch */
+int cfb_attention(const float* q, const float* k, const float* v, float* out,
+                  int32_t batch, int32_t tokens, int32_t heads, int32_t d,
+                  int32_t q_pitch, int32_t k_pitch, int32_t v_pitch, int32_t o_pitch, float scale, void* stream);
+/* LayerNorm over the last dim (eps 1e-5); y2 (optional) = y + pos[t % pos_rows] */
+int cfb_layer_norm(const float* x, const float* gamma, const float* beta, float* y, float* y2,
+                   const float* pos, int32_t pos_rows, int32_t rows, int32_t c, void* stream);
+/* AdaIN of codeformer_arch.py:29-43 on NHWC [B,HW,C] */
+int cfb_adain_nhwc(const float* content, const float* style, float* out, int32_t batch, int32_t hw, int32_t c, void* stream);
+/* layout plumbing */
+int cfb_nchw_to_nhwc(const float* in, float* out, int32_t n, int32_t c, int32_t hw, void* stream);
+int cfb_nhwc_to_nchw(const float* in, float* out, int32_t n, int32_t c, int32_t hw, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CFB200_H_ */

@@ -1,0 +1,130 @@
+"""-m gpu: the whole hot path through the reference-facing API (nn.Module.forward -> C ABI) against
+(a) the golden vectors of the UNMODIFIED reference and (b) the oracle run on this box's CPU.
+Bar (BASELINE.json north_star): <= 1e-3 max-abs on fp32 outputs, code indices bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+import codeformer_b200 as cb
+from codeformer_b200 import spec as S
+from tests.util import faces_input, golden, maxabs
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+TOL_OUT = 1e-3          # north_star: 1e-3 max abs fp32
+TOL_LAT = 2e-4          # logits / lq_feat (observed ~1e-5; the index decision depends on them)
+
+
+@pytest.fixture(scope='module')
+def net_main():
+    net = cb.ARCH_REGISTRY.get('CodeFormer')(dim_embd=512, codebook_size=1024, n_head=8, n_layers=9,
+                                            connect_list=['32', '64', '128', '256']).to('cuda')
+    net.load_state_dict(S.random_state_dict(S.codeformer_spec(), 1), strict=True)
+    return net.eval()
+
+
+def test_config1_single_face_vs_reference_golden(net_main):
+    g = golden('codeformer_main.npz')
+    x = faces_input(slice(0, 1)).cuda()
+    out, logits, lq = net_main(x, w=0.5, adain=True)
+    assert out.shape == (1, 3, 512, 512) and logits.shape == (1, 256, 1024) and lq.shape == (1, 256, 16, 16)
+    e_out, e_log, e_lq = maxabs(out.cpu(), g['out']), maxabs(logits.cpu(), g['logits']), maxabs(lq.cpu(), g['lq_feat'])
+    print(f'config1 max-abs: out {e_out:.3e} (|out|max {float(np.abs(g["out"]).max()):.2f}) logits {e_log:.3e} lq {e_lq:.3e}')
+    assert np.array_equal(logits.argmax(2).cpu().numpy(), g['top_idx']), 'code indices must be bit-exact'
+    assert e_out < TOL_OUT and e_log < TOL_LAT and e_lq < TOL_LAT
+    assert net_main.last_launch_count > 50
+
+
+def test_variants_vs_reference_golden(net_main):
+    g = golden('codeformer_variants.npz')
+    x = faces_input(slice(1, 2)).cuda()
+    o, l, q = net_main(x, w=0, adain=True)                                    # w<=0 skips the fusion (:276)
+    assert maxabs(o[..., ::4, ::4].cpu(), g['w0_out']) < TOL_OUT and np.array_equal(l.argmax(2).cpu().numpy(), g['w0_idx'])
+    assert maxabs(q.cpu(), g['w0_lq']) < TOL_LAT
+    o, l, q = net_main(x, w=1.0, adain=False)
+    assert maxabs(o[..., ::4, ::4].cpu(), g['w1_out']) < TOL_OUT and np.array_equal(l.argmax(2).cpu().numpy(), g['w1_idx'])
+    l, q = net_main(x, w=0, code_only=True)                                   # training stage II return (:247-249)
+    assert maxabs(l[0, :4].cpu(), g['code_only_logits_row0']) < TOL_LAT
+    net3 = cb.CodeFormer(connect_list=['32', '64', '128']).cuda().eval()       # inference_colorization.py:45
+    net3.load_state_dict(S.random_state_dict(S.codeformer_spec(connect_list=('32', '64', '128')), 3))
+    o, l, q = net3(x, w=0.7, adain=True)
+    assert maxabs(o[..., ::4, ::4].cpu(), g['c3_out']) < TOL_OUT and np.array_equal(l.argmax(2).cpu().numpy(), g['c3_idx'])
+    net5 = cb.CodeFormer(codebook_size=512, connect_list=['32', '64', '128']).cuda().eval()   # inference_inpainting.py:45
+    net5.load_state_dict(S.random_state_dict(S.codeformer_spec(codebook_size=512, connect_list=('32', '64', '128')), 4))
+    o, l, q = net5(x, w=1, adain=False)
+    assert l.shape == (1, 256, 512)
+    assert maxabs(o[..., ::4, ::4].cpu(), g['k512_out']) < TOL_OUT and np.array_equal(l.argmax(2).cpu().numpy(), g['k512_idx'])
+
+
+def test_batch_vs_oracle_on_this_box(net_main):
+    """4 committed faces as one batch vs the oracle on the box's CPU; also batch invariance (B=4 == 4 x B=1)."""
+    from oracle import codeformer_oracle as O
+    sd = S.random_state_dict(S.codeformer_spec(), 1)
+    x = faces_input(slice(0, 4))
+    ro, rl, rq = O.codeformer_forward(sd, x, w=0.5, adain_on=True)
+    out, logits, lq = net_main(x.cuda(), w=0.5, adain=True)
+    assert torch.equal(logits.argmax(2).cpu(), rl.argmax(2))
+    srt = rl.sort(dim=2, descending=True).values
+    print(f'batch4 max-abs: out {maxabs(out.cpu(), ro):.3e} logits {maxabs(logits.cpu(), rl):.3e}; '
+          f'oracle top1-top2 margin min {float((srt[..., 0] - srt[..., 1]).min()):.3e}')
+    assert maxabs(out.cpu(), ro) < TOL_OUT and maxabs(logits.cpu(), rl) < TOL_LAT and maxabs(lq.cpu(), rq) < TOL_LAT
+    for i in range(4):
+        oi, li, qi = net_main(x[i:i + 1].cuda(), w=0.5, adain=True)
+        assert torch.equal(oi[0], out[i]) and torch.equal(li[0], logits[i]), 'forward must be batch-invariant (bit-identical)'
+
+
+def test_vqautoencoder_vs_reference_golden():
+    g = golden('vqae.npz')
+    v = cb.ARCH_REGISTRY.get('VQAutoEncoder')(512, 64, [1, 2, 2, 4, 4, 8], 'nearest', 2, [16], 1024).cuda().eval()
+    v.load_state_dict(S.random_state_dict(S.vqae_spec(), 2), strict=True)
+    out, loss, st = v(faces_input(slice(0, 1)).cuda(), return_min_encodings=True)
+    assert np.array_equal(st['min_encoding_indices'].cpu().numpy(), g['idx']), 'argmin code indices must be bit-exact'
+    assert maxabs(out[..., ::4, ::4].cpu(), g['out']) < TOL_OUT
+    assert abs(float(loss) - float(g['loss'])) < 1e-4 * float(g['loss'])
+    assert abs(float(st['perplexity']) - float(g['perplexity'])) < 1e-3 * float(g['perplexity'])
+    assert abs(float(st['mean_distance']) - float(g['mean_distance'])) < 1e-4 * float(g['mean_distance'])
+    assert st['min_encodings'].shape == (256, 1024)
+
+
+def test_reload_weights_and_errors(net_main):
+    x = faces_input(slice(2, 3)).cuda()
+    a = net_main(x, w=0.5, adain=True)[0]
+    sd2 = S.random_state_dict(S.codeformer_spec(), 7)
+    net = cb.CodeFormer().cuda().eval()
+    net.load_state_dict(sd2)
+    b = net(x, w=0.5, adain=True)[0]
+    net.load_state_dict(S.random_state_dict(S.codeformer_spec(), 1))       # re-prepared on weight change
+    c = net(x, w=0.5, adain=True)[0]
+    assert not torch.equal(a, b) and torch.equal(a, c)
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 3, 256, 256, device='cuda'))                     # wrong size must raise, not abort
+    with pytest.raises(RuntimeError):
+        net(x.half())
+    e = net(torch.empty(0, 3, 512, 512, device='cuda'), w=0.5)              # empty batch
+    assert e[0].shape == (0, 3, 512, 512)
+    assert torch.equal(net(x, w=0.5, adain=True)[0], a)                     # still healthy afterwards
+
+
+def test_host_buffer_entry_point(net_main):
+    x = faces_input(slice(0, 2))
+    out_d = net_main(x.cuda(), w=0.5, adain=True)
+    out_h = net_main.forward_host(x.pin_memory(), w=0.5, adain=True)
+    for d, h in zip(out_d, out_h):
+        assert not h.is_cuda and torch.equal(d.cpu(), h)
+
+
+def test_two_threads_share_one_net(net_main):
+    """web-demos/hugging_face/app.py:282 runs two worker threads on one net."""
+    import threading
+    x = faces_input(slice(0, 2)).cuda()
+    ref = [net_main(x[i:i + 1], w=0.5, adain=True)[0].clone() for i in range(2)]
+    res = [None, None]
+
+    def work(i):
+        for _ in range(3):
+            res[i] = net_main(x[i:i + 1], w=0.5, adain=True)[0].clone()
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    torch.cuda.synchronize()
+    assert torch.equal(res[0], ref[0]) and torch.equal(res[1], ref[1])
