@@ -33,6 +33,8 @@ SIGNATURES = {
     'cfb_net_prepare': (c_int, [_P, _P]),
     'cfb_workspace_bytes': (c_int64, [_P, c_int32]),
     'cfb_last_launch_count': (c_int64, [_P]),
+    'cfb_net_set_engine': (c_int, [_P, c_int32]),
+    'cfb_net_capture': (c_int, [_P, c_char_p, _P, c_int64]),
     'cfb_codeformer_forward': (c_int, [_P, _P, _P, _P, _P, _P, c_int32, c_float, c_int32, c_int32, _P, c_int64, _P]),
     'cfb_host_io_bytes': (c_int64, [_P, c_int32]),
     'cfb_codeformer_forward_host': (c_int, [_P, _P, _P, _P, _P, c_int32, c_float, c_int32, _P, c_int64, _P, c_int64, _P]),

@@ -270,6 +270,7 @@ class VQAutoEncoder(nn.Module):
             if not h:
                 _lib.check(1, 'cfb_net_create')
             object.__setattr__(self, '_cfb_net', ctypes.c_void_p(h))
+            _lib.check(lib.cfb_net_set_engine(self._cfb_net, getattr(self, '_cfb_engine', 0)), 'cfb_net_set_engine')
         keep = []
         for k, v in params:
             if v.device != device:
@@ -308,6 +309,21 @@ class VQAutoEncoder(nn.Module):
         if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != self.resolution or x.shape[3] != self.resolution:
             raise RuntimeError(f'expected input [B,3,{self.resolution},{self.resolution}], got {tuple(x.shape)}')
         return x.contiguous()
+
+    def set_engine(self, engine: str = 'auto'):
+        """Engine of the dense convs/linears: 'auto' (tcgen05 tensor cores wherever the shape allows), 'f32'
+        (fp32 CUDA-core implicit GEMM) or 'tc' (tcgen05 only).  Both are CUDA kernels of libcfb200."""
+        code = {'auto': 0, 'f32': 1, 'tc': 2}[engine]
+        object.__setattr__(self, '_cfb_engine', code)
+        if self._cfb_net is not None:
+            _lib.check(_lib.load().cfb_net_set_engine(self._cfb_net, code), 'cfb_net_set_engine')
+
+    def capture(self, stage: str, dst: Optional[torch.Tensor]):
+        """Parity hook (cfb_net_capture): copy the NHWC activation after ``stage`` into ``dst`` on the next forwards."""
+        if self._cfb_net is None:
+            raise RuntimeError('capture: run one forward (or load weights on the device) first')
+        _lib.check(_lib.load().cfb_net_capture(self._cfb_net, stage.encode(), _lib.ptr(dst),
+                                               0 if dst is None else dst.numel()), 'cfb_net_capture')
 
     @property
     def last_launch_count(self) -> int:

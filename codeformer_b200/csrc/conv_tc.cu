@@ -1,41 +1,519 @@
-// tcgen05 implicit-GEMM convolution engine (sm_100a) -- see conv_tc.cuh.
+// tcgen05 implicit-GEMM convolution engine for sm_100a (B200).
+//
+// Computes the 3x3 / 1x1 convolutions and linears of the CodeFormer hot path
+//   nn.Conv2d call sites      /root/reference/basicsr/archs/vqgan_arch.py:120,132,147-151,173-200,243,266,292,314
+//   Fuse_sft convs, Linear    /root/reference/basicsr/archs/codeformer_arch.py:104-106,141-149,183,192
+// as GEMMs  D[M = 128 output pixels, N = Cout tile] += A[M, K] * B[N, K]^T  with K = taps * Cin, on the
+// 5th-generation tensor cores:
+//   * operands are error-compensated fp16 pairs  x = hi + lo  (hi = fp16(x), lo = fp16(x - hi)); every k-block
+//     issues three tcgen05.mma kind::f16:  hi*hi + hi*lo + lo*hi  into ONE fp32 accumulator in TMEM
+//     (>= 21 effective mantissa bits; the 1e-3 parity bar needs >= 16);
+//   * A tiles are fetched by TMA straight from the NHWC activation planes: one 4-D box {64 ch, BW, BH, 1} per
+//     filter tap at shifted (x+s-1, y+r-1) coordinates -- out-of-bounds rows/cols are zero-filled by the TMA
+//     unit, which *is* the conv padding; the box lands in shared memory as 128 rows x 128 B in the 128B-swizzled
+//     K-major layout the UMMA descriptor expects (no im2col buffer anywhere);
+//   * B tiles ([tap][Cout][Cin] fp16) by 3-D TMA boxes {64, BN, 1};
+//   * warp-specialised persistent CTAs (1 per SM): warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc),
+//     warps 2..5 = epilogue (tcgen05.ld -> bias / residual / activation / SFT -> fp32 NHWC stores);
+//     smem ring of STAGES k-blocks (full/empty mbarriers), 2 TMEM accumulators (tmem_full/tmem_empty) so the
+//     epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include <mutex>
 
 #include "conv_tc.cuh"
 
 namespace cfb {
 
+// ------------------------------------------------------------------------------------------------------
+// weight split: OIHW fp32 -> [tap][Cout][Cin] fp16 hi/lo of (w * 2^k), k chosen so max|w| lands in [2^13,2^14)
+// (keeps `lo` out of the fp16 subnormal range); scale_slot[0] = |w|max bits, scale_slot[1] = 2^-k for the epilogue
+// ------------------------------------------------------------------------------------------------------
+__global__ void tc_absmax_kernel(const float* __restrict__ w, int64_t total, unsigned* __restrict__ slot) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(w[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(slot, __float_as_uint(m));
+}
+
 __global__ void tc_split_weights_kernel(const float* __restrict__ w, __half* __restrict__ hi, __half* __restrict__ lo,
-                                        int Cout, int Cin, int k) {
+                                        int Cout, int Cin, int k, float* __restrict__ slot) {
+  const float amax = __uint_as_float(reinterpret_cast<const unsigned*>(slot)[0]);
+  int e = 0;
+  if (amax > 0.f && isfinite(amax)) frexpf(amax, &e);
+  const float scale = exp2f((float)(14 - e));
   const int64_t total = (int64_t)Cout * Cin * k * k;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    // i indexes out [tap][co][ci]
     const int ci = (int)(i % Cin);
     const int co = (int)((i / Cin) % Cout);
     const int tap = (int)(i / ((int64_t)Cout * Cin));
-    const float v = w[((int64_t)co * Cin + ci) * k * k + tap];
+    const float v = w[((int64_t)co * Cin + ci) * k * k + tap] * scale;
     const __half h = __float2half_rn(v);
     hi[i] = h;
     lo[i] = __float2half_rn(v - __half2float(h));
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0) slot[1] = exp2f((float)(e - 14));
 }
 
-int tc_split_weights(const float* oihw, __half* hi, __half* lo, int Cout, int Cin, int k, cudaStream_t st) {
+int tc_split_weights(const float* oihw, __half* hi, __half* lo, int Cout, int Cin, int k, float* scale_slot,
+                     cudaStream_t st) {
   const int64_t total = (int64_t)Cout * Cin * k * k;
   const int64_t blocks = (total + 255) / 256;
-  tc_split_weights_kernel<<<(unsigned)(blocks > 4096 ? 4096 : blocks), 256, 0, st>>>(oihw, hi, lo, Cout, Cin, k);
+  const unsigned g = (unsigned)(blocks > 1024 ? 1024 : blocks);
+  CFB_CUDA(cudaMemsetAsync(scale_slot, 0, 2 * sizeof(float), st));
+  tc_absmax_kernel<<<g, 256, 0, st>>>(oihw, total, reinterpret_cast<unsigned*>(scale_slot));
+  CFB_LAUNCH_CHECK();
+  tc_split_weights_kernel<<<g, 256, 0, st>>>(oihw, hi, lo, Cout, Cin, k, scale_slot);
   CFB_LAUNCH_CHECK();
   return 0;
 }
 
-bool tc_supported(const ConvArgs& a) { (void)a; return false; }
-size_t tc_scratch_bytes(const ConvArgs& a) { (void)a; return 0; }
+// ------------------------------------------------------------------------------------------------------
+// operand preparation: fp32 NHWC (+ fused GroupNorm affine, SiLU, nearest x2) -> fp16 hi / lo NHWC planes
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float tc_silu(float x) { return x / (1.f + expf(-x)); }
+
+__global__ void __launch_bounds__(256) tc_prep_kernel(const float* __restrict__ in, const float* __restrict__ scale,
+                                                      const float* __restrict__ shift, int act, int up, int N, int H, int W,
+                                                      int C, __half* __restrict__ hi, __half* __restrict__ lo) {
+  const int C8 = C >> 3;
+  const int Hp = H << up, Wp = W << up;
+  const int64_t total = (int64_t)N * Hp * Wp * C8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8) * 8;
+    const int64_t pix = i / C8;
+    const int ox = (int)(pix % Wp);
+    const int oy = (int)((pix / Wp) % Hp);
+    const int n = (int)(pix / ((int64_t)Wp * Hp));
+    const float* src = in + (((int64_t)n * H + (oy >> up)) * W + (ox >> up)) * C + c;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src + 4));
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    if (scale) {
+      const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + (int64_t)n * C + c));
+      const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + (int64_t)n * C + c + 4));
+      const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + (int64_t)n * C + c));
+      const float4 h1 = __ldg(reinterpret_cast<const float4*>(shift + (int64_t)n * C + c + 4));
+      const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+      const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sv[j], hv[j]);
+    }
+    if (act == IN_SILU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = tc_silu(v[j]);
+    }
+    __align__(16) __half hh[8];
+    __align__(16) __half ll[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      hh[j] = __float2half_rn(v[j]);
+      ll[j] = __float2half_rn(v[j] - __half2float(hh[j]));
+    }
+    *reinterpret_cast<uint4*>(hi + pix * C + c) = *reinterpret_cast<const uint4*>(hh);
+    *reinterpret_cast<uint4*>(lo + pix * C + c) = *reinterpret_cast<const uint4*>(ll);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug must surface as a trap (-> cudaError, Python exception), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// K-major, 128B-swizzled operand tile (rows of 128 B, 8-row atoms 1024 B apart): cute::UMMA::SmemDescriptor
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------------
+struct TcParams {
+  int N, Ho, Wo, Cout;
+  int taps, pad;          // 9/1 (3x3 'same') or 1/0 (1x1)
+  int BW, BH;             // pixel tile = BH rows x BW cols = 128
+  int tiles_x, tiles_y;   // per image
+  int m_tiles, n_tiles;
+  int kblocks;            // Cin / 64
+  const float* bias;
+  const float* residual;
+  int out_act;
+  const float* sft_dec;
+  const float* sft_scale;
+  float sft_w;
+  const float* wscale_inv;  // device scalar: 2^-k of the weight split
+  float* out;
+};
+
+constexpr int TC_THREADS = 192;
+constexpr int TC_A_BYTES = 128 * 128;   // 128 pixels x 64 fp16
+
+template <int BN>
+struct TcCfg {
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = (BN == 64) ? 4 : ((BN == 128) ? 3 : 2);
+  static constexpr int TMEM_COLS = 2 * BN;                 // two accumulators (power of two >= 32)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const TcParams p) {
+  using Cfg = TcCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_lo) : "memory");
+    for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(full + s), 1); mbar_init(smem_u32(empty + s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(tfull + a), 1); mbar_init(smem_u32(tempty + a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int nk = p.taps * p.kblocks;
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+        const int per_img = p.tiles_x * p.tiles_y;
+        const int n = mt / per_img;
+        const int rem = mt - n * per_img;
+        const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+        const int y0 = ty * p.BH, x0 = tx * p.BW;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int r = (p.taps == 9) ? tap / 3 : 0;
+          const int s = (p.taps == 9) ? tap - r * 3 : 0;
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(smem_u32(empty + stage), phase ^ 1);
+            const uint32_t fb = smem_u32(full + stage);
+            mbar_expect_tx(fb, (uint32_t)Cfg::STAGE_BYTES);
+            const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+            tma_load_4d(sa, &tmA_hi, fb, kb * 64, x0 + s - p.pad, y0 + r - p.pad, n);
+            tma_load_4d(sa + TC_A_BYTES, &tmA_lo, fb, kb * 64, x0 + s - p.pad, y0 + r - p.pad, n);
+            tma_load_3d(sa + 2 * TC_A_BYTES, &tmB_hi, fb, kb * 64, nt * BN, tap);
+            tma_load_3d(sa + 2 * TC_A_BYTES + Cfg::B_BYTES, &tmB_lo, fb, kb * 64, nt * BN, tap);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    if (lane == 0) {
+      // kind::f16, A=B=F16 (0), D=F32 (1<<4), K-major A and B, N>>3 @17, M>>4 @24   (cute::UMMA::InstrDescriptor)
+      constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(tempty + acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int it = 0; it < nk; ++it) {
+          mbar_wait(smem_u32(full + stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {   // 64-wide k-block = 4 x UMMA_K(16); +32 B inside the swizzle atom
+            const uint64_t a_hi = umma_desc_sw128(sa + k * 32);
+            const uint64_t a_lo = umma_desc_sw128(sa + TC_A_BYTES + k * 32);
+            const uint64_t b_hi = umma_desc_sw128(sa + 2 * TC_A_BYTES + k * 32);
+            const uint64_t b_lo = umma_desc_sw128(sa + 2 * TC_A_BYTES + Cfg::B_BYTES + k * 32);
+            tc_mma_f16(d_tmem, a_lo, b_hi, idesc, (it > 0 || k > 0) ? 1u : 0u);   // small terms first
+            tc_mma_f16(d_tmem, a_hi, b_lo, idesc, 1u);
+            tc_mma_f16(d_tmem, a_hi, b_hi, idesc, 1u);
+          }
+          tc_commit(smem_u32(empty + stage));           // smem slot reusable once these MMAs have read it
+          if (it == nk - 1) tc_commit(smem_u32(tfull + acc));   // accumulator complete -> epilogue
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ============================ epilogue (warps 2..5) ============================
+    const int lg = warp & 3;                 // TMEM lane group this warp may access: lanes [32*lg, 32*lg+32)
+    const int row = lg * 32 + lane;          // pixel row of the tile
+    const float wsi = __ldg(p.wscale_inv);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      const int per_img = p.tiles_x * p.tiles_y;
+      const int n = mt / per_img;
+      const int rem = mt - n * per_img;
+      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+      const int h = row / p.BW, w = row - h * p.BW;
+      const int64_t pix = ((int64_t)n * p.Ho + (ty * p.BH + h)) * p.Wo + (tx * p.BW + w);
+      const int64_t off0 = pix * p.Cout + (int64_t)nt * BN;
+      mbar_wait(smem_u32(tfull + acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c0, r);
+        const int col = nt * BN + c0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 v = make_float4(__uint_as_float(r[j]) * wsi, __uint_as_float(r[j + 1]) * wsi,
+                                 __uint_as_float(r[j + 2]) * wsi, __uint_as_float(r[j + 3]) * wsi);
+          if (p.bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col + j));
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+          }
+          const int64_t off = off0 + c0 + j;
+          if (p.residual) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(p.residual + off));
+            v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+          }
+          if (p.out_act == OUT_LRELU) {
+            v.x = v.x > 0.f ? v.x : 0.2f * v.x; v.y = v.y > 0.f ? v.y : 0.2f * v.y;
+            v.z = v.z > 0.f ? v.z : 0.2f * v.z; v.w = v.w > 0.f ? v.w : 0.2f * v.w;
+          } else if (p.out_act == OUT_GELU) {
+            v.x = 0.5f * v.x * (1.f + erff(v.x * 0.70710678118654752440f));
+            v.y = 0.5f * v.y * (1.f + erff(v.y * 0.70710678118654752440f));
+            v.z = 0.5f * v.z * (1.f + erff(v.z * 0.70710678118654752440f));
+            v.w = 0.5f * v.w * (1.f + erff(v.w * 0.70710678118654752440f));
+          }
+          if (p.sft_dec) {
+            const float4 d = __ldg(reinterpret_cast<const float4*>(p.sft_dec + off));
+            const float4 s = __ldg(reinterpret_cast<const float4*>(p.sft_scale + off));
+            v.x = d.x + p.sft_w * (d.x * s.x + v.x); v.y = d.y + p.sft_w * (d.y * s.y + v.y);
+            v.z = d.z + p.sft_w * (d.z * s.z + v.z); v.w = d.w + p.sft_w * (d.w * s.w + v.w);
+          }
+          *reinterpret_cast<float4*>(p.out + off) = v;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(tempty + acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  CFB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUresult rc = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+                         reinterpret_cast<const cuuint64_t*>(dims), reinterpret_cast<const cuuint64_t*>(strides_bytes),
+                         reinterpret_cast<const cuuint32_t*>(box), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CFB_REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (" + std::to_string((int)rc) + ")");
+  return 0;
+}
+
+static inline int tile_bw(int Wo) { return Wo < 128 ? Wo : 128; }
+
+bool tc_supported(const ConvArgs& a) {
+  if (a.Cin % 64 != 0 || a.Cout % 64 != 0) return false;
+  if (!(a.ksize == 1 || a.ksize == 3)) return false;
+  if (!(a.mode == CONV_SAME || a.mode == CONV_UP)) return false;
+  if (a.Wo < 1 || a.Ho < 1) return false;
+  const int BW = tile_bw(a.Wo);
+  if (128 % BW != 0 || a.Wo % BW != 0) return false;
+  const int BH = 128 / BW;
+  if (a.Ho % BH != 0) return false;
+  if ((int64_t)a.N * (a.Ho / BH) * (a.Wo / BW) * (a.Cout / 64) > 0x7fffffffLL) return false;
+  return true;
+}
+
+size_t tc_scratch_bytes(const ConvArgs& a) {
+  if (!tc_supported(a)) return 0;
+  const size_t plane = ((size_t)a.N * a.Ho * a.Wo * a.Cin * 2 + 1023) / 1024 * 1024;   // operand planes have the OUTPUT size
+  return 2 * plane;
+}
+
+template <int BN>
+static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                     const TcParams& p, int sm_count, cudaStream_t st) {
+  using Cfg = TcCfg<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CFB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int total = p.m_tiles * p.n_tiles;
+  const int grid = total < sm_count ? total : sm_count;
+  conv_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(a_hi, a_lo, b_hi, b_lo, p);
+  CFB_LAUNCH_CHECK();
+  return 0;
+}
+
 int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
-  (void)a; (void)scratch; (void)sm_count; (void)st;
-  set_error("conv_tc: tcgen05 engine not built yet");
-  return 1;
+  CFB_REQUIRE(tc_supported(a), "conv_tc: unsupported shape");
+  CFB_REQUIRE(a.wgt_hi && a.wgt_lo && a.wscale_inv, "conv_tc: split weights missing");
+  const int64_t M = (int64_t)a.N * a.Ho * a.Wo;
+  if (M == 0) return 0;
+  // ---- operand planes (fp16 hi/lo, NHWC at the conv's output resolution)
+  const size_t plane = ((size_t)M * a.Cin * 2 + 1023) / 1024 * 1024;
+  __half* hi = (__half*)scratch;
+  __half* lo = (__half*)((char*)scratch + plane);
+  {
+    const int64_t total = M * (a.Cin / 8);
+    const int64_t blocks = (total + 255) / 256;
+    tc_prep_kernel<<<(unsigned)(blocks > 148 * 32 ? 148 * 32 : blocks), 256, 0, st>>>(
+        a.in, a.in_scale, a.in_shift, a.in_act, a.mode == CONV_UP ? 1 : 0, a.N, a.H, a.W, a.Cin, hi, lo);
+    CFB_LAUNCH_CHECK();
+  }
+  // ---- tensor maps
+  const int BW = tile_bw(a.Wo), BH = 128 / BW;
+  const int BN = (a.Cout % 128 == 0) ? 128 : 64;
+  CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
+  {
+    const uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)a.Wo, (uint64_t)a.Ho, (uint64_t)a.N};
+    const uint64_t str[3] = {(uint64_t)a.Cin * 2, (uint64_t)a.Wo * a.Cin * 2, (uint64_t)a.Ho * a.Wo * a.Cin * 2};
+    const uint32_t box[4] = {64, (uint32_t)BW, (uint32_t)BH, 1};
+    CFB_CHECK(make_map(&mA_hi, hi, 4, dims, str, box));
+    CFB_CHECK(make_map(&mA_lo, lo, 4, dims, str, box));
+  }
+  {
+    const int taps = a.ksize * a.ksize;
+    const uint64_t dims[3] = {(uint64_t)a.Cin, (uint64_t)a.Cout, (uint64_t)taps};
+    const uint64_t str[2] = {(uint64_t)a.Cin * 2, (uint64_t)a.Cout * a.Cin * 2};
+    const uint32_t box[3] = {64, (uint32_t)BN, 1};
+    CFB_CHECK(make_map(&mB_hi, a.wgt_hi, 3, dims, str, box));
+    CFB_CHECK(make_map(&mB_lo, a.wgt_lo, 3, dims, str, box));
+  }
+  TcParams p;
+  p.N = a.N; p.Ho = a.Ho; p.Wo = a.Wo; p.Cout = a.Cout;
+  p.taps = a.ksize * a.ksize; p.pad = a.ksize / 2;
+  p.BW = BW; p.BH = BH; p.tiles_x = a.Wo / BW; p.tiles_y = a.Ho / BH;
+  p.m_tiles = a.N * p.tiles_x * p.tiles_y; p.n_tiles = a.Cout / BN; p.kblocks = a.Cin / 64;
+  p.bias = a.bias; p.residual = a.residual; p.out_act = a.out_act;
+  p.sft_dec = a.sft_dec; p.sft_scale = a.sft_scale; p.sft_w = a.sft_w; p.wscale_inv = a.wscale_inv; p.out = a.out;
+  if (BN == 128) return launch_tc<128>(mA_hi, mA_lo, mB_hi, mB_lo, p, sm_count, st);
+  return launch_tc<64>(mA_hi, mA_lo, mB_hi, mB_lo, p, sm_count, st);
 }
 
 }  // namespace cfb

@@ -6,8 +6,9 @@
 #include "kernels.cuh"
 
 namespace cfb {
-// OIHW fp32 -> [taps][Cout][Cin] fp16 hi / lo with hi = fp16(w), lo = fp16(w - hi)
-int tc_split_weights(const float* oihw, __half* hi, __half* lo, int Cout, int Cin, int k, cudaStream_t st);
+// OIHW fp32 -> [taps][Cout][Cin] fp16 hi / lo of w*2^k (hi = fp16(.), lo = fp16(. - hi)); scale_slot = 2 device floats,
+// [1] receives 2^-k for the epilogue
+int tc_split_weights(const float* oihw, __half* hi, __half* lo, int Cout, int Cin, int k, float* scale_slot, cudaStream_t st);
 bool tc_supported(const ConvArgs& a);
 size_t tc_scratch_bytes(const ConvArgs& a);   // operand (hi/lo fp16 activation planes) staging
 int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st);

@@ -59,6 +59,7 @@ struct ConvArgs {
   const float* wgt_f32 = nullptr;   // [taps][Cin][Cout] fp32 (CUDA-core engine)
   const void* wgt_hi = nullptr;     // [taps][Cout][Cin] fp16 hi   (tensor-core engine)
   const void* wgt_lo = nullptr;     // [taps][Cout][Cin] fp16 lo
+  const float* wscale_inv = nullptr; // device scalar 2^-k undoing the power-of-two scaling of the fp16 weight split
   const float* bias = nullptr;      // [Cout] | null
   const float* in_scale = nullptr;  // [N,Cin] fused per-sample affine (GroupNorm folded) | null
   const float* in_shift = nullptr;

@@ -101,6 +101,7 @@ struct ConvW {
   __half* w_hi = nullptr;        // [taps][cout][cin]
   __half* w_lo = nullptr;
   float* bias = nullptr;
+  float* wscale = nullptr;       // 2 floats: [0] scratch |w|max, [1] 2^-k of the fp16 split
 };
 struct NormW { std::string name; int c = 0; const float* gamma = nullptr; const float* beta = nullptr; };
 struct ResW { NormW n1, n2; ConvW c1, c2, co; bool has_out = false; };
@@ -136,6 +137,8 @@ struct cfb_net {
   // small owned copies of norm params etc. live in the slab too
   std::vector<std::pair<const float**, std::pair<std::string, int64_t>>> vec_params;  // (dst, (name, numel))
   std::vector<ConvW*> convs;
+  int engine = 0;                     // 0 auto (tcgen05 where the shape allows), 1 fp32 CUDA cores, 2 tcgen05 only
+  std::map<std::string, std::pair<float*, int64_t>> captures;   // stage name -> (device dst, capacity in floats)
 };
 
 namespace cfb {
@@ -320,7 +323,7 @@ static int prepare(cfb_net* n, cudaStream_t st) {
   size_t total = 0;
   for (ConvW* c : n->convs) {
     const size_t wn = (size_t)c->cout * c->cin * c->k * c->k;
-    total += align256(wn * 4) + 2 * align256(wn * 2) + align256((size_t)c->cout * 4);
+    total += align256(wn * 4) + 2 * align256(wn * 2) + align256((size_t)c->cout * 4) + 256;
   }
   for (auto& v : n->vec_params) total += align256((size_t)v.second.second * 4);
   total += align256((size_t)n->cfg.codebook_size * n->cfg.emb_dim * 4);
@@ -346,8 +349,9 @@ static int prepare(cfb_net* n, cudaStream_t st) {
     c->w_hi = (__half*)take(wn * 2);
     c->w_lo = (__half*)take(wn * 2);
     c->bias = (float*)take((size_t)c->cout * 4);
+    c->wscale = (float*)take(8);
     CFB_CHECK(relayout_oihw_to_tck(c->src_w, c->w_f32, c->cout, c->cin, c->k, st));
-    CFB_CHECK(tc_split_weights(c->src_w, c->w_hi, c->w_lo, c->cout, c->cin, c->k, st));
+    CFB_CHECK(tc_split_weights(c->src_w, c->w_hi, c->w_lo, c->cout, c->cin, c->k, c->wscale, st));
     if (c->has_bias) CFB_CUDA(cudaMemcpyAsync(c->bias, c->src_b, (size_t)c->cout * 4, cudaMemcpyDeviceToDevice, st));
     else CFB_CUDA(cudaMemsetAsync(c->bias, 0, (size_t)c->cout * 4, st));
   }
@@ -402,6 +406,16 @@ struct Fwd {
   void release(Tensor& t) { if (t.owned && t.p) ar.release(t.p); t.p = nullptr; }
   void release_raw(void* p) { ar.release(p); }
 
+  // debug/parity hook: copy a stage's NHWC activation out (cfb_net_capture)
+  int capture(const std::string& stage, const Tensor& t) {
+    if (dry || n->captures.empty()) return 0;
+    auto it = n->captures.find(stage);
+    if (it == n->captures.end()) return 0;
+    CFB_REQUIRE(it->second.second >= t.numel(), "capture buffer too small for stage " + stage);
+    CFB_CUDA(cudaMemcpyAsync(it->second.first, t.p, (size_t)t.numel() * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
+
   struct ConvOpt {
     int mode = CONV_SAME;
     const float* in_scale = nullptr; const float* in_shift = nullptr; int in_act = IN_NONE;
@@ -419,7 +433,7 @@ struct Fwd {
     else CFB_CHECK(alloc(out, in.N, Ho, Wo, w.cout));
     ConvArgs a;
     a.in = in.p; a.N = in.N; a.H = in.H; a.W = in.W; a.Cin = in.C; a.Ho = Ho; a.Wo = Wo; a.Cout = w.cout;
-    a.ksize = w.k; a.mode = o.mode; a.wgt_f32 = w.w_f32; a.wgt_hi = w.w_hi; a.wgt_lo = w.w_lo; a.bias = w.bias;
+    a.ksize = w.k; a.mode = o.mode; a.wgt_f32 = w.w_f32; a.wgt_hi = w.w_hi; a.wgt_lo = w.w_lo; a.wscale_inv = w.wscale + 1; a.bias = w.bias;
     a.in_scale = o.in_scale; a.in_shift = o.in_shift; a.in_act = o.in_act; a.residual = o.residual;
     a.out_act = o.out_act; a.sft_dec = o.sft_dec; a.sft_scale = o.sft_scale; a.sft_w = o.sft_w; a.out = out.p;
     bool use_tc = engine == 2 || (engine == 0 && n->tc_ok && tc_supported(a));
@@ -517,6 +531,7 @@ struct Fwd {
     Tensor x;
     CFB_CHECK(alloc(x, B, c.img_size, c.img_size, c.nf));
     if (!dry) CFB_CHECK(conv_first(x_nchw, n->enc[0].conv.w_f32, n->enc[0].conv.bias, x.p, B, c.img_size, c.img_size, c.nf, st));
+    CFB_CHECK(capture("enc.0", x));
     float *ps = nullptr, *ph = nullptr;   // pending GroupNorm of a 'norm' block
     for (size_t i = 1; i < n->enc.size(); ++i) {
       const Block& b = n->enc[i];
@@ -536,6 +551,7 @@ struct Fwd {
       }
       release(x);
       x = y;
+      CFB_CHECK(capture("enc." + std::to_string(i), x));
       for (int tb : tap_blocks)
         if ((int)i == tb && taps) { x.owned = false; (*taps)[x.W] = x; (*taps)[x.W].owned = true; }
     }
@@ -570,6 +586,7 @@ struct Fwd {
       }
       release(x);
       x = y;
+      CFB_CHECK(capture("gen." + std::to_string(i), x));
       if (taps && w > 0.f)
         for (int fb : fuse_blocks)
           if ((int)i == fb) {
@@ -582,6 +599,7 @@ struct Fwd {
             release(x);
             release(it->second);
             x = fz;
+            CFB_CHECK(capture("fuse." + std::to_string(x.W), x));
           }
     }
     CFB_REQUIRE(false, "generator: plan does not end with a conv");
@@ -618,6 +636,7 @@ struct Fwd {
       { ConvOpt o; o.residual = x2.p; CFB_CHECK(conv(L.l2, hdn, x3, o)); }
       release(hdn); release(x2);
       x = x3;
+      CFB_CHECK(capture("ft." + std::to_string((int)(&L - &n->layers[0])), x));
     }
     Tensor t2, lg;
     CFB_CHECK(alloc(t2, B, lq.H, lq.W, E));
@@ -648,7 +667,7 @@ static int codeformer_forward_impl(cfb_net* n, const float* x, float* out, float
   CFB_REQUIRE(B >= 0, "negative batch");
   if (B == 0) return 0;
   n->arena.reset(ws, (size_t)ws_bytes, dry);
-  Fwd f{n, st, n->arena, dry, 0};
+  Fwd f{n, st, n->arena, dry, n->engine};
   const cfb_config& c = n->cfg;
   std::map<int, Tensor> taps;
   Tensor lq;
@@ -675,6 +694,7 @@ static int codeformer_forward_impl(cfb_net* n, const float* x, float* out, float
     f.release(quant);
     quant = q2;
   }
+  CFB_CHECK(f.capture("quant", quant));
   f.release(lq);
   CFB_CHECK(f.generator(quant, out, want_taps ? &taps : nullptr, tap_blocks_of(c, false), w));
   return 0;
@@ -685,7 +705,7 @@ static int vqae_forward_impl(cfb_net* n, const float* x, float* out, int64_t* id
   CFB_REQUIRE(dry || n->prepared, "cfb_net_prepare has not been called");
   if (B == 0) return 0;
   n->arena.reset(ws, (size_t)ws_bytes, dry);
-  Fwd f{n, st, n->arena, dry, 0};
+  Fwd f{n, st, n->arena, dry, n->engine};
   const cfb_config& c = n->cfg;
   Tensor z;
   CFB_CHECK(f.encoder(x, B, z, nullptr, {}));
@@ -793,6 +813,25 @@ int64_t cfb_workspace_bytes(cfb_net* n, int32_t batch) {
 }
 
 int64_t cfb_last_launch_count(cfb_net* n) { return n ? n->last_launches : 0; }
+
+int cfb_net_set_engine(cfb_net* n, int32_t engine) {
+  API_BEGIN
+  CFB_REQUIRE(n && engine >= 0 && engine <= 2, "cfb_net_set_engine: engine must be 0 (auto), 1 (fp32) or 2 (tcgen05)");
+  std::lock_guard<std::mutex> lk(n->mu);
+  n->engine = engine;
+  return 0;
+  API_END(1)
+}
+
+int cfb_net_capture(cfb_net* n, const char* stage, float* dst, int64_t capacity) {
+  API_BEGIN
+  CFB_REQUIRE(n && stage, "cfb_net_capture: NULL argument");
+  std::lock_guard<std::mutex> lk(n->mu);
+  if (dst) n->captures[stage] = {dst, capacity};
+  else n->captures.erase(stage);
+  return 0;
+  API_END(1)
+}
 
 int cfb_codeformer_forward(cfb_net* n, const float* x, float* out, float* logits, float* lq_feat, int64_t* top_idx,
                            int32_t batch, float w, int32_t adain, int32_t code_only, void* workspace,
@@ -907,7 +946,7 @@ int64_t cfb_conv2d_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t cin,
   a.Ho = mode == cfb::CONV_DOWN ? h / 2 : (mode == cfb::CONV_UP ? h * 2 : h);
   a.Wo = mode == cfb::CONV_DOWN ? w / 2 : (mode == cfb::CONV_UP ? w * 2 : w);
   const size_t wn = (size_t)cout * cin * ksize * ksize;
-  return (int64_t)(align256(wn * 4) + 2 * align256(wn * 2) + cfb::tc_scratch_bytes(a) + 8192);
+  return (int64_t)(align256(wn * 4) + 2 * align256(wn * 2) + 256 + cfb::tc_scratch_bytes(a) + 8192);
 }
 
 int cfb_conv2d_nhwc(const float* in, const float* weight_oihw, const float* bias, float* out, int32_t n, int32_t h,
@@ -929,8 +968,9 @@ int cfb_conv2d_nhwc(const float* in, const float* weight_oihw, const float* bias
   float* wf = (float*)p; p += align256(wn * 4);
   __half* whi = (__half*)p; p += align256(wn * 2);
   __half* wlo = (__half*)p; p += align256(wn * 2);
+  float* wsc = (float*)p; p += 256;
   p = (char*)(((uintptr_t)p + 1023) / 1024 * 1024);
-  a.wgt_f32 = wf; a.wgt_hi = whi; a.wgt_lo = wlo;
+  a.wgt_f32 = wf; a.wgt_hi = whi; a.wgt_lo = wlo; a.wscale_inv = wsc + 1;
   bool use_tc = engine == 2;
   if (engine == 0) {
     int dev = 0, major = 0;
@@ -943,7 +983,7 @@ int cfb_conv2d_nhwc(const float* in, const float* weight_oihw, const float* bias
     int dev = 0, sms = 148;
     CFB_CUDA(cudaGetDevice(&dev));
     CFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    CFB_CHECK(cfb::tc_split_weights(weight_oihw, whi, wlo, cout, cin, ksize, st));
+    CFB_CHECK(cfb::tc_split_weights(weight_oihw, whi, wlo, cout, cin, ksize, wsc, st));
     CFB_CHECK(cfb::conv_tc(a, p, sms, st));
   } else {
     CFB_CHECK(cfb::relayout_oihw_to_tck(weight_oihw, wf, cout, cin, ksize, st));

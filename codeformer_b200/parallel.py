@@ -1,0 +1,57 @@
+"""Multi-GPU execution of the hot path: pure data parallelism over faces.
+
+Every face is independent through the whole forward (GroupNorm / LayerNorm / AdaIN / attention are per
+sample), so the batch is split contiguously across ranks -- rank r owns faces
+[r*B/n, (r+1)*B/n) -- the weights are replicated, and the path has exactly ONE collective: the all-gather of
+`out` that collates the result.  One process per GPU (torchrun), ``torch.distributed`` NCCL over
+NVLink 5 / NVSwitch; ``gloo`` works for CPU tests of the host logic.
+The reference itself has no multi-GPU inference (its DDP is training-only, basicsr/models/base_model.py:71-76).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(batch: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced split of ``batch`` faces: the first ``batch % world`` ranks get one extra face."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f'bad rank/world {rank}/{world}')
+    base, extra = divmod(batch, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def gather_faces(local: torch.Tensor, batch: int, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """All-gather per-rank results ``[b_r, ...]`` into the full ``[batch, ...]`` tensor on every rank.
+    Equal shards use one ``all_gather_into_tensor`` (a single NCCL kernel); ragged shards are padded to the
+    largest shard for the collective and trimmed afterwards."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    sizes = [shard_bounds(batch, r, world)[1] - shard_bounds(batch, r, world)[0] for r in range(world)]
+    if local.shape[0] != sizes[rank]:
+        raise RuntimeError(f'rank {rank} holds {local.shape[0]} faces, expected {sizes[rank]}')
+    mx = max(sizes)
+    if mx == 0:
+        return local.new_empty((0,) + tuple(local.shape[1:]))
+    buf = local
+    if local.shape[0] != mx:
+        buf = local.new_zeros((mx,) + tuple(local.shape[1:]))
+        buf[:local.shape[0]] = local
+    out = local.new_empty((world * mx,) + tuple(local.shape[1:]))
+    dist.all_gather_into_tensor(out, buf.contiguous(), group=group)
+    if all(s == mx for s in sizes):
+        return out
+    return torch.cat([out[r * mx:r * mx + sizes[r]] for r in range(world)], dim=0)
+
+
+def sharded_forward(net, x_full: torch.Tensor, group: Optional[dist.ProcessGroup] = None, **fwd_kwargs) -> torch.Tensor:
+    """Run ``net`` on this rank's shard of ``x_full`` (same tensor on every rank) and return the gathered
+    restored faces ``[B,3,512,512]``."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    lo, hi = shard_bounds(x_full.shape[0], rank, world)
+    out = net(x_full[lo:hi], **fwd_kwargs)[0]
+    return gather_faces(out, x_full.shape[0], group)

@@ -69,6 +69,12 @@ void     cfb_net_destroy(cfb_net* net);
 int      cfb_net_set_param(cfb_net* net, const char* name, const float* dev_ptr, int64_t numel);
 int      cfb_net_prepare(cfb_net* net, void* stream);          /* errors if any key is missing */
 int64_t  cfb_workspace_bytes(cfb_net* net, int32_t batch);     /* scratch needed for a forward at this batch; <0 on error */
+/* engine of the dense convolutions / linears: 0 = auto (tcgen05 tensor cores wherever the shape allows, default),
+ * 1 = fp32 CUDA-core implicit GEMM everywhere, 2 = tcgen05 only (unsupported shapes are an error) */
+int      cfb_net_set_engine(cfb_net* net, int32_t engine);
+/* parity hook: after stage `name` ("enc.<i>", "gen.<i>", "fuse.<size>", "ft.<l>", "quant") of the next forwards, copy
+ * that NHWC fp32 activation to dst (device, `capacity` floats).  dst = NULL removes the hook. */
+int      cfb_net_capture(cfb_net* net, const char* stage, float* dst, int64_t capacity);
 /* number of kernel launches the last forward on this net enqueued (bench.py "gpu_launches") */
 int64_t  cfb_last_launch_count(cfb_net* net);
 

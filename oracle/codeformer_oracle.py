@@ -173,11 +173,15 @@ def run_block(sd: SD, p: str, kind: str, x: Tensor) -> Tensor:
     raise ValueError(kind)
 
 
-def encoder_forward(sd: SD, x: Tensor, taps: Sequence[int] = ()) -> Tuple[Tensor, Dict[str, Tensor]]:
-    """``Encoder.forward`` (vqgan_arch.py:269-273) + the taps of codeformer_arch.py:226-230."""
+def encoder_forward(sd: SD, x: Tensor, taps: Sequence[int] = (), collect: Optional[dict] = None
+                    ) -> Tuple[Tensor, Dict[str, Tensor]]:
+    """``Encoder.forward`` (vqgan_arch.py:269-273) + the taps of codeformer_arch.py:226-230.
+    ``collect`` (tests): every block output is stored under 'enc.<i>'."""
     feats: Dict[str, Tensor] = {}
     for i, (kind, _, _) in enumerate(encoder_plan()):
         x = run_block(sd, f'encoder.blocks.{i}', kind, x)
+        if collect is not None:
+            collect[f'enc.{i}'] = x
         if i in taps:
             feats[str(x.shape[-1])] = x.clone()
     return x, feats
@@ -293,15 +297,17 @@ def n_layers_of(sd: SD) -> int:
 
 def codeformer_forward(sd: SD, x: Tensor, w: float = 0, code_only: bool = False, adain_on: bool = False,
                        connect_list: Sequence[str] = ('32', '64', '128', '256'), n_head: int = 8,
-                       return_intermediates: bool = False):
+                       return_intermediates: bool = False, collect: Optional[dict] = None):
     """``CodeFormer.forward`` -- codeformer_arch.py:223-280."""
     taps = [FUSE_ENCODER_BLOCK[s] for s in connect_list]
-    lq_feat, enc_feats = encoder_forward(sd, x, taps)
+    lq_feat, enc_feats = encoder_forward(sd, x, taps, collect)
     B = x.shape[0]
     pos = sd['position_emb'].unsqueeze(1).repeat(1, B, 1)                                  # :235
     q = F.linear(lq_feat.flatten(2).permute(2, 0, 1), sd['feat_emb.weight'], sd['feat_emb.bias'])  # :237
     for l in range(n_layers_of(sd)):                                                        # :240-241
         q = transformer_layer(sd, f'ft_layers.{l}', q, pos, n_head)
+        if collect is not None:
+            collect[f'ft.{l}'] = q
     E = q.shape[-1]
     logits = F.linear(F.layer_norm(q, (E,), sd['idx_pred_layer.0.weight'], sd['idx_pred_layer.0.bias']),
                       sd['idx_pred_layer.1.weight'])                                        # :244
@@ -314,14 +320,20 @@ def codeformer_forward(sd: SD, x: Tensor, w: float = 0, code_only: bool = False,
     if adain_on:
         quant = adain(quant, lq_feat)                                                       # :266
     x = quant
+    if collect is not None:
+        collect['quant'] = quant
     fuse = [FUSE_GENERATOR_BLOCK[s] for s in connect_list]
     inter = {}
     for i, (kind, _, _) in enumerate(generator_plan()):                                     # :272-277
         x = run_block(sd, f'generator.blocks.{i}', kind, x)
+        if collect is not None:
+            collect[f'gen.{i}'] = x
         if i in fuse:
             size = str(x.shape[-1])
             if w > 0:
                 x = fuse_sft(sd, f'fuse_convs_dict.{size}', enc_feats[size], x, w)
+                if collect is not None:
+                    collect[f'fuse.{size}'] = x
     if return_intermediates:
         inter.update(top_idx=top_idx, quant=quant, enc_feats=enc_feats)
         return x, logits, lq_feat, inter

@@ -50,7 +50,9 @@ def gn_coef(x_nchw, gamma, beta, groups=32, eps=1e-6):
     shift = torch.empty((N, C), device='cuda')
     wsb = lib.cfb_gn_workspace_bytes(N, H * W, C)
     ws = torch.empty(int(wsb), dtype=torch.uint8, device='cuda')
-    _lib.check(lib.cfb_group_norm_coef(_lib.ptr(xin), _lib.ptr(gamma.cuda()), _lib.ptr(beta.cuda()), _lib.ptr(scale),
+    g_d, b_d = gamma.cuda(), beta.cuda()        # keep alive: ptr() of a temporary dangles once it is freed
+    _lib.check(lib.cfb_group_norm_coef(_lib.ptr(xin), _lib.ptr(g_d), _lib.ptr(b_d), _lib.ptr(scale),
                                        _lib.ptr(shift), N, H * W, C, groups, eps, _lib.ptr(ws), wsb, stream()),
                'cfb_group_norm_coef')
+    torch.cuda.synchronize()
     return xin, scale, shift

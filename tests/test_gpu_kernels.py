@@ -103,7 +103,8 @@ def test_attention_core(heads, d):
     ref = (F.softmax(qh @ kh.transpose(-1, -2) * scale, dim=-1) @ vh).transpose(1, 2).reshape(B, S, E)
     out = torch.empty(B, S, E, device='cuda')
     lib = _lib.load()
-    _lib.check(lib.cfb_attention(_lib.ptr(q.cuda()), _lib.ptr(k.cuda()), _lib.ptr(v.cuda()), _lib.ptr(out), B, S, heads, d,
+    qd, kd, vd = q.cuda(), k.cuda(), v.cuda()          # keep device copies alive across the call
+    _lib.check(lib.cfb_attention(_lib.ptr(qd), _lib.ptr(kd), _lib.ptr(vd), _lib.ptr(out), B, S, heads, d,
                                  E, E, E, E, scale, G.stream()))
     assert maxabs(out.cpu(), ref) < 2e-5
 
@@ -115,8 +116,9 @@ def test_layer_norm_and_pos():
     ref = F.layer_norm(x, (C,), g, b)
     y, y2 = torch.empty(T, C, device='cuda'), torch.empty(T, C, device='cuda')
     lib = _lib.load()
-    _lib.check(lib.cfb_layer_norm(_lib.ptr(x.cuda()), _lib.ptr(g.cuda()), _lib.ptr(b.cuda()), _lib.ptr(y), _lib.ptr(y2),
-                                  _lib.ptr(pos.cuda()), 256, T, C, G.stream()))
+    xd, gd, bd, pd = x.cuda(), g.cuda(), b.cuda(), pos.cuda()
+    _lib.check(lib.cfb_layer_norm(_lib.ptr(xd), _lib.ptr(gd), _lib.ptr(bd), _lib.ptr(y), _lib.ptr(y2),
+                                  _lib.ptr(pd), 256, T, C, G.stream()))
     assert maxabs(y.cpu(), ref) < 5e-6
     assert maxabs(y2.cpu(), ref + pos.repeat(2, 1)) < 5e-6
 
@@ -126,7 +128,8 @@ def test_adain_and_layout():
     c, s = _rand(2, 256, 16, 16, seed=1), _rand(2, 256, 16, 16, seed=2) * 3 + 1
     out = torch.empty(2, 16, 16, 256, device='cuda')
     lib = _lib.load()
-    _lib.check(lib.cfb_adain_nhwc(_lib.ptr(G.nhwc(c)), _lib.ptr(G.nhwc(s)), _lib.ptr(out), 2, 256, 256, G.stream()))
+    cd, sdv = G.nhwc(c), G.nhwc(s)
+    _lib.check(lib.cfb_adain_nhwc(_lib.ptr(cd), _lib.ptr(sdv), _lib.ptr(out), 2, 256, 256, G.stream()))
     assert maxabs(G.nchw(out).cpu(), O.adain(c, s)) < 2e-5
     x = _rand(3, 40, 7, 9, seed=3).cuda()
     y = torch.empty(3, 63, 40, device='cuda')
