@@ -22,6 +22,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "conv_tc.cuh"
@@ -199,11 +201,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // ------------------------------------------------------------------------------------------------------
 struct TcParams {
   int N, Ho, Wo, Cout;
-  int taps, pad;          // 9/1 (3x3 'same') or 1/0 (1x1)
+  int taps, pad, stride;  // 9/1/1 (3x3 'same'), 1/0/1 (1x1), 9/0/2 (Downsample: pad right/bottom = TMA OOB zero fill)
   int BW, BH;             // pixel tile = BH rows x BW cols = 128
   int tiles_x, tiles_y;   // per image
   int m_tiles, n_tiles;
   int kblocks;            // Cin / 64
+  int chunk;              // k-blocks accumulated in TMEM before the partial sum is folded into registers
   const float* bias;
   const float* residual;
   int out_act;
@@ -216,16 +219,22 @@ struct TcParams {
 
 constexpr int TC_THREADS = 192;
 constexpr int TC_A_BYTES = 128 * 128;   // 128 pixels x 64 fp16
+constexpr int TC_SLOTS = 4;             // TMEM partial-sum ring
 
 template <int BN>
 struct TcCfg {
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
-  static constexpr int STAGES = (BN == 64) ? 4 : ((BN == 128) ? 3 : 2);
-  static constexpr int TMEM_COLS = 2 * BN;                 // two accumulators (power of two >= 32)
+  static constexpr int STAGES = (BN == 64) ? 4 : 3;
+  static constexpr int TMEM_COLS = TC_SLOTS * BN;          // 256 or 512 columns (power of two)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+// Accumulation scheme (why the TMEM ring): tcgen05.mma adds into its fp32 accumulator with truncation, so a long
+// K loop into one accumulator drifts by ~(#MMAs)*2^-25 relative (measured 2e-5 at K=4608 -- too much for the
+// 1e-3 end-to-end bar).  Each TMEM slot therefore only receives `chunk` k-blocks (64 K-elements each), the small
+// cross terms (lo*hi, hi*lo) are issued first while the slot is still tiny, and the epilogue warps fold every
+// finished slot into fp32 registers with round-to-nearest adds while the tensor core fills the next slot.
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -237,9 +246,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
-  uint64_t* tfull = bars + 2 * STAGES;
-  uint64_t* tempty = bars + 2 * STAGES + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* cfull = bars + 2 * STAGES;
+  uint64_t* cempty = bars + 2 * STAGES + TC_SLOTS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * TC_SLOTS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -249,7 +258,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_hi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_lo) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(full + s), 1); mbar_init(smem_u32(empty + s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(tfull + a), 1); mbar_init(smem_u32(tempty + a), 4); }
+    for (int a = 0; a < TC_SLOTS; ++a) { mbar_init(smem_u32(cfull + a), 1); mbar_init(smem_u32(cempty + a), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -277,7 +286,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int n = mt / per_img;
         const int rem = mt - n * per_img;
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-        const int y0 = ty * p.BH, x0 = tx * p.BW;
+        const int y0 = ty * p.BH * p.stride, x0 = tx * p.BW * p.stride;
         for (int tap = 0; tap < p.taps; ++tap) {
           const int r = (p.taps == 9) ? tap / 3 : 0;
           const int s = (p.taps == 9) ? tap - r * 3 : 0;
@@ -302,31 +311,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
+      int slot = 0;
+      uint32_t slot_phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(smem_u32(tempty + acc), acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int it = 0; it < nk; ++it) {
-          mbar_wait(smem_u32(full + stage), phase);
+        for (int it0 = 0; it0 < nk; it0 += p.chunk) {
+          mbar_wait(smem_u32(cempty + slot), slot_phase ^ 1);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(slot * BN);
+          const int it1 = (it0 + p.chunk < nk) ? it0 + p.chunk : nk;
+          for (int it = it0; it < it1; ++it) {
+            mbar_wait(smem_u32(full + stage), phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+            const uint32_t a_hi = sa, a_lo = sa + TC_A_BYTES, b_hi = sa + 2 * TC_A_BYTES,
+                           b_lo = sa + 2 * TC_A_BYTES + Cfg::B_BYTES;
+            // 64-wide k-block = 4 x UMMA_K(16): +32 B inside the 128B swizzle atom.  Cross terms first.
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {   // 64-wide k-block = 4 x UMMA_K(16); +32 B inside the swizzle atom
-            const uint64_t a_hi = umma_desc_sw128(sa + k * 32);
-            const uint64_t a_lo = umma_desc_sw128(sa + TC_A_BYTES + k * 32);
-            const uint64_t b_hi = umma_desc_sw128(sa + 2 * TC_A_BYTES + k * 32);
-            const uint64_t b_lo = umma_desc_sw128(sa + 2 * TC_A_BYTES + Cfg::B_BYTES + k * 32);
-            tc_mma_f16(d_tmem, a_lo, b_hi, idesc, (it > 0 || k > 0) ? 1u : 0u);   // small terms first
-            tc_mma_f16(d_tmem, a_hi, b_lo, idesc, 1u);
-            tc_mma_f16(d_tmem, a_hi, b_hi, idesc, 1u);
+            for (int k = 0; k < 4; ++k) {
+              tc_mma_f16(d_tmem, umma_desc_sw128(a_lo + k * 32), umma_desc_sw128(b_hi + k * 32), idesc,
+                         (it > it0 || k > 0) ? 1u : 0u);
+              tc_mma_f16(d_tmem, umma_desc_sw128(a_hi + k * 32), umma_desc_sw128(b_lo + k * 32), idesc, 1u);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma_f16(d_tmem, umma_desc_sw128(a_hi + k * 32), umma_desc_sw128(b_hi + k * 32), idesc, 1u);
+            tc_commit(smem_u32(empty + stage));           // smem slot reusable once these MMAs have read it
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          tc_commit(smem_u32(empty + stage));           // smem slot reusable once these MMAs have read it
-          if (it == nk - 1) tc_commit(smem_u32(tfull + acc));   // accumulator complete -> epilogue
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          tc_commit(smem_u32(cfull + slot));              // partial sum complete -> epilogue warps fold it
+          if (++slot == TC_SLOTS) { slot = 0; slot_phase ^= 1; }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
@@ -334,9 +348,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int lg = warp & 3;                 // TMEM lane group this warp may access: lanes [32*lg, 32*lg+32)
     const int row = lg * 32 + lane;          // pixel row of the tile
     const float wsi = __ldg(p.wscale_inv);
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    int slot = 0;
+    uint32_t slot_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      float acc[BN];
+#pragma unroll
+      for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+      for (int it0 = 0; it0 < nk; it0 += p.chunk) {
+        mbar_wait(smem_u32(cfull + slot), slot_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(slot * BN);
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c0, r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(cempty + slot));
+        if (++slot == TC_SLOTS) { slot = 0; slot_phase ^= 1; }
+      }
+      // ---- finalize this tile: scale, bias, residual, activation, SFT, store (fp32 NHWC)
       const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
       const int per_img = p.tiles_x * p.tiles_y;
       const int n = mt / per_img;
@@ -345,49 +379,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const int h = row / p.BW, w = row - h * p.BW;
       const int64_t pix = ((int64_t)n * p.Ho + (ty * p.BH + h)) * p.Wo + (tx * p.BW + w);
       const int64_t off0 = pix * p.Cout + (int64_t)nt * BN;
-      mbar_wait(smem_u32(tfull + acc), acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c0, r);
-        const int col = nt * BN + c0;
+      const int col0 = nt * BN;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 v = make_float4(__uint_as_float(r[j]) * wsi, __uint_as_float(r[j + 1]) * wsi,
-                                 __uint_as_float(r[j + 2]) * wsi, __uint_as_float(r[j + 3]) * wsi);
-          if (p.bias) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col + j));
-            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-          }
-          const int64_t off = off0 + c0 + j;
-          if (p.residual) {
-            const float4 q = __ldg(reinterpret_cast<const float4*>(p.residual + off));
-            v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
-          }
-          if (p.out_act == OUT_LRELU) {
-            v.x = v.x > 0.f ? v.x : 0.2f * v.x; v.y = v.y > 0.f ? v.y : 0.2f * v.y;
-            v.z = v.z > 0.f ? v.z : 0.2f * v.z; v.w = v.w > 0.f ? v.w : 0.2f * v.w;
-          } else if (p.out_act == OUT_GELU) {
-            v.x = 0.5f * v.x * (1.f + erff(v.x * 0.70710678118654752440f));
-            v.y = 0.5f * v.y * (1.f + erff(v.y * 0.70710678118654752440f));
-            v.z = 0.5f * v.z * (1.f + erff(v.z * 0.70710678118654752440f));
-            v.w = 0.5f * v.w * (1.f + erff(v.w * 0.70710678118654752440f));
-          }
-          if (p.sft_dec) {
-            const float4 d = __ldg(reinterpret_cast<const float4*>(p.sft_dec + off));
-            const float4 s = __ldg(reinterpret_cast<const float4*>(p.sft_scale + off));
-            v.x = d.x + p.sft_w * (d.x * s.x + v.x); v.y = d.y + p.sft_w * (d.y * s.y + v.y);
-            v.z = d.z + p.sft_w * (d.z * s.z + v.z); v.w = d.w + p.sft_w * (d.w * s.w + v.w);
-          }
-          *reinterpret_cast<float4*>(p.out + off) = v;
+      for (int j = 0; j < BN; j += 4) {
+        float4 v = make_float4(acc[j] * wsi, acc[j + 1] * wsi, acc[j + 2] * wsi, acc[j + 3] * wsi);
+        if (p.bias) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+          v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
         }
+        const int64_t off = off0 + j;
+        if (p.residual) {
+          const float4 q = __ldg(reinterpret_cast<const float4*>(p.residual + off));
+          v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+        }
+        if (p.out_act == OUT_LRELU) {
+          v.x = v.x > 0.f ? v.x : 0.2f * v.x; v.y = v.y > 0.f ? v.y : 0.2f * v.y;
+          v.z = v.z > 0.f ? v.z : 0.2f * v.z; v.w = v.w > 0.f ? v.w : 0.2f * v.w;
+        } else if (p.out_act == OUT_GELU) {
+          v.x = 0.5f * v.x * (1.f + erff(v.x * 0.70710678118654752440f));
+          v.y = 0.5f * v.y * (1.f + erff(v.y * 0.70710678118654752440f));
+          v.z = 0.5f * v.z * (1.f + erff(v.z * 0.70710678118654752440f));
+          v.w = 0.5f * v.w * (1.f + erff(v.w * 0.70710678118654752440f));
+        }
+        if (p.sft_dec) {
+          const float4 d = __ldg(reinterpret_cast<const float4*>(p.sft_dec + off));
+          const float4 s = __ldg(reinterpret_cast<const float4*>(p.sft_scale + off));
+          v.x = d.x + p.sft_w * (d.x * s.x + v.x); v.y = d.y + p.sft_w * (d.y * s.y + v.y);
+          v.z = d.z + p.sft_w * (d.z * s.z + v.z); v.w = d.w + p.sft_w * (d.w * s.w + v.w);
+        }
+        *reinterpret_cast<float4*>(p.out + off) = v;
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(tempty + acc));
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -421,10 +442,11 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box) {
+                    const uint32_t* box, int spatial_stride = 1) {
   EncodeTiledFn fn = get_encode_fn();
   CFB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  // traversal stride 2 along W and H turns the box into the stride-2 sampling pattern of Downsample
+  cuuint32_t estr[5] = {1, (cuuint32_t)spatial_stride, (cuuint32_t)spatial_stride, 1, 1};
   const CUresult rc = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
                          reinterpret_cast<const cuuint64_t*>(dims), reinterpret_cast<const cuuint64_t*>(strides_bytes),
                          reinterpret_cast<const cuuint32_t*>(box), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -435,10 +457,20 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* 
 
 static inline int tile_bw(int Wo) { return Wo < 128 ? Wo : 128; }
 
+// k-blocks (64 K-elements) per TMEM partial sum; env CFB_TC_CHUNK overrides for experiments (1..64)
+static int tc_chunk_kblocks() {
+  static int v = [] {
+    const char* e = getenv("CFB_TC_CHUNK");
+    int c = e ? atoi(e) : 1;
+    return c < 1 ? 1 : (c > 4096 ? 4096 : c);
+  }();
+  return v;
+}
+
 bool tc_supported(const ConvArgs& a) {
   if (a.Cin % 64 != 0 || a.Cout % 64 != 0) return false;
   if (!(a.ksize == 1 || a.ksize == 3)) return false;
-  if (!(a.mode == CONV_SAME || a.mode == CONV_UP)) return false;
+  if (a.mode == CONV_DOWN && a.ksize != 3) return false;
   if (a.Wo < 1 || a.Ho < 1) return false;
   const int BW = tile_bw(a.Wo);
   if (128 % BW != 0 || a.Wo % BW != 0) return false;
@@ -450,7 +482,8 @@ bool tc_supported(const ConvArgs& a) {
 
 size_t tc_scratch_bytes(const ConvArgs& a) {
   if (!tc_supported(a)) return 0;
-  const size_t plane = ((size_t)a.N * a.Ho * a.Wo * a.Cin * 2 + 1023) / 1024 * 1024;   // operand planes have the OUTPUT size
+  const int Hp = a.mode == CONV_DOWN ? a.H : a.Ho, Wp = a.mode == CONV_DOWN ? a.W : a.Wo;   // operand plane resolution
+  const size_t plane = ((size_t)a.N * Hp * Wp * a.Cin * 2 + 1023) / 1024 * 1024;
   return 2 * plane;
 }
 
@@ -475,12 +508,14 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
   CFB_REQUIRE(a.wgt_hi && a.wgt_lo && a.wscale_inv, "conv_tc: split weights missing");
   const int64_t M = (int64_t)a.N * a.Ho * a.Wo;
   if (M == 0) return 0;
-  // ---- operand planes (fp16 hi/lo, NHWC at the conv's output resolution)
-  const size_t plane = ((size_t)M * a.Cin * 2 + 1023) / 1024 * 1024;
+  // ---- operand planes (fp16 hi/lo NHWC; at the output resolution, or the input resolution for Downsample)
+  const int Hp = a.mode == CONV_DOWN ? a.H : a.Ho, Wp = a.mode == CONV_DOWN ? a.W : a.Wo;
+  const int64_t Mp = (int64_t)a.N * Hp * Wp;
+  const size_t plane = ((size_t)Mp * a.Cin * 2 + 1023) / 1024 * 1024;
   __half* hi = (__half*)scratch;
   __half* lo = (__half*)((char*)scratch + plane);
   {
-    const int64_t total = M * (a.Cin / 8);
+    const int64_t total = Mp * (a.Cin / 8);
     const int64_t blocks = (total + 255) / 256;
     tc_prep_kernel<<<(unsigned)(blocks > 148 * 32 ? 148 * 32 : blocks), 256, 0, st>>>(
         a.in, a.in_scale, a.in_shift, a.in_act, a.mode == CONV_UP ? 1 : 0, a.N, a.H, a.W, a.Cin, hi, lo);
@@ -491,11 +526,12 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
   const int BN = (a.Cout % 128 == 0) ? 128 : 64;
   CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
   {
-    const uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)a.Wo, (uint64_t)a.Ho, (uint64_t)a.N};
-    const uint64_t str[3] = {(uint64_t)a.Cin * 2, (uint64_t)a.Wo * a.Cin * 2, (uint64_t)a.Ho * a.Wo * a.Cin * 2};
-    const uint32_t box[4] = {64, (uint32_t)BW, (uint32_t)BH, 1};
-    CFB_CHECK(make_map(&mA_hi, hi, 4, dims, str, box));
-    CFB_CHECK(make_map(&mA_lo, lo, 4, dims, str, box));
+    const int sp = a.mode == CONV_DOWN ? 2 : 1;
+    const uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)Wp, (uint64_t)Hp, (uint64_t)a.N};
+    const uint64_t str[3] = {(uint64_t)a.Cin * 2, (uint64_t)Wp * a.Cin * 2, (uint64_t)Hp * Wp * a.Cin * 2};
+    const uint32_t box[4] = {64, (uint32_t)(BW * sp), (uint32_t)(BH * sp), 1};   // ceil(box/stride) = BW x BH elements land
+    CFB_CHECK(make_map(&mA_hi, hi, 4, dims, str, box, sp));
+    CFB_CHECK(make_map(&mA_lo, lo, 4, dims, str, box, sp));
   }
   {
     const int taps = a.ksize * a.ksize;
@@ -507,7 +543,8 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
   }
   TcParams p;
   p.N = a.N; p.Ho = a.Ho; p.Wo = a.Wo; p.Cout = a.Cout;
-  p.taps = a.ksize * a.ksize; p.pad = a.ksize / 2;
+  p.taps = a.ksize * a.ksize; p.pad = a.mode == CONV_DOWN ? 0 : a.ksize / 2; p.stride = a.mode == CONV_DOWN ? 2 : 1;
+  p.chunk = tc_chunk_kblocks();
   p.BW = BW; p.BH = BH; p.tiles_x = a.Wo / BW; p.tiles_y = a.Ho / BH;
   p.m_tiles = a.N * p.tiles_x * p.tiles_y; p.n_tiles = a.Cout / BN; p.kblocks = a.Cin / 64;
   p.bias = a.bias; p.residual = a.residual; p.out_act = a.out_act;

@@ -21,17 +21,22 @@ def rnd(*s, seed=0, scale=1.0):
 CASES = [  # N, Cin, Cout, H, k, mode
     (1, 64, 64, 16, 1, 0), (1, 64, 64, 16, 3, 0), (1, 64, 128, 16, 3, 0), (2, 128, 128, 32, 3, 0), (1, 128, 64, 128, 3, 0),
     (1, 256, 256, 64, 3, 0), (1, 512, 512, 16, 3, 0), (1, 512, 1536, 16, 1, 0), (1, 128, 128, 16, 3, 2), (1, 64, 64, 256, 3, 0),
+    (1, 64, 64, 32, 3, 1), (2, 128, 128, 256, 3, 1), (1, 256, 256, 64, 3, 1), (1, 512, 256, 16, 3, 0),
 ]
 
 
 def main():
-    print(torch.cuda.get_device_name(0), flush=True)
+    import os
+    print(torch.cuda.get_device_name(0), 'CFB_TC_CHUNK=', os.environ.get('CFB_TC_CHUNK'), flush=True)
     for (N, Cin, Cout, H, k, mode) in CASES:
         x = rnd(N, Cin, H, H, seed=1)
         w = rnd(Cout, Cin, k, k, seed=2, scale=1 / math.sqrt(Cin * k * k))
         b = rnd(Cout, seed=3, scale=0.1)
-        xin = F.interpolate(x, scale_factor=2.0, mode='nearest') if mode == 2 else x
-        ref = F.conv2d(xin.double(), w.double(), b.double(), padding=k // 2).float()
+        if mode == 1:
+            ref = F.conv2d(F.pad(x, (0, 1, 0, 1)).double(), w.double(), b.double(), stride=2).float()
+        else:
+            xin = F.interpolate(x, scale_factor=2.0, mode='nearest') if mode == 2 else x
+            ref = F.conv2d(xin.double(), w.double(), b.double(), padding=k // 2).float()
         try:
             t = time.time()
             o2 = G.conv2d(x, w, b, mode=mode, engine=2).cpu()
