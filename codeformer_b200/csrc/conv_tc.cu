@@ -193,8 +193,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------------
 // the kernel
@@ -215,6 +215,8 @@ struct TcParams {
   float sft_w;
   const float* wscale_inv;  // device scalar: 2^-k of the weight split
   float* out;
+  float* gn_part;           // optional GroupNorm(32) partial sums of `out`: [m_tile*4 + warp][32][2]
+  int gn_cpg;               // channels per group = Cout/32
 };
 
 constexpr int TC_THREADS = 192;
@@ -359,11 +361,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(slot * BN);
 #pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(taddr + c0, r);
+        for (int c0 = 0; c0 < BN; c0 += 64) {       // two loads in flight per wait
+          uint32_t r0[32], r1[32];
+          tmem_ld32(taddr + c0, r0);
+          tmem_ld32(taddr + c0 + 32, r1);
+          tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+          for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r0[j]);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[c0 + 32 + j] += __uint_as_float(r1[j]);
         }
         tc_fence_before();
         __syncwarp();
@@ -380,6 +386,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const int64_t pix = ((int64_t)n * p.Ho + (ty * p.BH + h)) * p.Wo + (tx * p.BW + w);
       const int64_t off0 = pix * p.Cout + (int64_t)nt * BN;
       const int col0 = nt * BN;
+      float gs = 0.f, gq = 0.f;
+      float* gpart = p.gn_part ? p.gn_part + ((int64_t)mt * 4 + lg) * 64 : nullptr;
 #pragma unroll
       for (int j = 0; j < BN; j += 4) {
         float4 v = make_float4(acc[j] * wsi, acc[j + 1] * wsi, acc[j + 2] * wsi, acc[j + 3] * wsi);
@@ -408,6 +416,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           v.z = d.z + p.sft_w * (d.z * s.z + v.z); v.w = d.w + p.sft_w * (d.w * s.w + v.w);
         }
         *reinterpret_cast<float4*>(p.out + off) = v;
+        if (gpart) {
+          // GroupNorm statistics of the values just stored: per group, sum / sum of squares over this warp's 32 pixels
+          if (p.gn_cpg == 2) {
+            float s0 = v.x + v.y, q0 = fmaf(v.x, v.x, v.y * v.y), s1 = v.z + v.w, q1 = fmaf(v.z, v.z, v.w * v.w);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              s0 += __shfl_xor_sync(0xffffffffu, s0, o); q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+              s1 += __shfl_xor_sync(0xffffffffu, s1, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+            }
+            if (lane == 0) *reinterpret_cast<float4*>(gpart + ((col0 + j) >> 1) * 2) = make_float4(s0, q0, s1, q1);
+          } else {
+            gs += (v.x + v.y) + (v.z + v.w);
+            gq += fmaf(v.x, v.x, v.y * v.y) + fmaf(v.z, v.z, v.w * v.w);
+            if (((j + 4) & (p.gn_cpg - 1)) == 0) {
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                gs += __shfl_xor_sync(0xffffffffu, gs, o); gq += __shfl_xor_sync(0xffffffffu, gq, o);
+              }
+              if (lane == 0) *reinterpret_cast<float2*>(gpart + ((col0 + j) / p.gn_cpg) * 2) = make_float2(gs, gq);
+              gs = 0.f; gq = 0.f;
+            }
+          }
+        }
       }
     }
   }
@@ -461,10 +492,15 @@ static inline int tile_bw(int Wo) { return Wo < 128 ? Wo : 128; }
 static int tc_chunk_kblocks() {
   static int v = [] {
     const char* e = getenv("CFB_TC_CHUNK");
-    int c = e ? atoi(e) : 1;
+    int c = e ? atoi(e) : 2;
     return c < 1 ? 1 : (c > 4096 ? 4096 : c);
   }();
   return v;
+}
+
+int tc_tiles_per_image(const ConvArgs& a) {
+  const int BW = tile_bw(a.Wo);
+  return (a.Wo / BW) * (a.Ho / (128 / BW));
 }
 
 bool tc_supported(const ConvArgs& a) {
@@ -549,6 +585,8 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
   p.m_tiles = a.N * p.tiles_x * p.tiles_y; p.n_tiles = a.Cout / BN; p.kblocks = a.Cin / 64;
   p.bias = a.bias; p.residual = a.residual; p.out_act = a.out_act;
   p.sft_dec = a.sft_dec; p.sft_scale = a.sft_scale; p.sft_w = a.sft_w; p.wscale_inv = a.wscale_inv; p.out = a.out;
+  p.gn_part = a.gn_part; p.gn_cpg = a.Cout / 32;
+  CFB_REQUIRE(!a.gn_part || (a.Cout % 64 == 0), "conv_tc: GroupNorm partials need Cout % 64 == 0");
   if (BN == 128) return launch_tc<128>(mA_hi, mA_lo, mB_hi, mB_lo, p, sm_count, st);
   return launch_tc<64>(mA_hi, mA_lo, mB_hi, mB_lo, p, sm_count, st);
 }

@@ -11,5 +11,6 @@ namespace cfb {
 int tc_split_weights(const float* oihw, __half* hi, __half* lo, int Cout, int Cin, int k, float* scale_slot, cudaStream_t st);
 bool tc_supported(const ConvArgs& a);
 size_t tc_scratch_bytes(const ConvArgs& a);   // operand (hi/lo fp16 activation planes) staging
+int tc_tiles_per_image(const ConvArgs& a);    // 128-pixel tiles per image (GroupNorm partial slots = 4x this)
 int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st);
 }  // namespace cfb

@@ -71,6 +71,8 @@ struct ConvArgs {
   const float* sft_scale = nullptr;
   float sft_w = 0.f;
   float* out = nullptr;             // [N,Ho,Wo,Cout]
+  // tensor-core engine only: GroupNorm(32) partial sums of `out`, [N*tiles_per_image*4][32 groups][2] floats
+  float* gn_part = nullptr;
 };
 
 int conv_f32(const ConvArgs& a, cudaStream_t st);                       // CUDA-core fp32 implicit GEMM
@@ -88,6 +90,9 @@ int relayout_oihw_to_tck(const float* oihw, float* out, int Cout, int Cin, int k
 size_t gn_workspace_bytes(int N, int HW, int C);
 int gn_coef(const float* x, const float* gamma, const float* beta, float* scale, float* shift, int N, int HW, int C,
             int groups, float eps, void* ws, cudaStream_t st);
+// finalize from the tensor-core epilogue's partial sums (slots per image = tiles_per_image*4)
+int gn_coef_from_partials(const float* part, int slots, const float* gamma, const float* beta, float* scale, float* shift,
+                          int N, int HW, int C, int groups, float eps, cudaStream_t st);
 int affine_act(const float* x, const float* scale, const float* shift, float* y, int N, int HW, int C, int act,
                cudaStream_t st);
 

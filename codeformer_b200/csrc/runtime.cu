@@ -88,6 +88,8 @@ struct Tensor {
   float* p = nullptr;
   int N = 0, H = 0, W = 0, C = 0;
   bool owned = true;  // false: caller memory or kept-alive tap
+  float* gn_part = nullptr;   // GroupNorm partial sums emitted by the producing tensor-core conv (or null)
+  int gn_slots = 0;           // partial slots per image
   int64_t numel() const { return (int64_t)N * H * W * C; }
 };
 
@@ -403,7 +405,10 @@ struct Fwd {
     CFB_REQUIRE(*p != nullptr, "workspace too small (use cfb_workspace_bytes)");
     return 0;
   }
-  void release(Tensor& t) { if (t.owned && t.p) ar.release(t.p); t.p = nullptr; }
+  void release(Tensor& t) {
+    if (t.owned && t.p) { ar.release(t.p); if (t.gn_part) ar.release(t.gn_part); }
+    t.p = nullptr; t.gn_part = nullptr;
+  }
   void release_raw(void* p) { ar.release(p); }
 
   // debug/parity hook: copy a stage's NHWC activation out (cfb_net_capture)
@@ -422,6 +427,7 @@ struct Fwd {
     const float* residual = nullptr; int out_act = OUT_NONE;
     const float* sft_dec = nullptr; const float* sft_scale = nullptr; float sft_w = 0.f;
     float* out_ptr = nullptr;   // write into caller memory instead of the arena
+    bool want_stats = false;    // consumer is a GroupNorm: let the tensor-core epilogue emit the partial sums
   };
 
   int conv(const ConvW& w, const Tensor& in, Tensor& out, const ConvOpt& o) {
@@ -439,6 +445,11 @@ struct Fwd {
     bool use_tc = engine == 2 || (engine == 0 && n->tc_ok && tc_supported(a));
     if (use_tc) {
       CFB_REQUIRE(tc_supported(a), "conv: shape not supported by the tcgen05 engine: " + w.name);
+      if (o.want_stats && !o.out_ptr) {
+        out.gn_slots = tc_tiles_per_image(a) * 4;
+        CFB_CHECK(alloc_raw((void**)&out.gn_part, (size_t)in.N * out.gn_slots * 64 * sizeof(float)));
+        a.gn_part = out.gn_part;
+      }
       const size_t sb = tc_scratch_bytes(a);
       void* scratch = nullptr;
       CFB_CHECK(alloc_raw(&scratch, sb));
@@ -455,6 +466,11 @@ struct Fwd {
     CFB_REQUIRE(x.C == w.c, "norm: channel mismatch for " + w.name);
     CFB_CHECK(alloc_raw((void**)scale, (size_t)x.N * x.C * 4));
     CFB_CHECK(alloc_raw((void**)shift, (size_t)x.N * x.C * 4));
+    if (x.gn_part) {   // statistics already reduced per tile by the producing conv's epilogue
+      if (!dry)
+        CFB_CHECK(gn_coef_from_partials(x.gn_part, x.gn_slots, w.gamma, w.beta, *scale, *shift, x.N, x.H * x.W, x.C, 32, 1e-6f, st));
+      return 0;
+    }
     void* ws = nullptr;
     CFB_CHECK(alloc_raw(&ws, gn_workspace_bytes(x.N, x.H * x.W, x.C)));
     if (!dry) CFB_CHECK(gn_coef(x.p, w.gamma, w.beta, *scale, *shift, x.N, x.H * x.W, x.C, 32, 1e-6f, ws, st));
@@ -467,13 +483,13 @@ struct Fwd {
     float *s1, *h1, *s2, *h2;
     CFB_CHECK(gn(r.n1, x, &s1, &h1));
     Tensor h;
-    ConvOpt o1; o1.in_scale = s1; o1.in_shift = h1; o1.in_act = IN_SILU;
+    ConvOpt o1; o1.in_scale = s1; o1.in_shift = h1; o1.in_act = IN_SILU; o1.want_stats = true;
     CFB_CHECK(conv(r.c1, x, h, o1));
     release_raw(s1); release_raw(h1);
     CFB_CHECK(gn(r.n2, h, &s2, &h2));
     Tensor skip = x; skip.owned = false;
     if (r.has_out) { ConvOpt oo; CFB_CHECK(conv(r.co, x, skip, oo)); }
-    ConvOpt o2; o2.in_scale = s2; o2.in_shift = h2; o2.in_act = IN_SILU; o2.residual = skip.p;
+    ConvOpt o2; o2.in_scale = s2; o2.in_shift = h2; o2.in_act = IN_SILU; o2.residual = skip.p; o2.want_stats = true;
     CFB_CHECK(conv(r.c2, h, y, o2));
     release_raw(s2); release_raw(h2);
     release(h);
@@ -497,7 +513,7 @@ struct Fwd {
       CFB_CHECK(attention(qkv.p, qkv.p + C, qkv.p + 2 * C, a.p, x.N, 256, 1, C, 3 * C, 3 * C, 3 * C, C,
                           1.0f / sqrtf((float)C), st));
     release(qkv);
-    ConvOpt op; op.residual = x.p;
+    ConvOpt op; op.residual = x.p; op.want_stats = true;
     CFB_CHECK(conv(w.proj, a, y, op));
     release(a);
     return 0;
@@ -519,7 +535,7 @@ struct Fwd {
     release(s0);
     CFB_CHECK(conv(f.h0, e, h0, ol));
     release(e);
-    ConvOpt of; of.sft_dec = dec.p; of.sft_scale = sc.p; of.sft_w = wgt;
+    ConvOpt of; of.sft_dec = dec.p; of.sft_scale = sc.p; of.sft_w = wgt; of.want_stats = true;
     CFB_CHECK(conv(f.h2, h0, y, of));
     release(h0); release(sc);
     return 0;
@@ -539,7 +555,7 @@ struct Fwd {
       switch (b.kind) {
         case B_RES: CFB_CHECK(resblock(b.res_w, x, y)); break;
         case B_ATTN: CFB_CHECK(attnblock(b.attn, x, y)); break;
-        case B_DOWN: { ConvOpt o; o.mode = CONV_DOWN; CFB_CHECK(conv(b.conv, x, y, o)); break; }
+        case B_DOWN: { ConvOpt o; o.mode = CONV_DOWN; o.want_stats = true; CFB_CHECK(conv(b.conv, x, y, o)); break; }
         case B_NORM: CFB_CHECK(gn(b.norm, x, &ps, &ph)); continue;   // consumed by the next conv
         case B_CONV: {
           ConvOpt o; o.in_scale = ps; o.in_shift = ph;
@@ -568,7 +584,7 @@ struct Fwd {
       switch (b.kind) {
         case B_RES: CFB_CHECK(resblock(b.res_w, x, y)); break;
         case B_ATTN: CFB_CHECK(attnblock(b.attn, x, y)); break;
-        case B_UP: { ConvOpt o; o.mode = CONV_UP; CFB_CHECK(conv(b.conv, x, y, o)); break; }
+        case B_UP: { ConvOpt o; o.mode = CONV_UP; o.want_stats = true; CFB_CHECK(conv(b.conv, x, y, o)); break; }
         case B_NORM: CFB_CHECK(gn(b.norm, x, &ps, &ph)); continue;
         case B_CONV:
           if (i + 1 == n->gen.size()) {
@@ -577,7 +593,7 @@ struct Fwd {
             release(x);
             return 0;
           } else {
-            ConvOpt o; o.in_scale = ps; o.in_shift = ph;
+            ConvOpt o; o.in_scale = ps; o.in_shift = ph; o.want_stats = true;
             CFB_CHECK(conv(b.conv, x, y, o));
             if (ps) { release_raw(ps); release_raw(ph); ps = ph = nullptr; }
           }

@@ -439,6 +439,49 @@ int gn_coef(const float* x, const float* gamma, const float* beta, float* scale,
   return 0;
 }
 
+__global__ void __launch_bounds__(256) gn_final_f32_kernel(const float* __restrict__ part, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float* __restrict__ scale,
+                                                           float* __restrict__ shift, int HW, int C, int slots, float eps) {
+  // 32 groups; thread t -> group t%32, slot stripe t/32 (fixed-order => deterministic)
+  __shared__ double ps[8][32], pq[8][32];
+  __shared__ double gmean[32], grstd[32];
+  const int n = blockIdx.x, t = threadIdx.x;
+  const int g = t & 31, stripe = t >> 5;
+  double a = 0.0, b = 0.0;
+  for (int k = stripe; k < slots; k += 8) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(part + (((int64_t)n * slots + k) * 32 + g) * 2));
+    a += (double)v.x; b += (double)v.y;
+  }
+  ps[stripe][g] = a; pq[stripe][g] = b;
+  __syncthreads();
+  const int cpg = C / 32;
+  if (t < 32) {
+    double sa = 0.0, sb = 0.0;
+    for (int k = 0; k < 8; ++k) { sa += ps[k][t]; sb += pq[k][t]; }
+    const double cnt = (double)HW * cpg;
+    const double mean = sa / cnt;
+    double var = sb / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    gmean[t] = mean;
+    grstd[t] = 1.0 / sqrt(var + (double)eps);
+  }
+  __syncthreads();
+  for (int c = t; c < C; c += 256) {
+    const int gg = c / cpg;
+    const double sc = grstd[gg] * (double)gamma[c];
+    scale[(int64_t)n * C + c] = (float)sc;
+    shift[(int64_t)n * C + c] = (float)((double)beta[c] - gmean[gg] * sc);
+  }
+}
+int gn_coef_from_partials(const float* part, int slots, const float* gamma, const float* beta, float* scale, float* shift,
+                          int N, int HW, int C, int groups, float eps, cudaStream_t st) {
+  CFB_REQUIRE(groups == 32 && C % 32 == 0, "gn_coef_from_partials: 32 groups only");
+  if (N == 0) return 0;
+  gn_final_f32_kernel<<<N, 256, 0, st>>>(part, gamma, beta, scale, shift, HW, C, slots, eps);
+  CFB_LAUNCH_CHECK();
+  return 0;
+}
+
 __global__ void affine_act_kernel(const float4* __restrict__ x, const float* __restrict__ scale,
                                   const float* __restrict__ shift, float4* __restrict__ y, int64_t total4, int64_t HWC4,
                                   int C, int act) {
@@ -720,24 +763,31 @@ int gather_rows(const int64_t* idx, const float* codebook, float* out, int T, in
 // =====================================================================================================
 // AdaIN on NHWC [B,HW,C]: per (b,c) mean / unbiased var (+1e-5) of both tensors
 // =====================================================================================================
+// Statistics are accumulated in double and then rounded to fp32, and the elementwise part replays the reference's
+// fp32 operation order with explicit (non-contracted) roundings.  Reason: when most tokens of a face pick the same
+// code a content channel is nearly constant, (x - mean)/std then amplifies a 1e-7 error of the mean by 1/std
+// (observed 3e-5 relative on quant_feat with sequential fp32 sums); an accurately rounded mean reproduces the
+// reference's own fp32 value and the rest is IEEE-deterministic.
 __global__ void adain_kernel(const float* __restrict__ content, const float* __restrict__ style, float* __restrict__ out,
                              int HW, int C) {
   const int b = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float* cp = content + (int64_t)b * HW * C + c;
     const float* sp = style + (int64_t)b * HW * C + c;
-    float cs = 0.f, ss = 0.f;
-    for (int p = 0; p < HW; ++p) { cs += cp[(int64_t)p * C]; ss += sp[(int64_t)p * C]; }
-    const float cm = cs / HW, sm = ss / HW;
-    float cv = 0.f, sv = 0.f;
+    double cs = 0.0, ss = 0.0;
+    for (int p = 0; p < HW; ++p) { cs += (double)cp[(int64_t)p * C]; ss += (double)sp[(int64_t)p * C]; }
+    const double cmd = cs / HW, smd = ss / HW;
+    double cv = 0.0, sv = 0.0;
     for (int p = 0; p < HW; ++p) {
-      const float a = cp[(int64_t)p * C] - cm, d = sp[(int64_t)p * C] - sm;
-      cv = fmaf(a, a, cv); sv = fmaf(d, d, sv);
+      const double a = (double)cp[(int64_t)p * C] - cmd, d = (double)sp[(int64_t)p * C] - smd;
+      cv += a * a; sv += d * d;
     }
-    const float cstd = sqrtf(cv / (HW - 1) + 1e-5f), sstd = sqrtf(sv / (HW - 1) + 1e-5f);
+    const float cm = (float)cmd, sm = (float)smd;
+    const float cstd = sqrtf(__fadd_rn((float)(cv / (HW - 1)), 1e-5f));    // calc_mean_std: var(unbiased) + eps, sqrt
+    const float sstd = sqrtf(__fadd_rn((float)(sv / (HW - 1)), 1e-5f));
     for (int p = 0; p < HW; ++p) {
-      const float nrm = (cp[(int64_t)p * C] - cm) / cstd;
-      out[(int64_t)b * HW * C + (int64_t)p * C + c] = nrm * sstd + sm;
+      const float nrm = __fdiv_rn(__fsub_rn(cp[(int64_t)p * C], cm), cstd);   // (content - mean) / std
+      out[(int64_t)b * HW * C + (int64_t)p * C + c] = __fadd_rn(__fmul_rn(nrm, sstd), sm);   // * style_std + style_mean
     }
   }
 }
