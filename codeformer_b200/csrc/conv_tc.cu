@@ -14,9 +14,10 @@
 //     K-major layout the UMMA descriptor expects (no im2col buffer anywhere);
 //   * B tiles ([tap][Cout][Cin] fp16) by 3-D TMA boxes {64, BN, 1};
 //   * warp-specialised persistent CTAs (1 per SM): warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc),
-//     warps 2..5 = epilogue (tcgen05.ld -> bias / residual / activation / SFT -> fp32 NHWC stores);
-//     smem ring of STAGES k-blocks (full/empty mbarriers), 2 TMEM accumulators (tmem_full/tmem_empty) so the
-//     epilogue of tile i overlaps the MMAs of tile i+1.
+//     warps 2..9 = epilogue (tcgen05.ld -> fold partial sums -> bias / residual / activation / SFT -> fp32 NHWC
+//     stores + GroupNorm partial sums); smem ring of STAGES k-blocks (full/empty mbarriers) and a ring of 4 TMEM
+//     partial-sum slots (cfull/cempty) so folding / storing overlaps the MMAs of the following k-blocks / tile;
+//   * stride-2 Downsample uses TMA traversal strides (elementStrides = 2) on the same path.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -219,9 +220,10 @@ struct TcParams {
   int gn_cpg;               // channels per group = Cout/32
 };
 
-constexpr int TC_THREADS = 192;
-constexpr int TC_A_BYTES = 128 * 128;   // 128 pixels x 64 fp16
-constexpr int TC_SLOTS = 4;             // TMEM partial-sum ring
+constexpr int TC_EPI_WARPS = 8;                       // 4 TMEM lane quadrants x 2 column halves
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // warp0 TMA, warp1 MMA, warps 2..9 epilogue
+constexpr int TC_A_BYTES = 128 * 128;                 // 128 pixels x 64 fp16
+constexpr int TC_SLOTS = 4;                           // TMEM partial-sum ring
 
 template <int BN>
 struct TcCfg {
@@ -232,12 +234,34 @@ struct TcCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+// Butterfly reduction of G per-lane group sums over the 32 lanes of a warp: after log2(G) exchange steps every lane
+// owns ONE group (index lane / (32/G)) and the remaining steps are plain xor-reductions.  G-1 + (5-log2 G) shuffles
+// instead of 5*G.  Fixed order => deterministic.
+template <int G>
+__device__ __forceinline__ void warp_group_reduce(float (&v)[G], int lane) {
+  int o = 16;
+#pragma unroll
+  for (int n = G; n > 1; n >>= 1) {
+    const int half = n >> 1;
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = up ? v[i] : v[i + half];
+      const float keep = up ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+    o >>= 1;
+  }
+  for (; o >= 1; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+}
+
 // Accumulation scheme (why the TMEM ring): tcgen05.mma adds into its fp32 accumulator with truncation, so a long
 // K loop into one accumulator drifts by ~(#MMAs)*2^-25 relative (measured 2e-5 at K=4608 -- too much for the
 // 1e-3 end-to-end bar).  Each TMEM slot therefore only receives `chunk` k-blocks (64 K-elements each), the small
 // cross terms (lo*hi, hi*lo) are issued first while the slot is still tiny, and the epilogue warps fold every
 // finished slot into fp32 registers with round-to-nearest adds while the tensor core fills the next slot.
-template <int BN>
+// CPG > 0: the epilogue also emits GroupNorm(32) partial sums of the stored tile (CPG = Cout/32 channels per group).
+template <int BN, int CPG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const TcParams p) {
@@ -260,7 +284,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_hi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_lo) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(full + s), 1); mbar_init(smem_u32(empty + s), 1); }
-    for (int a = 0; a < TC_SLOTS; ++a) { mbar_init(smem_u32(cfull + a), 1); mbar_init(smem_u32(cempty + a), 4); }
+    for (int a = 0; a < TC_SLOTS; ++a) { mbar_init(smem_u32(cfull + a), 1); mbar_init(smem_u32(cempty + a), TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -346,37 +370,45 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
     }
   } else {
-    // ============================ epilogue (warps 2..5) ============================
-    const int lg = warp & 3;                 // TMEM lane group this warp may access: lanes [32*lg, 32*lg+32)
+    // ============================ epilogue (warps 2..9) ============================
+    constexpr int HC = BN / 2;               // columns owned by this thread
+    const int lg = warp & 3;                 // TMEM lane quadrant this warp may access: lanes [32*lg, 32*lg+32)
+    const int half = (warp - 2) >> 2;        // which half of the tile's columns
     const int row = lg * 32 + lane;          // pixel row of the tile
+    const int cbase = half * HC;
     const float wsi = __ldg(p.wscale_inv);
     int slot = 0;
     uint32_t slot_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      float acc[BN];
+      float acc[HC];
 #pragma unroll
-      for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+      for (int j = 0; j < HC; ++j) acc[j] = 0.f;
       for (int it0 = 0; it0 < nk; it0 += p.chunk) {
         mbar_wait(smem_u32(cfull + slot), slot_phase);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(slot * BN);
-#pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 64) {       // two loads in flight per wait
+        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(slot * BN + cbase);
+        if constexpr (HC == 64) {
           uint32_t r0[32], r1[32];
-          tmem_ld32(taddr + c0, r0);
-          tmem_ld32(taddr + c0 + 32, r1);
+          tmem_ld32(taddr, r0);
+          tmem_ld32(taddr + 32, r1);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r0[j]);
+          for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r0[j]);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc[c0 + 32 + j] += __uint_as_float(r1[j]);
+          for (int j = 0; j < 32; ++j) acc[32 + j] += __uint_as_float(r1[j]);
+        } else {
+          uint32_t r0[32];
+          tmem_ld32(taddr, r0);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r0[j]);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(cempty + slot));
         if (++slot == TC_SLOTS) { slot = 0; slot_phase ^= 1; }
       }
-      // ---- finalize this tile: scale, bias, residual, activation, SFT, store (fp32 NHWC)
+      // ---- finalize this tile: scale, bias, residual, activation, SFT, store (fp32 NHWC), GroupNorm partials
       const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
       const int per_img = p.tiles_x * p.tiles_y;
       const int n = mt / per_img;
@@ -384,12 +416,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
       const int h = row / p.BW, w = row - h * p.BW;
       const int64_t pix = ((int64_t)n * p.Ho + (ty * p.BH + h)) * p.Wo + (tx * p.BW + w);
-      const int64_t off0 = pix * p.Cout + (int64_t)nt * BN;
-      const int col0 = nt * BN;
-      float gs = 0.f, gq = 0.f;
-      float* gpart = p.gn_part ? p.gn_part + ((int64_t)mt * 4 + lg) * 64 : nullptr;
+      const int col0 = nt * BN + cbase;
+      const int64_t off0 = pix * p.Cout + col0;
+      constexpr int G = (CPG > 0) ? HC / CPG : 1;
+      float gs[G], gq[G];
 #pragma unroll
-      for (int j = 0; j < BN; j += 4) {
+      for (int g = 0; g < G; ++g) { gs[g] = 0.f; gq[g] = 0.f; }
+#pragma unroll
+      for (int j = 0; j < HC; j += 4) {
         float4 v = make_float4(acc[j] * wsi, acc[j + 1] * wsi, acc[j + 2] * wsi, acc[j + 3] * wsi);
         if (p.bias) {
           const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
@@ -416,28 +450,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           v.z = d.z + p.sft_w * (d.z * s.z + v.z); v.w = d.w + p.sft_w * (d.w * s.w + v.w);
         }
         *reinterpret_cast<float4*>(p.out + off) = v;
-        if (gpart) {
-          // GroupNorm statistics of the values just stored: per group, sum / sum of squares over this warp's 32 pixels
-          if (p.gn_cpg == 2) {
-            float s0 = v.x + v.y, q0 = fmaf(v.x, v.x, v.y * v.y), s1 = v.z + v.w, q1 = fmaf(v.z, v.z, v.w * v.w);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              s0 += __shfl_xor_sync(0xffffffffu, s0, o); q0 += __shfl_xor_sync(0xffffffffu, q0, o);
-              s1 += __shfl_xor_sync(0xffffffffu, s1, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o);
-            }
-            if (lane == 0) *reinterpret_cast<float4*>(gpart + ((col0 + j) >> 1) * 2) = make_float4(s0, q0, s1, q1);
-          } else {
-            gs += (v.x + v.y) + (v.z + v.w);
-            gq += fmaf(v.x, v.x, v.y * v.y) + fmaf(v.z, v.z, v.w * v.w);
-            if (((j + 4) & (p.gn_cpg - 1)) == 0) {
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) {
-                gs += __shfl_xor_sync(0xffffffffu, gs, o); gq += __shfl_xor_sync(0xffffffffu, gq, o);
-              }
-              if (lane == 0) *reinterpret_cast<float2*>(gpart + ((col0 + j) / p.gn_cpg) * 2) = make_float2(gs, gq);
-              gs = 0.f; gq = 0.f;
-            }
-          }
+        if constexpr (CPG == 2) {
+          gs[j / 2] += v.x + v.y; gq[j / 2] += fmaf(v.x, v.x, v.y * v.y);
+          gs[j / 2 + 1] += v.z + v.w; gq[j / 2 + 1] += fmaf(v.z, v.z, v.w * v.w);
+        } else if constexpr (CPG >= 4) {
+          gs[j / CPG] += (v.x + v.y) + (v.z + v.w);
+          gq[j / CPG] += fmaf(v.x, v.x, v.y * v.y) + fmaf(v.z, v.z, v.w * v.w);
+        }
+      }
+      if constexpr (CPG > 0) {
+        // sum / sum of squares per group over this warp's 32 pixels -> [m_tile*4 + quadrant][32 groups][2]
+        warp_group_reduce<G>(gs, lane);
+        warp_group_reduce<G>(gq, lane);
+        constexpr int LPG = 32 / G;                       // lanes per group after the butterfly
+        if ((lane & (LPG - 1)) == 0) {
+          const int g = col0 / CPG + lane / LPG;
+          *reinterpret_cast<float2*>(p.gn_part + (((int64_t)mt * 4 + lg) * 32 + g) * 2) = make_float2(gs[0], gq[0]);
         }
       }
     }
@@ -523,20 +551,27 @@ size_t tc_scratch_bytes(const ConvArgs& a) {
   return 2 * plane;
 }
 
-template <int BN>
+template <int BN, int CPG>
 static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
                      const TcParams& p, int sm_count, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
   static bool attr_done = false;
   if (!attr_done) {
-    CFB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    CFB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, CPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;
   }
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < sm_count ? total : sm_count;
-  conv_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(a_hi, a_lo, b_hi, b_lo, p);
+  conv_tc_kernel<BN, CPG><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(a_hi, a_lo, b_hi, b_lo, p);
   CFB_LAUNCH_CHECK();
   return 0;
+}
+
+// GroupNorm partial sums can be emitted for (BN=64, Cout=64) and (BN=128, Cout in {128,256,512})
+bool tc_can_emit_stats(const ConvArgs& a) {
+  if (!tc_supported(a)) return false;
+  if (a.Cout % 128 == 0) return a.Cout == 128 || a.Cout == 256 || a.Cout == 512;
+  return a.Cout == 64;
 }
 
 int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
@@ -586,9 +621,21 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
   p.bias = a.bias; p.residual = a.residual; p.out_act = a.out_act;
   p.sft_dec = a.sft_dec; p.sft_scale = a.sft_scale; p.sft_w = a.sft_w; p.wscale_inv = a.wscale_inv; p.out = a.out;
   p.gn_part = a.gn_part; p.gn_cpg = a.Cout / 32;
-  CFB_REQUIRE(!a.gn_part || (a.Cout % 64 == 0), "conv_tc: GroupNorm partials need Cout % 64 == 0");
-  if (BN == 128) return launch_tc<128>(mA_hi, mA_lo, mB_hi, mB_lo, p, sm_count, st);
-  return launch_tc<64>(mA_hi, mA_lo, mB_hi, mB_lo, p, sm_count, st);
+  const int cpg = a.gn_part ? a.Cout / 32 : 0;
+  CFB_REQUIRE(!a.gn_part || tc_can_emit_stats(a), "conv_tc: GroupNorm partials are not available for this Cout");
+  if (BN == 128) {
+    switch (cpg) {
+      case 0: return launch_tc<128, 0>(mA_hi, mA_lo, mB_hi, mB_lo, p, sm_count, st);
+      case 4: return launch_tc<128, 4>(mA_hi, mA_lo, mB_hi, mB_lo, p, sm_count, st);
+      case 8: return launch_tc<128, 8>(mA_hi, mA_lo, mB_hi, mB_lo, p, sm_count, st);
+      case 16: return launch_tc<128, 16>(mA_hi, mA_lo, mB_hi, mB_lo, p, sm_count, st);
+    }
+  } else {
+    if (cpg == 0) return launch_tc<64, 0>(mA_hi, mA_lo, mB_hi, mB_lo, p, sm_count, st);
+    if (cpg == 2) return launch_tc<64, 2>(mA_hi, mA_lo, mB_hi, mB_lo, p, sm_count, st);
+  }
+  CFB_REQUIRE(false, "conv_tc: no kernel variant for this configuration");
+  return 1;
 }
 
 }  // namespace cfb

@@ -11,6 +11,7 @@ namespace cfb {
 int tc_split_weights(const float* oihw, __half* hi, __half* lo, int Cout, int Cin, int k, float* scale_slot, cudaStream_t st);
 bool tc_supported(const ConvArgs& a);
 size_t tc_scratch_bytes(const ConvArgs& a);   // operand (hi/lo fp16 activation planes) staging
+bool tc_can_emit_stats(const ConvArgs& a);    // GroupNorm(32) partial sums available from the epilogue for this shape
 int tc_tiles_per_image(const ConvArgs& a);    // 128-pixel tiles per image (GroupNorm partial slots = 4x this)
 int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st);
 }  // namespace cfb

@@ -445,7 +445,7 @@ struct Fwd {
     bool use_tc = engine == 2 || (engine == 0 && n->tc_ok && tc_supported(a));
     if (use_tc) {
       CFB_REQUIRE(tc_supported(a), "conv: shape not supported by the tcgen05 engine: " + w.name);
-      if (o.want_stats && !o.out_ptr) {
+      if (o.want_stats && !o.out_ptr && tc_can_emit_stats(a)) {
         out.gn_slots = tc_tiles_per_image(a) * 4;
         CFB_CHECK(alloc_raw((void**)&out.gn_part, (size_t)in.N * out.gn_slots * 64 * sizeof(float)));
         a.gn_part = out.gn_part;

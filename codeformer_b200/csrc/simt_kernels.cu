@@ -439,17 +439,25 @@ int gn_coef(const float* x, const float* gamma, const float* beta, float* scale,
   return 0;
 }
 
-__global__ void __launch_bounds__(256) gn_final_f32_kernel(const float* __restrict__ part, const float* __restrict__ gamma,
-                                                           const float* __restrict__ beta, float* __restrict__ scale,
-                                                           float* __restrict__ shift, int HW, int C, int slots, float eps) {
-  // 32 groups; thread t -> group t%32, slot stripe t/32 (fixed-order => deterministic)
-  __shared__ double ps[8][32], pq[8][32];
+__global__ void __launch_bounds__(1024) gn_final_f32_kernel(const float* __restrict__ part, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float* __restrict__ scale,
+                                                            float* __restrict__ shift, int HW, int C, int slots, float eps) {
+  // 32 groups; thread t -> group t%32, slot stripe t/32 (32 stripes, fixed order => deterministic)
+  __shared__ double ps[32][33], pq[32][33];
   __shared__ double gmean[32], grstd[32];
   const int n = blockIdx.x, t = threadIdx.x;
   const int g = t & 31, stripe = t >> 5;
   double a = 0.0, b = 0.0;
-  for (int k = stripe; k < slots; k += 8) {
-    const float2 v = __ldg(reinterpret_cast<const float2*>(part + (((int64_t)n * slots + k) * 32 + g) * 2));
+  const float2* base = reinterpret_cast<const float2*>(part) + (int64_t)n * slots * 32 + g;
+  int k = stripe;
+  for (; k + 96 < slots; k += 128) {     // 4 independent loads in flight
+    const float2 v0 = __ldg(base + (int64_t)k * 32), v1 = __ldg(base + (int64_t)(k + 32) * 32);
+    const float2 v2 = __ldg(base + (int64_t)(k + 64) * 32), v3 = __ldg(base + (int64_t)(k + 96) * 32);
+    a += ((double)v0.x + (double)v1.x) + ((double)v2.x + (double)v3.x);
+    b += ((double)v0.y + (double)v1.y) + ((double)v2.y + (double)v3.y);
+  }
+  for (; k < slots; k += 32) {
+    const float2 v = __ldg(base + (int64_t)k * 32);
     a += (double)v.x; b += (double)v.y;
   }
   ps[stripe][g] = a; pq[stripe][g] = b;
@@ -457,7 +465,7 @@ __global__ void __launch_bounds__(256) gn_final_f32_kernel(const float* __restri
   const int cpg = C / 32;
   if (t < 32) {
     double sa = 0.0, sb = 0.0;
-    for (int k = 0; k < 8; ++k) { sa += ps[k][t]; sb += pq[k][t]; }
+    for (int s = 0; s < 32; ++s) { sa += ps[s][t]; sb += pq[s][t]; }
     const double cnt = (double)HW * cpg;
     const double mean = sa / cnt;
     double var = sb / cnt - mean * mean;
@@ -466,7 +474,7 @@ __global__ void __launch_bounds__(256) gn_final_f32_kernel(const float* __restri
     grstd[t] = 1.0 / sqrt(var + (double)eps);
   }
   __syncthreads();
-  for (int c = t; c < C; c += 256) {
+  for (int c = t; c < C; c += 1024) {
     const int gg = c / cpg;
     const double sc = grstd[gg] * (double)gamma[c];
     scale[(int64_t)n * C + c] = (float)sc;
@@ -477,7 +485,7 @@ int gn_coef_from_partials(const float* part, int slots, const float* gamma, cons
                           int N, int HW, int C, int groups, float eps, cudaStream_t st) {
   CFB_REQUIRE(groups == 32 && C % 32 == 0, "gn_coef_from_partials: 32 groups only");
   if (N == 0) return 0;
-  gn_final_f32_kernel<<<N, 256, 0, st>>>(part, gamma, beta, scale, shift, HW, C, slots, eps);
+  gn_final_f32_kernel<<<N, 1024, 0, st>>>(part, gamma, beta, scale, shift, HW, C, slots, eps);
   CFB_LAUNCH_CHECK();
   return 0;
 }
