@@ -51,6 +51,7 @@ SIGNATURES = {
     'cfb_attention': (c_int, [_P, _P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, _P]),
     'cfb_layer_norm': (c_int, [_P, _P, _P, _P, _P, _P, c_int32, c_int32, c_int32, _P]),
     'cfb_adain_nhwc': (c_int, [_P, _P, _P, c_int32, c_int32, c_int32, _P]),
+    'cfb_debug_umma_probe': (c_int, [_P, c_int32, _P, _P, c_int32, _P, _P]),
     'cfb_nchw_to_nhwc': (c_int, [_P, _P, c_int32, c_int32, c_int32, _P]),
     'cfb_nhwc_to_nchw': (c_int, [_P, _P, c_int32, c_int32, c_int32, _P]),
 }

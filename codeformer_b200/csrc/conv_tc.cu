@@ -208,6 +208,7 @@ struct TcParams {
   int m_tiles, n_tiles;
   int kblocks;            // Cin / 64
   int chunk;              // k-blocks accumulated in TMEM before the partial sum is folded into registers
+  int PW, PH;             // halo engine: input patch (BW+k-1) x (BH+k-1) pixels fetched once per 64-channel block
   const float* bias;
   const float* residual;
   int out_act;
@@ -232,6 +233,14 @@ struct TcCfg {
   static constexpr int STAGES = (BN == 64) ? 4 : 3;
   static constexpr int TMEM_COLS = TC_SLOTS * BN;          // 256 or 512 columns (power of two)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  // halo engine: 16x8-pixel tiles; the (16+2)x(8+2) input patch of one 64-channel block is fetched ONCE (hi and lo
+  // planes) and all 9 taps read it through row-shifted UMMA descriptors; weights stream through their own ring.
+  static constexpr int H_A_PLANE = 23 * 1024;              // >= 18*10*128 B, 1024-aligned
+  static constexpr int H_A_SLOT = 2 * H_A_PLANE;
+  static constexpr int H_A_SLOTS = 2;
+  static constexpr int H_B_SLOT = 2 * B_BYTES;
+  static constexpr int H_B_SLOTS = (BN == 64) ? 8 : 4;
+  static constexpr int H_SMEM_BYTES = H_A_SLOTS * H_A_SLOT + H_B_SLOTS * H_B_SLOT + 1024 + 256;
 };
 
 // Butterfly reduction of G per-lane group sums over the 32 lanes of a warp: after log2(G) exchange steps every lane
@@ -261,7 +270,7 @@ __device__ __forceinline__ void warp_group_reduce(float (&v)[G], int lane) {
 // cross terms (lo*hi, hi*lo) are issued first while the slot is still tiny, and the epilogue warps fold every
 // finished slot into fp32 registers with round-to-nearest adds while the tensor core fills the next slot.
 // CPG > 0: the epilogue also emits GroupNorm(32) partial sums of the stored tile (CPG = Cout/32 channels per group).
-template <int BN, int CPG>
+template <int BN, int CPG, bool HALO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const TcParams p) {
@@ -269,21 +278,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  // ring "full/empty": per-tap engine = STAGES k-block stages; halo engine = weight (B) slots.  "afull/aempty": halo A slots.
+  constexpr int NRING = HALO ? Cfg::H_B_SLOTS : STAGES;
+  uint8_t* ring_base = HALO ? smem + Cfg::H_A_SLOTS * Cfg::H_A_SLOT : smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_base + NRING * (HALO ? Cfg::H_B_SLOT : Cfg::STAGE_BYTES));
   uint64_t* full = bars;
-  uint64_t* empty = bars + STAGES;
-  uint64_t* cfull = bars + 2 * STAGES;
-  uint64_t* cempty = bars + 2 * STAGES + TC_SLOTS;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * TC_SLOTS);
+  uint64_t* empty = bars + NRING;
+  uint64_t* cfull = bars + 2 * NRING;
+  uint64_t* cempty = bars + 2 * NRING + TC_SLOTS;
+  uint64_t* afull = bars + 2 * NRING + 2 * TC_SLOTS;
+  uint64_t* aempty = afull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
+    for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(afull + a), 1); mbar_init(smem_u32(aempty + a), 1); }
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_lo) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_hi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_lo) : "memory");
-    for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(full + s), 1); mbar_init(smem_u32(empty + s), 1); }
+    for (int s = 0; s < NRING; ++s) { mbar_init(smem_u32(full + s), 1); mbar_init(smem_u32(empty + s), 1); }
     for (int a = 0; a < TC_SLOTS; ++a) { mbar_init(smem_u32(cfull + a), 1); mbar_init(smem_u32(cempty + a), TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -306,6 +321,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int aslot = 0;
+      uint32_t aphase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
         const int per_img = p.tiles_x * p.tiles_y;
@@ -313,19 +330,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int rem = mt - n * per_img;
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
         const int y0 = ty * p.BH * p.stride, x0 = tx * p.BW * p.stride;
-        for (int tap = 0; tap < p.taps; ++tap) {
-          const int r = (p.taps == 9) ? tap / 3 : 0;
-          const int s = (p.taps == 9) ? tap - r * 3 : 0;
+        if constexpr (HALO) {
           for (int kb = 0; kb < p.kblocks; ++kb) {
-            mbar_wait(smem_u32(empty + stage), phase ^ 1);
-            const uint32_t fb = smem_u32(full + stage);
-            mbar_expect_tx(fb, (uint32_t)Cfg::STAGE_BYTES);
-            const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-            tma_load_4d(sa, &tmA_hi, fb, kb * 64, x0 + s - p.pad, y0 + r - p.pad, n);
-            tma_load_4d(sa + TC_A_BYTES, &tmA_lo, fb, kb * 64, x0 + s - p.pad, y0 + r - p.pad, n);
-            tma_load_3d(sa + 2 * TC_A_BYTES, &tmB_hi, fb, kb * 64, nt * BN, tap);
-            tma_load_3d(sa + 2 * TC_A_BYTES + Cfg::B_BYTES, &tmB_lo, fb, kb * 64, nt * BN, tap);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            mbar_wait(smem_u32(aempty + aslot), aphase ^ 1);
+            const uint32_t ab = smem_u32(afull + aslot);
+            mbar_expect_tx(ab, (uint32_t)(2 * p.PW * p.PH * 128));
+            const uint32_t sa = smem_u32(smem + aslot * Cfg::H_A_SLOT);
+            tma_load_4d(sa, &tmA_hi, ab, kb * 64, x0 - p.pad, y0 - p.pad, n);
+            tma_load_4d(sa + Cfg::H_A_PLANE, &tmA_lo, ab, kb * 64, x0 - p.pad, y0 - p.pad, n);
+            if (++aslot == Cfg::H_A_SLOTS) { aslot = 0; aphase ^= 1; }
+            for (int tap = 0; tap < p.taps; ++tap) {
+              mbar_wait(smem_u32(empty + stage), phase ^ 1);
+              const uint32_t fb = smem_u32(full + stage);
+              mbar_expect_tx(fb, (uint32_t)Cfg::H_B_SLOT);
+              const uint32_t sb = smem_u32(ring_base + stage * Cfg::H_B_SLOT);
+              tma_load_3d(sb, &tmB_hi, fb, kb * 64, nt * BN, tap);
+              tma_load_3d(sb + Cfg::B_BYTES, &tmB_lo, fb, kb * 64, nt * BN, tap);
+              if (++stage == NRING) { stage = 0; phase ^= 1; }
+            }
+          }
+        } else {
+          for (int tap = 0; tap < p.taps; ++tap) {
+            const int r = (p.taps == 9) ? tap / 3 : 0;
+            const int s = (p.taps == 9) ? tap - r * 3 : 0;
+            for (int kb = 0; kb < p.kblocks; ++kb) {
+              mbar_wait(smem_u32(empty + stage), phase ^ 1);
+              const uint32_t fb = smem_u32(full + stage);
+              mbar_expect_tx(fb, (uint32_t)Cfg::STAGE_BYTES);
+              const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+              tma_load_4d(sa, &tmA_hi, fb, kb * 64, x0 + s - p.pad, y0 + r - p.pad, n);
+              tma_load_4d(sa + TC_A_BYTES, &tmA_lo, fb, kb * 64, x0 + s - p.pad, y0 + r - p.pad, n);
+              tma_load_3d(sa + 2 * TC_A_BYTES, &tmB_hi, fb, kb * 64, nt * BN, tap);
+              tma_load_3d(sa + 2 * TC_A_BYTES + Cfg::B_BYTES, &tmB_lo, fb, kb * 64, nt * BN, tap);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
           }
         }
       }
@@ -339,33 +377,83 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       uint32_t phase = 0;
       int slot = 0;
       uint32_t slot_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        for (int it0 = 0; it0 < nk; it0 += p.chunk) {
-          mbar_wait(smem_u32(cempty + slot), slot_phase ^ 1);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)(slot * BN);
-          const int it1 = (it0 + p.chunk < nk) ? it0 + p.chunk : nk;
-          for (int it = it0; it < it1; ++it) {
-            mbar_wait(smem_u32(full + stage), phase);
-            tc_fence_after();
-            const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-            const uint32_t a_hi = sa, a_lo = sa + TC_A_BYTES, b_hi = sa + 2 * TC_A_BYTES,
-                           b_lo = sa + 2 * TC_A_BYTES + Cfg::B_BYTES;
-            // 64-wide k-block = 4 x UMMA_K(16): +32 B inside the 128B swizzle atom.  Cross terms first.
+      if constexpr (HALO) {
+        // A descriptors: rows of the tile are pixels (h, w) of a 16x8 patch; patch row h is one 8-row core-matrix
+        // group that starts (h + r) * PW + s rows into the halo buffer => group stride SBO = PW*128 B and a start
+        // address that is only 128-byte aligned.  The tensor core applies the 128B swizzle on absolute shared-memory
+        // address bits (verified on B200 with tools/umma_probe.py: base_offset must stay 0), i.e. exactly the
+        // pattern the TMA unit used when it wrote the buffer.
+        const uint64_t a_desc_hi_bits = ((uint64_t)1 << 16) | ((uint64_t)((p.PW * 128) >> 4) << 32) | ((uint64_t)1 << 46) |
+                                        ((uint64_t)2 << 61);
+        int aslot = 0;
+        uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+          int it = 0;
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(smem_u32(afull + aslot), aphase);
+            const uint32_t a_hi0 = smem_u32(smem + aslot * Cfg::H_A_SLOT), a_lo0 = a_hi0 + Cfg::H_A_PLANE;
+            for (int tap = 0; tap < p.taps; ++tap, ++it) {
+              const int r = (p.taps == 9) ? tap / 3 : 0;
+              const int sft = (p.taps == 9) ? tap - r * 3 : 0;
+              const bool first = (it % p.chunk) == 0;
+              if (first) mbar_wait(smem_u32(cempty + slot), slot_phase ^ 1);
+              mbar_wait(smem_u32(full + stage), phase);
+              tc_fence_after();
+              const uint32_t d_tmem = tmem_base + (uint32_t)(slot * BN);
+              const uint32_t aoff = (uint32_t)((r * p.PW + sft) * 128);
+              const uint32_t a_hi = a_hi0 + aoff, a_lo = a_lo0 + aoff;
+              const uint32_t b_hi = smem_u32(ring_base + stage * Cfg::H_B_SLOT), b_lo = b_hi + Cfg::B_BYTES;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              tc_mma_f16(d_tmem, umma_desc_sw128(a_lo + k * 32), umma_desc_sw128(b_hi + k * 32), idesc,
-                         (it > it0 || k > 0) ? 1u : 0u);
-              tc_mma_f16(d_tmem, umma_desc_sw128(a_hi + k * 32), umma_desc_sw128(b_lo + k * 32), idesc, 1u);
+              for (int k = 0; k < 4; ++k) {
+                tc_mma_f16(d_tmem, a_desc_hi_bits | (uint64_t)(((a_lo + k * 32) >> 4) & 0x3FFFu), umma_desc_sw128(b_hi + k * 32),
+                           idesc, (!first || k > 0) ? 1u : 0u);
+                tc_mma_f16(d_tmem, a_desc_hi_bits | (uint64_t)(((a_hi + k * 32) >> 4) & 0x3FFFu), umma_desc_sw128(b_lo + k * 32),
+                           idesc, 1u);
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                tc_mma_f16(d_tmem, a_desc_hi_bits | (uint64_t)(((a_hi + k * 32) >> 4) & 0x3FFFu), umma_desc_sw128(b_hi + k * 32),
+                           idesc, 1u);
+              tc_commit(smem_u32(empty + stage));
+              if (++stage == NRING) { stage = 0; phase ^= 1; }
+              if ((it % p.chunk) == p.chunk - 1 || it == nk - 1) {
+                tc_commit(smem_u32(cfull + slot));
+                if (++slot == TC_SLOTS) { slot = 0; slot_phase ^= 1; }
+              }
             }
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              tc_mma_f16(d_tmem, umma_desc_sw128(a_hi + k * 32), umma_desc_sw128(b_hi + k * 32), idesc, 1u);
-            tc_commit(smem_u32(empty + stage));           // smem slot reusable once these MMAs have read it
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            tc_commit(smem_u32(aempty + aslot));          // all taps of this 64-channel block have read the patch
+            if (++aslot == Cfg::H_A_SLOTS) { aslot = 0; aphase ^= 1; }
           }
-          tc_commit(smem_u32(cfull + slot));              // partial sum complete -> epilogue warps fold it
-          if (++slot == TC_SLOTS) { slot = 0; slot_phase ^= 1; }
+        }
+      } else {
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+          for (int it0 = 0; it0 < nk; it0 += p.chunk) {
+            mbar_wait(smem_u32(cempty + slot), slot_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(slot * BN);
+            const int it1 = (it0 + p.chunk < nk) ? it0 + p.chunk : nk;
+            for (int it = it0; it < it1; ++it) {
+              mbar_wait(smem_u32(full + stage), phase);
+              tc_fence_after();
+              const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+              const uint32_t a_hi = sa, a_lo = sa + TC_A_BYTES, b_hi = sa + 2 * TC_A_BYTES,
+                             b_lo = sa + 2 * TC_A_BYTES + Cfg::B_BYTES;
+              // 64-wide k-block = 4 x UMMA_K(16): +32 B inside the 128B swizzle atom.  Cross terms first.
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                tc_mma_f16(d_tmem, umma_desc_sw128(a_lo + k * 32), umma_desc_sw128(b_hi + k * 32), idesc,
+                           (it > it0 || k > 0) ? 1u : 0u);
+                tc_mma_f16(d_tmem, umma_desc_sw128(a_hi + k * 32), umma_desc_sw128(b_lo + k * 32), idesc, 1u);
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                tc_mma_f16(d_tmem, umma_desc_sw128(a_hi + k * 32), umma_desc_sw128(b_hi + k * 32), idesc, 1u);
+              tc_commit(smem_u32(empty + stage));           // smem slot reusable once these MMAs have read it
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            tc_commit(smem_u32(cfull + slot));              // partial sum complete -> epilogue warps fold it
+            if (++slot == TC_SLOTS) { slot = 0; slot_phase ^= 1; }
+          }
         }
       }
     }
@@ -526,9 +614,24 @@ static int tc_chunk_kblocks() {
   return v;
 }
 
+// halo engine (one patch fetch per 64-channel block, taps via shifted descriptors): stride-1 convs on 16x8 tiles.
+// env CFB_TC_HALO=0 forces the per-tap engine everywhere (A/B experiments).
+static bool halo_enabled() {
+  static bool v = [] { const char* e = getenv("CFB_TC_HALO"); return !(e && atoi(e) == 0); }();
+  return v;
+}
+struct TcGeom { int BW, BH; bool halo; };
+static TcGeom tc_geometry(const ConvArgs& a) {
+  TcGeom g;
+  g.halo = halo_enabled() && a.mode != CONV_DOWN && a.Wo % 8 == 0 && a.Ho % 16 == 0;
+  if (g.halo) { g.BW = 8; g.BH = 16; }
+  else { g.BW = tile_bw(a.Wo); g.BH = 128 / g.BW; }
+  return g;
+}
+
 int tc_tiles_per_image(const ConvArgs& a) {
-  const int BW = tile_bw(a.Wo);
-  return (a.Wo / BW) * (a.Ho / (128 / BW));
+  const TcGeom g = tc_geometry(a);
+  return (a.Wo / g.BW) * (a.Ho / g.BH);
 }
 
 bool tc_supported(const ConvArgs& a) {
@@ -536,9 +639,9 @@ bool tc_supported(const ConvArgs& a) {
   if (!(a.ksize == 1 || a.ksize == 3)) return false;
   if (a.mode == CONV_DOWN && a.ksize != 3) return false;
   if (a.Wo < 1 || a.Ho < 1) return false;
-  const int BW = tile_bw(a.Wo);
+  const TcGeom g = tc_geometry(a);
+  const int BW = g.BW, BH = g.BH;
   if (128 % BW != 0 || a.Wo % BW != 0) return false;
-  const int BH = 128 / BW;
   if (a.Ho % BH != 0) return false;
   if ((int64_t)a.N * (a.Ho / BH) * (a.Wo / BW) * (a.Cout / 64) > 0x7fffffffLL) return false;
   return true;
@@ -551,20 +654,28 @@ size_t tc_scratch_bytes(const ConvArgs& a) {
   return 2 * plane;
 }
 
-template <int BN, int CPG>
-static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
-                     const TcParams& p, int sm_count, cudaStream_t st) {
+template <int BN, int CPG, bool HALO>
+static int launch_tc2(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                      const TcParams& p, int sm_count, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
+  constexpr int SMEM = HALO ? Cfg::H_SMEM_BYTES : Cfg::SMEM_BYTES;
+  static_assert(SMEM <= 232448, "shared memory budget");
   static bool attr_done = false;
   if (!attr_done) {
-    CFB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, CPG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    CFB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, CPG, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_done = true;
   }
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < sm_count ? total : sm_count;
-  conv_tc_kernel<BN, CPG><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(a_hi, a_lo, b_hi, b_lo, p);
+  conv_tc_kernel<BN, CPG, HALO><<<grid, TC_THREADS, SMEM, st>>>(a_hi, a_lo, b_hi, b_lo, p);
   CFB_LAUNCH_CHECK();
   return 0;
+}
+template <int BN, int CPG>
+static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                     const TcParams& p, int sm_count, cudaStream_t st) {
+  if (p.PW > 0) return launch_tc2<BN, CPG, true>(a_hi, a_lo, b_hi, b_lo, p, sm_count, st);
+  return launch_tc2<BN, CPG, false>(a_hi, a_lo, b_hi, b_lo, p, sm_count, st);
 }
 
 // GroupNorm partial sums can be emitted for (BN=64, Cout=64) and (BN=128, Cout in {128,256,512})
@@ -593,14 +704,17 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
     CFB_LAUNCH_CHECK();
   }
   // ---- tensor maps
-  const int BW = tile_bw(a.Wo), BH = 128 / BW;
+  const TcGeom geo = tc_geometry(a);
+  const int BW = geo.BW, BH = geo.BH;
+  const int PW = geo.halo ? BW + a.ksize - 1 : 0, PH = geo.halo ? BH + a.ksize - 1 : 0;
   const int BN = (a.Cout % 128 == 0) ? 128 : 64;
   CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
   {
     const int sp = a.mode == CONV_DOWN ? 2 : 1;
     const uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)Wp, (uint64_t)Hp, (uint64_t)a.N};
     const uint64_t str[3] = {(uint64_t)a.Cin * 2, (uint64_t)Wp * a.Cin * 2, (uint64_t)Hp * Wp * a.Cin * 2};
-    const uint32_t box[4] = {64, (uint32_t)(BW * sp), (uint32_t)(BH * sp), 1};   // ceil(box/stride) = BW x BH elements land
+    // per-tap engine: ceil(box/stride) = BW x BH pixels land; halo engine: the whole (BW+k-1) x (BH+k-1) patch
+    const uint32_t box[4] = {64, (uint32_t)(geo.halo ? PW : BW * sp), (uint32_t)(geo.halo ? PH : BH * sp), 1};
     CFB_CHECK(make_map(&mA_hi, hi, 4, dims, str, box, sp));
     CFB_CHECK(make_map(&mA_lo, lo, 4, dims, str, box, sp));
   }
@@ -616,6 +730,7 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
   p.N = a.N; p.Ho = a.Ho; p.Wo = a.Wo; p.Cout = a.Cout;
   p.taps = a.ksize * a.ksize; p.pad = a.mode == CONV_DOWN ? 0 : a.ksize / 2; p.stride = a.mode == CONV_DOWN ? 2 : 1;
   p.chunk = tc_chunk_kblocks();
+  p.PW = PW; p.PH = PH;
   p.BW = BW; p.BH = BH; p.tiles_x = a.Wo / BW; p.tiles_y = a.Ho / BH;
   p.m_tiles = a.N * p.tiles_x * p.tiles_y; p.n_tiles = a.Cout / BN; p.kblocks = a.Cin / 64;
   p.bias = a.bias; p.residual = a.residual; p.out_act = a.out_act;
@@ -636,6 +751,93 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
   }
   CFB_REQUIRE(false, "conv_tc: no kernel variant for this configuration");
   return 1;
+}
+
+
+// ------------------------------------------------------------------------------------------------------
+// Diagnostics: which shared-memory rows does a K-major SWIZZLE_128B UMMA descriptor read when its start address is
+// NOT 1024-byte aligned (row-shifted views of one TMA-written tile) and how does the `base_offset` field enter?
+// D = A_view * I, so D[m][n] reveals the (row, 16-byte chunk) of A that reached the tensor core.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+umma_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const int* __restrict__ cfg,
+                  int ncfg, int rowsA, float* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                        // rowsA x 128 B (<= 32 KB)
+  uint8_t* sB = smem + 32768;                // 64 x 128 B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 32768 + 8192);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(bars), 1);
+    mbar_init(smem_u32(bars + 1), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(64u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(smem_u32(bars), (uint32_t)(rowsA * 128 + 64 * 128));
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(sA)), "l"(&tmA), "r"(smem_u32(bars)), "r"(0), "r"(0) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(sB)), "l"(&tmB), "r"(smem_u32(bars)), "r"(0), "r"(0) : "memory");
+  }
+  mbar_wait(smem_u32(bars), 0);
+  tc_fence_after();
+  constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  for (int c = 0; c < ncfg; ++c) {
+    const int shift = cfg[c * 3 + 0], boff = cfg[c * 3 + 1], sbo = cfg[c * 3 + 2];
+    if (threadIdx.x == 0) {
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t a_addr = smem_u32(sA) + shift * 128 + k * 32;
+        const uint64_t a_desc = (uint64_t)((a_addr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
+                                ((uint64_t)1 << 46) | ((uint64_t)(boff & 7) << 49) | ((uint64_t)2 << 61);
+        tc_mma_f16(tmem_base, a_desc, umma_desc_sw128(smem_u32(sB) + k * 32), idesc, k > 0 ? 1u : 0u);
+      }
+      tc_commit(smem_u32(bars + 1));
+    }
+    mbar_wait(smem_u32(bars + 1), (uint32_t)(c & 1));
+    tc_fence_after();
+    uint32_t r0[32], r1[32];
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    tmem_ld32(taddr, r0);
+    tmem_ld32(taddr + 32, r1);
+    tmem_ld_wait();
+    float* o = out + ((int64_t)c * 128 + warp * 32 + lane) * 64;
+    for (int j = 0; j < 32; ++j) { o[j] = __uint_as_float(r0[j]); o[32 + j] = __uint_as_float(r1[j]); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64u) : "memory");
+}
+
+int umma_probe(const void* a_f16, int rowsA, const void* b_f16, const int* cfg_dev, int ncfg, float* out, cudaStream_t st) {
+  CFB_REQUIRE(rowsA >= 8 && rowsA <= 256, "umma_probe: 8..256 rows");
+  CUtensorMap mA, mB;
+  {
+    const uint64_t dims[2] = {64, (uint64_t)rowsA};
+    const uint64_t str[1] = {128};
+    const uint32_t box[2] = {64, (uint32_t)rowsA};
+    CFB_CHECK(make_map(&mA, a_f16, 2, dims, str, box));
+  }
+  {
+    const uint64_t dims[2] = {64, 64};
+    const uint64_t str[1] = {128};
+    const uint32_t box[2] = {64, 64};
+    CFB_CHECK(make_map(&mB, b_f16, 2, dims, str, box));
+  }
+  const int smem = 32768 + 8192 + 64 + 1024;
+  umma_probe_kernel<<<1, 128, smem, st>>>(mA, mB, cfg_dev, ncfg, rowsA, out);
+  CFB_LAUNCH_CHECK();
+  return 0;
 }
 
 }  // namespace cfb

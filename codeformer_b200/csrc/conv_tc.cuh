@@ -14,4 +14,6 @@ size_t tc_scratch_bytes(const ConvArgs& a);   // operand (hi/lo fp16 activation 
 bool tc_can_emit_stats(const ConvArgs& a);    // GroupNorm(32) partial sums available from the epilogue for this shape
 int tc_tiles_per_image(const ConvArgs& a);    // 128-pixel tiles per image (GroupNorm partial slots = 4x this)
 int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st);
+// diagnostics (tools/umma_probe.py): row-shifted SWIZZLE_128B descriptor views
+int umma_probe(const void* a_f16, int rowsA, const void* b_f16, const int* cfg_dev, int ncfg, float* out, cudaStream_t st);
 }  // namespace cfb

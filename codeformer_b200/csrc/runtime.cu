@@ -1009,6 +1009,13 @@ int cfb_conv2d_nhwc(const float* in, const float* weight_oihw, const float* bias
   API_END(1)
 }
 
+int cfb_debug_umma_probe(const void* a_f16, int32_t rows_a, const void* b_f16, const int32_t* cfg_dev, int32_t ncfg, float* out,
+                         void* stream) {
+  API_BEGIN
+  return cfb::umma_probe(a_f16, rows_a, b_f16, cfg_dev, ncfg, out, (cudaStream_t)stream);
+  API_END(1)
+}
+
 int64_t cfb_gn_workspace_bytes(int32_t n, int32_t hw, int32_t c) { return (int64_t)cfb::gn_workspace_bytes(n, hw, c) + 256; }
 int cfb_group_norm_coef(const float* x, const float* gamma, const float* beta, float* scale, float* shift, int32_t n,
                         int32_t hw, int32_t c, int32_t groups, float eps, void* workspace, int64_t workspace_bytes,

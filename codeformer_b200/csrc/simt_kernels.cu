@@ -275,17 +275,18 @@ int conv_first(const float* x, const float* wgt, const float* bias, float* out, 
   return 0;
 }
 
+// 4 horizontally adjacent output pixels per thread: every weight read from shared memory feeds 4 pixels.
 __global__ void __launch_bounds__(256) conv_last_kernel(const float* __restrict__ in, const float* __restrict__ in_scale,
                                                         const float* __restrict__ in_shift, const float* __restrict__ wgt,
                                                         const float* __restrict__ bias, float* __restrict__ out, int N,
                                                         int H, int W, int Cin) {
   extern __shared__ __align__(16) float sm[];
-  float* ws = sm;                 // [9][Cin][3] padded to 4 -> [9][Cin][4]
+  float* ws = sm;                 // [9][Cin][3] padded -> [9][Cin][4]
   float* sc = ws + 9 * Cin * 4;   // [Cin]
   float* sh = sc + Cin;
   const int64_t HW = (int64_t)H * W;
-  const int64_t pix = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  const int n = (int)(((int64_t)blockIdx.x * 256) / HW);  // HW % 256 == 0: whole CTA in one image
+  const int64_t pix0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+  const int n = (int)(((int64_t)blockIdx.x * 1024) / HW);  // HW % 1024 == 0: whole CTA in one image
   for (int i = threadIdx.x; i < 9 * Cin; i += 256) {
     ws[i * 4 + 0] = wgt[i * 3 + 0]; ws[i * 4 + 1] = wgt[i * 3 + 1]; ws[i * 4 + 2] = wgt[i * 3 + 2]; ws[i * 4 + 3] = 0.f;
   }
@@ -294,41 +295,60 @@ __global__ void __launch_bounds__(256) conv_last_kernel(const float* __restrict_
     sh[i] = in_shift ? in_shift[(int64_t)n * Cin + i] : 0.f;
   }
   __syncthreads();
-  const int rem = (int)(pix - (int64_t)n * HW);
-  const int y = rem / W, xq = rem - y * W;
-  float a0 = bias ? bias[0] : 0.f, a1 = bias ? bias[1] : 0.f, a2 = bias ? bias[2] : 0.f;
+  const int rem = (int)(pix0 - (int64_t)n * HW);
+  const int y = rem / W, x0 = rem - y * W;     // W % 4 == 0: the 4 pixels share a row
+  float acc[4][3];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) { acc[p][0] = bias ? bias[0] : 0.f; acc[p][1] = bias ? bias[1] : 0.f; acc[p][2] = bias ? bias[2] : 0.f; }
   for (int r = 0; r < 3; ++r) {
     const int iy = y + r - 1;
     if (iy < 0 || iy >= H) continue;
-    for (int s = 0; s < 3; ++s) {
-      const int ix = xq + s - 1;
-      if (ix < 0 || ix >= W) continue;
-      const float* p = in + (((int64_t)n * H + iy) * W + ix) * Cin;
-      const float* wt = ws + (r * 3 + s) * Cin * 4;
-      for (int c = 0; c < Cin; c += 4) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(p + c));
-        const float vv[4] = {fmaf(v.x, sc[c], sh[c]), fmaf(v.y, sc[c + 1], sh[c + 1]), fmaf(v.z, sc[c + 2], sh[c + 2]),
-                             fmaf(v.w, sc[c + 3], sh[c + 3])};
+    const float* rowp = in + ((int64_t)n * H + iy) * W * Cin;
+    for (int c = 0; c < Cin; c += 4) {
+      const float4 s4 = *reinterpret_cast<const float4*>(sc + c);
+      const float4 h4 = *reinterpret_cast<const float4*>(sh + c);
+      float v[6][4];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        const int ix = x0 + q - 1;
+        if (ix >= 0 && ix < W) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(rowp + (int64_t)ix * Cin + c));
+          v[q][0] = fmaf(t.x, s4.x, h4.x); v[q][1] = fmaf(t.y, s4.y, h4.y);
+          v[q][2] = fmaf(t.z, s4.z, h4.z); v[q][3] = fmaf(t.w, s4.w, h4.w);
+        } else {
+          v[q][0] = v[q][1] = v[q][2] = v[q][3] = 0.f;      // zero padding of the *normalised* tensor
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const float* wt = ws + ((r * 3 + s) * Cin + c) * 4;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float4 w4 = *reinterpret_cast<const float4*>(wt + (c + j) * 4);
-          a0 = fmaf(vv[j], w4.x, a0); a1 = fmaf(vv[j], w4.y, a1); a2 = fmaf(vv[j], w4.z, a2);
+          const float4 w4 = *reinterpret_cast<const float4*>(wt + j * 4);
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            acc[p][0] = fmaf(v[p + s][j], w4.x, acc[p][0]);
+            acc[p][1] = fmaf(v[p + s][j], w4.y, acc[p][1]);
+            acc[p][2] = fmaf(v[p + s][j], w4.z, acc[p][2]);
+          }
         }
       }
     }
   }
   float* o = out + (int64_t)n * 3 * HW + rem;
-  o[0] = a0; o[HW] = a1; o[2 * HW] = a2;
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    *reinterpret_cast<float4*>(o + k * HW) = make_float4(acc[0][k], acc[1][k], acc[2][k], acc[3][k]);
 }
 
 int conv_last(const float* in, const float* in_scale, const float* in_shift, const float* wgt, const float* bias,
               float* out, int N, int H, int W, int Cin, cudaStream_t st) {
   const int64_t HW = (int64_t)H * W;
-  CFB_REQUIRE(HW % 256 == 0 && Cin % 4 == 0, "conv_last: H*W must be a multiple of 256");
+  CFB_REQUIRE(HW % 1024 == 0 && W % 4 == 0 && Cin % 4 == 0, "conv_last: H*W must be a multiple of 1024, W and Cin of 4");
   if (N == 0) return 0;
   const size_t smem = (size_t)(9 * Cin * 4 + 2 * Cin) * sizeof(float);
   CFB_REQUIRE(smem <= 48 * 1024, "conv_last: Cin too large");
-  conv_last_kernel<<<(unsigned)(N * HW / 256), 256, smem, st>>>(in, in_scale, in_shift, wgt, bias, out, N, H, W, Cin);
+  conv_last_kernel<<<(unsigned)(N * HW / 1024), 256, smem, st>>>(in, in_scale, in_shift, wgt, bias, out, N, H, W, Cin);
   CFB_LAUNCH_CHECK();
   return 0;
 }

@@ -145,6 +145,10 @@ int cfb_layer_norm(const float* x, const float* gamma, const float* beta, float*
                    const float* pos, int32_t pos_rows, int32_t rows, int32_t c, void* stream);
 /* AdaIN of codeformer_arch.py:29-43 on NHWC [B,HW,C] */
 int cfb_adain_nhwc(const float* content, const float* style, float* out, int32_t batch, int32_t hw, int32_t c, void* stream);
+/* diagnostics: D = A_view * I for row-shifted 128B-swizzled UMMA descriptor views (tools/umma_probe.py).
+ * a_f16 [rows_a,64] fp16, b_f16 [64,64] fp16, cfg_dev [ncfg][3] = {shift_rows, base_offset, sbo_bytes}, out [ncfg,128,64] */
+int cfb_debug_umma_probe(const void* a_f16, int32_t rows_a, const void* b_f16, const int32_t* cfg_dev, int32_t ncfg,
+                         float* out, void* stream);
 /* layout plumbing */
 int cfb_nchw_to_nhwc(const float* in, float* out, int32_t n, int32_t c, int32_t hw, void* stream);
 int cfb_nhwc_to_nchw(const float* in, float* out, int32_t n, int32_t c, int32_t hw, void* stream);
