@@ -178,6 +178,33 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
       : "memory");
 }
+// One leader lane of a fully converged warp (same lane every time).  Keeping the role warps converged and predicating
+// only the issue instructions lets ptxas hold descriptors / addresses in uniform registers; an `if (lane == 0)` region
+// instead forces a per-instruction ELECT/branch waterfall around every UTCHMMA (measured: issue-bound at N=64).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// descriptors as {lo32 = address field | LBO, hi32 = SBO | version | layout}: only lo changes between MMAs
+__device__ __forceinline__ void tc_mma_f16_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+constexpr uint32_t DESC_HI_SW128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
+
 // K-major, 128B-swizzled operand tile (rows of 128 B, 8-row atoms 1024 B apart): cute::UMMA::SmemDescriptor
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
@@ -290,7 +317,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint64_t* aempty = afull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
+  const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(afull + a), 1); mbar_init(smem_u32(aempty + a), 1); }
@@ -317,8 +345,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const int nk = p.taps * p.kblocks;
 
   if (warp == 0) {
-    // ============================ TMA producer ============================
-    if (lane == 0) {
+    // ============================ TMA producer (warp converged, one elected lane issues) ============================
+    {
       int stage = 0;
       uint32_t phase = 0;
       int aslot = 0;
@@ -333,19 +361,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if constexpr (HALO) {
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(smem_u32(aempty + aslot), aphase ^ 1);
-            const uint32_t ab = smem_u32(afull + aslot);
-            mbar_expect_tx(ab, (uint32_t)(2 * p.PW * p.PH * 128));
-            const uint32_t sa = smem_u32(smem + aslot * Cfg::H_A_SLOT);
-            tma_load_4d(sa, &tmA_hi, ab, kb * 64, x0 - p.pad, y0 - p.pad, n);
-            tma_load_4d(sa + Cfg::H_A_PLANE, &tmA_lo, ab, kb * 64, x0 - p.pad, y0 - p.pad, n);
+            if (elect_one()) {
+              const uint32_t ab = smem_u32(afull + aslot);
+              mbar_expect_tx(ab, (uint32_t)(2 * p.PW * p.PH * 128));
+              const uint32_t sa = smem_u32(smem + aslot * Cfg::H_A_SLOT);
+              tma_load_4d(sa, &tmA_hi, ab, kb * 64, x0 - p.pad, y0 - p.pad, n);
+              tma_load_4d(sa + Cfg::H_A_PLANE, &tmA_lo, ab, kb * 64, x0 - p.pad, y0 - p.pad, n);
+            }
+            __syncwarp();
             if (++aslot == Cfg::H_A_SLOTS) { aslot = 0; aphase ^= 1; }
             for (int tap = 0; tap < p.taps; ++tap) {
               mbar_wait(smem_u32(empty + stage), phase ^ 1);
-              const uint32_t fb = smem_u32(full + stage);
-              mbar_expect_tx(fb, (uint32_t)Cfg::H_B_SLOT);
-              const uint32_t sb = smem_u32(ring_base + stage * Cfg::H_B_SLOT);
-              tma_load_3d(sb, &tmB_hi, fb, kb * 64, nt * BN, tap);
-              tma_load_3d(sb + Cfg::B_BYTES, &tmB_lo, fb, kb * 64, nt * BN, tap);
+              if (elect_one()) {
+                const uint32_t fb = smem_u32(full + stage);
+                mbar_expect_tx(fb, (uint32_t)Cfg::H_B_SLOT);
+                const uint32_t sb = smem_u32(ring_base + stage * Cfg::H_B_SLOT);
+                tma_load_3d(sb, &tmB_hi, fb, kb * 64, nt * BN, tap);
+                tma_load_3d(sb + Cfg::B_BYTES, &tmB_lo, fb, kb * 64, nt * BN, tap);
+              }
+              __syncwarp();
               if (++stage == NRING) { stage = 0; phase ^= 1; }
             }
           }
@@ -355,13 +389,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             const int s = (p.taps == 9) ? tap - r * 3 : 0;
             for (int kb = 0; kb < p.kblocks; ++kb) {
               mbar_wait(smem_u32(empty + stage), phase ^ 1);
-              const uint32_t fb = smem_u32(full + stage);
-              mbar_expect_tx(fb, (uint32_t)Cfg::STAGE_BYTES);
-              const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-              tma_load_4d(sa, &tmA_hi, fb, kb * 64, x0 + s - p.pad, y0 + r - p.pad, n);
-              tma_load_4d(sa + TC_A_BYTES, &tmA_lo, fb, kb * 64, x0 + s - p.pad, y0 + r - p.pad, n);
-              tma_load_3d(sa + 2 * TC_A_BYTES, &tmB_hi, fb, kb * 64, nt * BN, tap);
-              tma_load_3d(sa + 2 * TC_A_BYTES + Cfg::B_BYTES, &tmB_lo, fb, kb * 64, nt * BN, tap);
+              if (elect_one()) {
+                const uint32_t fb = smem_u32(full + stage);
+                mbar_expect_tx(fb, (uint32_t)Cfg::STAGE_BYTES);
+                const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                tma_load_4d(sa, &tmA_hi, fb, kb * 64, x0 + s - p.pad, y0 + r - p.pad, n);
+                tma_load_4d(sa + TC_A_BYTES, &tmA_lo, fb, kb * 64, x0 + s - p.pad, y0 + r - p.pad, n);
+                tma_load_3d(sa + 2 * TC_A_BYTES, &tmB_hi, fb, kb * 64, nt * BN, tap);
+                tma_load_3d(sa + 2 * TC_A_BYTES + Cfg::B_BYTES, &tmB_lo, fb, kb * 64, nt * BN, tap);
+              }
+              __syncwarp();
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
           }
@@ -369,8 +406,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ============================ MMA issuer ============================
-    if (lane == 0) {
+    // ============================ MMA issuer (warp converged, one elected lane issues) ============================
+    {
       // kind::f16, A=B=F16 (0), D=F32 (1<<4), K-major A and B, N>>3 @17, M>>4 @24   (cute::UMMA::InstrDescriptor)
       constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       int stage = 0;
@@ -383,8 +420,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         // address that is only 128-byte aligned.  The tensor core applies the 128B swizzle on absolute shared-memory
         // address bits (verified on B200 with tools/umma_probe.py: base_offset must stay 0), i.e. exactly the
         // pattern the TMA unit used when it wrote the buffer.
-        const uint64_t a_desc_hi_bits = ((uint64_t)1 << 16) | ((uint64_t)((p.PW * 128) >> 4) << 32) | ((uint64_t)1 << 46) |
-                                        ((uint64_t)2 << 61);
+        const uint32_t a_desc_hi = (uint32_t)((p.PW * 128) >> 4) | (1u << 14) | (2u << 29);
         int aslot = 0;
         uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -399,29 +435,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               if (first) mbar_wait(smem_u32(cempty + slot), slot_phase ^ 1);
               mbar_wait(smem_u32(full + stage), phase);
               tc_fence_after();
-              const uint32_t d_tmem = tmem_base + (uint32_t)(slot * BN);
-              const uint32_t aoff = (uint32_t)((r * p.PW + sft) * 128);
-              const uint32_t a_hi = a_hi0 + aoff, a_lo = a_lo0 + aoff;
-              const uint32_t b_hi = smem_u32(ring_base + stage * Cfg::H_B_SLOT), b_lo = b_hi + Cfg::B_BYTES;
+              if (elect_one()) {
+                const uint32_t d_tmem = tmem_base + (uint32_t)(slot * BN);
+                const uint32_t aoff = (uint32_t)((r * p.PW + sft) * 128);
+                const uint32_t ah = desc_lo(a_hi0 + aoff), al = desc_lo(a_lo0 + aoff);
+                const uint32_t sb = smem_u32(ring_base + stage * Cfg::H_B_SLOT);
+                const uint32_t bh = desc_lo(sb), bl = desc_lo(sb + Cfg::B_BYTES);
+                // 64-wide k-block = 4 x UMMA_K(16): +32 B (= +2 in the >>4 address field) inside the swizzle atom.
+                // Cross terms first (they are ~2^-11 of the main term: added while the slot is still small).
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                tc_mma_f16(d_tmem, a_desc_hi_bits | (uint64_t)(((a_lo + k * 32) >> 4) & 0x3FFFu), umma_desc_sw128(b_hi + k * 32),
-                           idesc, (!first || k > 0) ? 1u : 0u);
-                tc_mma_f16(d_tmem, a_desc_hi_bits | (uint64_t)(((a_hi + k * 32) >> 4) & 0x3FFFu), umma_desc_sw128(b_lo + k * 32),
-                           idesc, 1u);
+                for (int k = 0; k < 4; ++k) {
+                  tc_mma_f16_w(d_tmem, al + 2 * k, a_desc_hi, bh + 2 * k, DESC_HI_SW128, idesc, (!first || k > 0) ? 1u : 0u);
+                  tc_mma_f16_w(d_tmem, ah + 2 * k, a_desc_hi, bl + 2 * k, DESC_HI_SW128, idesc, 1u);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) tc_mma_f16_w(d_tmem, ah + 2 * k, a_desc_hi, bh + 2 * k, DESC_HI_SW128, idesc, 1u);
+                tc_commit(smem_u32(empty + stage));
+                if ((it % p.chunk) == p.chunk - 1 || it == nk - 1) tc_commit(smem_u32(cfull + slot));
+                if (tap == p.taps - 1) tc_commit(smem_u32(aempty + aslot));   // every tap of this block has read the patch
               }
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                tc_mma_f16(d_tmem, a_desc_hi_bits | (uint64_t)(((a_hi + k * 32) >> 4) & 0x3FFFu), umma_desc_sw128(b_hi + k * 32),
-                           idesc, 1u);
-              tc_commit(smem_u32(empty + stage));
+              __syncwarp();
               if (++stage == NRING) { stage = 0; phase ^= 1; }
               if ((it % p.chunk) == p.chunk - 1 || it == nk - 1) {
-                tc_commit(smem_u32(cfull + slot));
                 if (++slot == TC_SLOTS) { slot = 0; slot_phase ^= 1; }
               }
             }
-            tc_commit(smem_u32(aempty + aslot));          // all taps of this 64-channel block have read the patch
             if (++aslot == Cfg::H_A_SLOTS) { aslot = 0; aphase ^= 1; }
           }
         }
@@ -429,29 +467,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
           for (int it0 = 0; it0 < nk; it0 += p.chunk) {
             mbar_wait(smem_u32(cempty + slot), slot_phase ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(slot * BN);
             const int it1 = (it0 + p.chunk < nk) ? it0 + p.chunk : nk;
             for (int it = it0; it < it1; ++it) {
               mbar_wait(smem_u32(full + stage), phase);
               tc_fence_after();
-              const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-              const uint32_t a_hi = sa, a_lo = sa + TC_A_BYTES, b_hi = sa + 2 * TC_A_BYTES,
-                             b_lo = sa + 2 * TC_A_BYTES + Cfg::B_BYTES;
-              // 64-wide k-block = 4 x UMMA_K(16): +32 B inside the 128B swizzle atom.  Cross terms first.
+              if (elect_one()) {
+                const uint32_t d_tmem = tmem_base + (uint32_t)(slot * BN);
+                const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                const uint32_t ah = desc_lo(sa), al = desc_lo(sa + TC_A_BYTES), bh = desc_lo(sa + 2 * TC_A_BYTES),
+                               bl = desc_lo(sa + 2 * TC_A_BYTES + Cfg::B_BYTES);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                tc_mma_f16(d_tmem, umma_desc_sw128(a_lo + k * 32), umma_desc_sw128(b_hi + k * 32), idesc,
-                           (it > it0 || k > 0) ? 1u : 0u);
-                tc_mma_f16(d_tmem, umma_desc_sw128(a_hi + k * 32), umma_desc_sw128(b_lo + k * 32), idesc, 1u);
+                for (int k = 0; k < 4; ++k) {
+                  tc_mma_f16_w(d_tmem, al + 2 * k, DESC_HI_SW128, bh + 2 * k, DESC_HI_SW128, idesc, (it > it0 || k > 0) ? 1u : 0u);
+                  tc_mma_f16_w(d_tmem, ah + 2 * k, DESC_HI_SW128, bl + 2 * k, DESC_HI_SW128, idesc, 1u);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) tc_mma_f16_w(d_tmem, ah + 2 * k, DESC_HI_SW128, bh + 2 * k, DESC_HI_SW128, idesc, 1u);
+                tc_commit(smem_u32(empty + stage));           // smem slot reusable once these MMAs have read it
+                if (it == it1 - 1) tc_commit(smem_u32(cfull + slot));   // partial sum complete -> epilogue warps fold it
               }
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                tc_mma_f16(d_tmem, umma_desc_sw128(a_hi + k * 32), umma_desc_sw128(b_hi + k * 32), idesc, 1u);
-              tc_commit(smem_u32(empty + stage));           // smem slot reusable once these MMAs have read it
+              __syncwarp();
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
-            tc_commit(smem_u32(cfull + slot));              // partial sum complete -> epilogue warps fold it
             if (++slot == TC_SLOTS) { slot = 0; slot_phase ^= 1; }
           }
         }

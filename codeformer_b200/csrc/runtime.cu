@@ -524,6 +524,12 @@ struct Fwd {
     Tensor cat;
     CFB_CHECK(alloc(cat, dec.N, dec.H, dec.W, enc_feat.C + dec.C));
     if (!dry) CFB_CHECK(concat_channels(enc_feat.p, dec.p, cat.p, (int64_t)dec.N * dec.H * dec.W, enc_feat.C, dec.C, st));
+    if (enc_feat.gn_part && dec.gn_part && enc_feat.gn_slots == dec.gn_slots && enc_feat.C == dec.C) {
+      // GroupNorm statistics of the concatenation follow from the two sources' partial sums (no extra pass)
+      cat.gn_slots = dec.gn_slots;
+      CFB_CHECK(alloc_raw((void**)&cat.gn_part, (size_t)dec.N * cat.gn_slots * 64 * sizeof(float)));
+      if (!dry) CFB_CHECK(gn_cat_partials(enc_feat.gn_part, dec.gn_part, cat.gn_part, (int64_t)dec.N * cat.gn_slots, st));
+    }
     Tensor e;
     CFB_CHECK(resblock(f.enc, cat, e));
     release(cat);

@@ -510,6 +510,27 @@ int gn_coef_from_partials(const float* part, int slots, const float* gamma, cons
   return 0;
 }
 
+__global__ void gn_cat_partials_kernel(const float2* __restrict__ a, const float2* __restrict__ b, float2* __restrict__ out,
+                                       int64_t total) {
+  // group g of the concatenated tensor = two adjacent groups of one source: channels/group doubles, 32 groups stay
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i & 31);
+    const int64_t slot = i >> 5;
+    const float2* src = (g < 16) ? a + slot * 32 + 2 * g : b + slot * 32 + 2 * (g - 16);
+    const float2 u = __ldg(src), v = __ldg(src + 1);
+    out[i] = make_float2(u.x + v.x, u.y + v.y);
+  }
+}
+int gn_cat_partials(const float* a_part, const float* b_part, float* out_part, int64_t total_slots, cudaStream_t st) {
+  const int64_t total = total_slots * 32;
+  if (total == 0) return 0;
+  const int64_t blocks = (total + 255) / 256;
+  gn_cat_partials_kernel<<<(unsigned)(blocks > 2048 ? 2048 : blocks), 256, 0, st>>>((const float2*)a_part, (const float2*)b_part,
+                                                                                     (float2*)out_part, total);
+  CFB_LAUNCH_CHECK();
+  return 0;
+}
+
 __global__ void affine_act_kernel(const float4* __restrict__ x, const float* __restrict__ scale,
                                   const float* __restrict__ shift, float4* __restrict__ y, int64_t total4, int64_t HWC4,
                                   int C, int act) {
