@@ -52,6 +52,7 @@ SIGNATURES = {
     'cfb_layer_norm': (c_int, [_P, _P, _P, _P, _P, _P, c_int32, c_int32, c_int32, _P]),
     'cfb_adain_nhwc': (c_int, [_P, _P, _P, c_int32, c_int32, c_int32, _P]),
     'cfb_debug_umma_probe': (c_int, [_P, c_int32, _P, _P, c_int32, _P, _P]),
+    'cfb_debug_umma_rate': (c_int, [c_int32, c_int32, c_int32, _P, c_int32, _P]),
     'cfb_nchw_to_nhwc': (c_int, [_P, _P, c_int32, c_int32, c_int32, _P]),
     'cfb_nhwc_to_nchw': (c_int, [_P, _P, c_int32, c_int32, c_int32, _P]),
 }

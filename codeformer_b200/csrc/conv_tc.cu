@@ -251,14 +251,20 @@ struct TcParams {
 constexpr int TC_EPI_WARPS = 8;                       // 4 TMEM lane quadrants x 2 column halves
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // warp0 TMA, warp1 MMA, warps 2..9 epilogue
 constexpr int TC_A_BYTES = 128 * 128;                 // 128 pixels x 64 fp16
-constexpr int TC_SLOTS = 4;                           // TMEM partial-sum ring
 
 template <int BN>
 struct TcCfg {
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
   static constexpr int STAGES = (BN == 64) ? 4 : 3;
-  static constexpr int TMEM_COLS = TC_SLOTS * BN;          // 256 or 512 columns (power of two)
+  // One TMEM partial-sum slot = 2*BN columns: [ hi*hi | hi*lo + lo*hi ].  tcgen05.mma (M=128, SS operands) has a floor of
+  // ~107 cycles per instruction whatever N <= 128 is (tools/umma_rate.py: N=64 30 %, N=128 60 %, N=256 100 % of peak), so
+  // the hi and lo weight tiles -- adjacent in shared memory -- are fed as ONE N = 2*BN operand: A_hi x [B_hi;B_lo] fills
+  // both halves, A_lo x B_hi accumulates into the cross half.  2 MMAs per k-step instead of 3, and the small cross terms
+  // never meet the large accumulator inside the truncating tensor-core adder.
+  static constexpr int SLOT_COLS = 2 * BN;
+  static constexpr int SLOTS = 512 / SLOT_COLS;            // 2 (BN=128) or 4 (BN=64)
+  static constexpr int TMEM_COLS = 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   // halo engine: 16x8-pixel tiles; the (16+2)x(8+2) input patch of one 64-channel block is fetched ONCE (hi and lo
   // planes) and all 9 taps read it through row-shifted UMMA descriptors; weights stream through their own ring.
@@ -303,6 +309,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const TcParams p) {
   using Cfg = TcCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int TC_SLOTS = Cfg::SLOTS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   // ring "full/empty": per-tap engine = STAGES k-block stages; halo engine = weight (B) slots.  "afull/aempty": halo A slots.
@@ -409,7 +416,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // ============================ MMA issuer (warp converged, one elected lane issues) ============================
     {
       // kind::f16, A=B=F16 (0), D=F32 (1<<4), K-major A and B, N>>3 @17, M>>4 @24   (cute::UMMA::InstrDescriptor)
-      constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);          // N = BN
+      constexpr uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // N = 2*BN
       int stage = 0;
       uint32_t phase = 0;
       int slot = 0;
@@ -436,20 +444,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               mbar_wait(smem_u32(full + stage), phase);
               tc_fence_after();
               if (elect_one()) {
-                const uint32_t d_tmem = tmem_base + (uint32_t)(slot * BN);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(slot * Cfg::SLOT_COLS);
                 const uint32_t aoff = (uint32_t)((r * p.PW + sft) * 128);
                 const uint32_t ah = desc_lo(a_hi0 + aoff), al = desc_lo(a_lo0 + aoff);
-                const uint32_t sb = smem_u32(ring_base + stage * Cfg::H_B_SLOT);
-                const uint32_t bh = desc_lo(sb), bl = desc_lo(sb + Cfg::B_BYTES);
+                const uint32_t bh = desc_lo(smem_u32(ring_base + stage * Cfg::H_B_SLOT));   // [B_hi ; B_lo] contiguous rows
                 // 64-wide k-block = 4 x UMMA_K(16): +32 B (= +2 in the >>4 address field) inside the swizzle atom.
-                // Cross terms first (they are ~2^-11 of the main term: added while the slot is still small).
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  tc_mma_f16_w(d_tmem, al + 2 * k, a_desc_hi, bh + 2 * k, DESC_HI_SW128, idesc, (!first || k > 0) ? 1u : 0u);
-                  tc_mma_f16_w(d_tmem, ah + 2 * k, a_desc_hi, bl + 2 * k, DESC_HI_SW128, idesc, 1u);
+                  tc_mma_f16_w(d_tmem, ah + 2 * k, a_desc_hi, bh + 2 * k, DESC_HI_SW128, idesc2, (!first || k > 0) ? 1u : 0u);
+                  tc_mma_f16_w(d_tmem + BN, al + 2 * k, a_desc_hi, bh + 2 * k, DESC_HI_SW128, idesc, 1u);
                 }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) tc_mma_f16_w(d_tmem, ah + 2 * k, a_desc_hi, bh + 2 * k, DESC_HI_SW128, idesc, 1u);
                 tc_commit(smem_u32(empty + stage));
                 if ((it % p.chunk) == p.chunk - 1 || it == nk - 1) tc_commit(smem_u32(cfull + slot));
                 if (tap == p.taps - 1) tc_commit(smem_u32(aempty + aslot));   // every tap of this block has read the patch
@@ -472,17 +476,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               mbar_wait(smem_u32(full + stage), phase);
               tc_fence_after();
               if (elect_one()) {
-                const uint32_t d_tmem = tmem_base + (uint32_t)(slot * BN);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(slot * Cfg::SLOT_COLS);
                 const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                const uint32_t ah = desc_lo(sa), al = desc_lo(sa + TC_A_BYTES), bh = desc_lo(sa + 2 * TC_A_BYTES),
-                               bl = desc_lo(sa + 2 * TC_A_BYTES + Cfg::B_BYTES);
+                const uint32_t ah = desc_lo(sa), al = desc_lo(sa + TC_A_BYTES), bh = desc_lo(sa + 2 * TC_A_BYTES);   // [B_hi;B_lo]
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  tc_mma_f16_w(d_tmem, al + 2 * k, DESC_HI_SW128, bh + 2 * k, DESC_HI_SW128, idesc, (it > it0 || k > 0) ? 1u : 0u);
-                  tc_mma_f16_w(d_tmem, ah + 2 * k, DESC_HI_SW128, bl + 2 * k, DESC_HI_SW128, idesc, 1u);
+                  tc_mma_f16_w(d_tmem, ah + 2 * k, DESC_HI_SW128, bh + 2 * k, DESC_HI_SW128, idesc2, (it > it0 || k > 0) ? 1u : 0u);
+                  tc_mma_f16_w(d_tmem + BN, al + 2 * k, DESC_HI_SW128, bh + 2 * k, DESC_HI_SW128, idesc, 1u);
                 }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) tc_mma_f16_w(d_tmem, ah + 2 * k, DESC_HI_SW128, bh + 2 * k, DESC_HI_SW128, idesc, 1u);
                 tc_commit(smem_u32(empty + stage));           // smem slot reusable once these MMAs have read it
                 if (it == it1 - 1) tc_commit(smem_u32(cfull + slot));   // partial sum complete -> epilogue warps fold it
               }
@@ -511,22 +512,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       for (int it0 = 0; it0 < nk; it0 += p.chunk) {
         mbar_wait(smem_u32(cfull + slot), slot_phase);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(slot * BN + cbase);
-        if constexpr (HC == 64) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(slot * Cfg::SLOT_COLS + cbase);
+#pragma unroll
+        for (int c0 = 0; c0 < HC; c0 += 32) {          // main half at +0, cross half at +BN; round-to-nearest adds
           uint32_t r0[32], r1[32];
-          tmem_ld32(taddr, r0);
-          tmem_ld32(taddr + 32, r1);
+          tmem_ld32(taddr + c0, r0);
+          tmem_ld32(taddr + BN + c0, r1);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r0[j]);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc[32 + j] += __uint_as_float(r1[j]);
-        } else {
-          uint32_t r0[32];
-          tmem_ld32(taddr, r0);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r0[j]);
+          for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
         }
         tc_fence_before();
         __syncwarp();
@@ -645,16 +639,17 @@ static inline int tile_bw(int Wo) { return Wo < 128 ? Wo : 128; }
 static int tc_chunk_kblocks() {
   static int v = [] {
     const char* e = getenv("CFB_TC_CHUNK");
-    int c = e ? atoi(e) : 2;
+    int c = e ? atoi(e) : 4;
     return c < 1 ? 1 : (c > 4096 ? 4096 : c);
   }();
   return v;
 }
 
 // halo engine (one patch fetch per 64-channel block, taps via shifted descriptors): stride-1 convs on 16x8 tiles.
-// env CFB_TC_HALO=0 forces the per-tap engine everywhere (A/B experiments).
+// Measured on B200 (profiles/round1_*): correct, halves L2->SM traffic, but the row-shifted A views make the
+// tensor core's A fetch ~10-25 % slower and the MMA A-fetch floor is the binding limit => OFF by default; CFB_TC_HALO=1 enables.
 static bool halo_enabled() {
-  static bool v = [] { const char* e = getenv("CFB_TC_HALO"); return !(e && atoi(e) == 0); }();
+  static bool v = [] { const char* e = getenv("CFB_TC_HALO"); return e && atoi(e) != 0; }();
   return v;
 }
 struct TcGeom { int BW, BH; bool halo; };
@@ -873,6 +868,63 @@ int umma_probe(const void* a_f16, int rowsA, const void* b_f16, const int* cfg_d
   }
   const int smem = 32768 + 8192 + 64 + 1024;
   umma_probe_kernel<<<1, 128, smem, st>>>(mA, mB, cfg_dev, ncfg, rowsA, out);
+  CFB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Diagnostics: sustained tcgen05.mma rate (cycles per 128 x N x 16 MMA) as a function of N and of how many distinct
+// TMEM accumulators consecutive MMAs rotate over (1 = every MMA depends on the previous one's accumulator).
+// Operands are whatever is in shared memory (values irrelevant).  One CTA per SM.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) umma_rate_kernel(int N, int nacc, int reps, long long* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 4 * 16384 + 4 * 32768);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  for (int i = threadIdx.x; i < (4 * 16384 + 4 * 32768) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;  // fp16 1.0
+  if (threadIdx.x == 0) { mbar_init(smem_u32(bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) {
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t a0 = desc_lo(smem_u32(smem)), b0 = desc_lo(smem_u32(smem + 4 * 16384));
+    const long long t0 = clock64();
+    if (elect_one()) {
+      for (int r = 0; r < reps; ++r) {
+#pragma unroll 1
+        for (int i = 0; i < 12; ++i) {
+          const uint32_t d = tmem_base + (uint32_t)(((r * 12 + i) % nacc) * N);
+          tc_mma_f16_w(d, a0 + 2 * (i & 3) + (uint32_t)((i >> 2) * 1024), DESC_HI_SW128, b0 + 2 * (i & 3) + (uint32_t)((i >> 2) * 2048),
+                       DESC_HI_SW128, idesc, 1u);
+        }
+      }
+      tc_commit(smem_u32(bar));
+    }
+    __syncwarp();
+    mbar_wait(smem_u32(bar), 0);
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+int umma_rate(int N, int nacc, int reps, long long* out_dev, int ctas, cudaStream_t st) {
+  CFB_REQUIRE((N == 64 || N == 128 || N == 256) && nacc >= 1 && nacc * N <= 512, "umma_rate: bad configuration");
+  const int smem = 4 * 16384 + 4 * 32768 + 64 + 1024;
+  static bool done = false;
+  if (!done) { CFB_CUDA(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); done = true; }
+  umma_rate_kernel<<<ctas, 128, smem, st>>>(N, nacc, reps, out_dev);
   CFB_LAUNCH_CHECK();
   return 0;
 }

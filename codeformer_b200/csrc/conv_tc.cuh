@@ -16,4 +16,5 @@ int tc_tiles_per_image(const ConvArgs& a);    // 128-pixel tiles per image (Grou
 int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st);
 // diagnostics (tools/umma_probe.py): row-shifted SWIZZLE_128B descriptor views
 int umma_probe(const void* a_f16, int rowsA, const void* b_f16, const int* cfg_dev, int ncfg, float* out, cudaStream_t st);
+int umma_rate(int N, int nacc, int reps, long long* out_dev, int ctas, cudaStream_t st);
 }  // namespace cfb

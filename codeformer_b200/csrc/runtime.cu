@@ -1022,6 +1022,12 @@ int cfb_debug_umma_probe(const void* a_f16, int32_t rows_a, const void* b_f16, c
   API_END(1)
 }
 
+int cfb_debug_umma_rate(int32_t n, int32_t nacc, int32_t reps, int64_t* out_dev, int32_t ctas, void* stream) {
+  API_BEGIN
+  return cfb::umma_rate(n, nacc, reps, (long long*)out_dev, ctas, (cudaStream_t)stream);
+  API_END(1)
+}
+
 int64_t cfb_gn_workspace_bytes(int32_t n, int32_t hw, int32_t c) { return (int64_t)cfb::gn_workspace_bytes(n, hw, c) + 256; }
 int cfb_group_norm_coef(const float* x, const float* gamma, const float* beta, float* scale, float* shift, int32_t n,
                         int32_t hw, int32_t c, int32_t groups, float eps, void* workspace, int64_t workspace_bytes,

@@ -149,6 +149,9 @@ int cfb_adain_nhwc(const float* content, const float* style, float* out, int32_t
  * a_f16 [rows_a,64] fp16, b_f16 [64,64] fp16, cfg_dev [ncfg][3] = {shift_rows, base_offset, sbo_bytes}, out [ncfg,128,64] */
 int cfb_debug_umma_probe(const void* a_f16, int32_t rows_a, const void* b_f16, const int32_t* cfg_dev, int32_t ncfg,
                          float* out, void* stream);
+/* diagnostics: sustained tcgen05.mma issue rate; out_dev[ctas] receives the cycles for reps*12 MMAs of 128 x n x 16
+ * rotating over `nacc` TMEM accumulators (tools/umma_rate.py) */
+int cfb_debug_umma_rate(int32_t n, int32_t nacc, int32_t reps, int64_t* out_dev, int32_t ctas, void* stream);
 /* layout plumbing */
 int cfb_nchw_to_nhwc(const float* in, float* out, int32_t n, int32_t c, int32_t hw, void* stream);
 int cfb_nhwc_to_nchw(const float* in, float* out, int32_t n, int32_t c, int32_t hw, void* stream);

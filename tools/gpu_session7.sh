@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out; rm -f gpurun_out/summary.txt
 timeout 300 python tools/tc_probe.py > gpurun_out/tc_probe.log 2>&1; echo "tc_probe rc=$?" >> gpurun_out/summary.txt
-CFB_TC_HALO=0 timeout 300 python tools/tc_probe.py > gpurun_out/tc_probe_nohalo.log 2>&1; echo "tc_probe_nohalo rc=$?" >> gpurun_out/summary.txt
+CFB_TC_HALO=1 timeout 300 python tools/tc_probe.py > gpurun_out/tc_probe_nohalo.log 2>&1; echo "tc_probe_nohalo rc=$?" >> gpurun_out/summary.txt
 timeout 600 python -m pytest tests/test_gpu_kernels.py -q -m gpu > gpurun_out/t_kernels.log 2>&1; echo "kernels rc=$?" >> gpurun_out/summary.txt
 timeout 900 python -m pytest tests/test_gpu_e2e.py -q -m gpu -s > gpurun_out/t_e2e.log 2>&1; echo "e2e rc=$?" >> gpurun_out/summary.txt
 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench.log 2>&1; echo "bench rc=$?" >> gpurun_out/summary.txt
