@@ -81,29 +81,36 @@ int tc_split_weights(const float* oihw, __half* hi, __half* lo, int Cout, int Ci
 // ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float tc_silu(float x) { return x / (1.f + expf(-x)); }
 
+// One block = PB consecutive output pixels of ONE image; a thread keeps the same 8-channel slice for all its pixels, so
+// the per-(n,c) GroupNorm scale/shift is loaded once per block instead of once per element.
 __global__ void __launch_bounds__(256) tc_prep_kernel(const float* __restrict__ in, const float* __restrict__ scale,
                                                       const float* __restrict__ shift, int act, int up, int N, int H, int W,
-                                                      int C, __half* __restrict__ hi, __half* __restrict__ lo) {
+                                                      int C, int PB, __half* __restrict__ hi, __half* __restrict__ lo) {
   const int C8 = C >> 3;
   const int Hp = H << up, Wp = W << up;
-  const int64_t total = (int64_t)N * Hp * Wp * C8;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C8) * 8;
-    const int64_t pix = i / C8;
-    const int ox = (int)(pix % Wp);
-    const int oy = (int)((pix / Wp) % Hp);
-    const int n = (int)(pix / ((int64_t)Wp * Hp));
+  const int64_t img_px = (int64_t)Hp * Wp;
+  const int64_t pix0 = (int64_t)blockIdx.x * PB;          // PB divides Hp*Wp: the block stays inside image n
+  const int n = (int)(pix0 / img_px);
+  const int c = (threadIdx.x % C8) * 8;
+  const int pstep = 256 / C8;
+  float sv[8], hv[8];
+  if (scale) {
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + (int64_t)n * C + c));
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + (int64_t)n * C + c + 4));
+    const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + (int64_t)n * C + c));
+    const float4 h1 = __ldg(reinterpret_cast<const float4*>(shift + (int64_t)n * C + c + 4));
+    sv[0] = s0.x; sv[1] = s0.y; sv[2] = s0.z; sv[3] = s0.w; sv[4] = s1.x; sv[5] = s1.y; sv[6] = s1.z; sv[7] = s1.w;
+    hv[0] = h0.x; hv[1] = h0.y; hv[2] = h0.z; hv[3] = h0.w; hv[4] = h1.x; hv[5] = h1.y; hv[6] = h1.z; hv[7] = h1.w;
+  }
+  for (int pl = threadIdx.x / C8; pl < PB; pl += pstep) {
+    const int64_t pix = pix0 + pl;
+    const int64_t rem = pix - (int64_t)n * img_px;
+    const int oy = (int)(rem / Wp), ox = (int)(rem - (int64_t)oy * Wp);
     const float* src = in + (((int64_t)n * H + (oy >> up)) * W + (ox >> up)) * C + c;
     const float4 a = __ldg(reinterpret_cast<const float4*>(src));
     const float4 b = __ldg(reinterpret_cast<const float4*>(src + 4));
     float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
     if (scale) {
-      const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + (int64_t)n * C + c));
-      const float4 s1 = __ldg(reinterpret_cast<const float4*>(scale + (int64_t)n * C + c + 4));
-      const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + (int64_t)n * C + c));
-      const float4 h1 = __ldg(reinterpret_cast<const float4*>(shift + (int64_t)n * C + c + 4));
-      const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-      const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sv[j], hv[j]);
     }
@@ -541,6 +548,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       float gs[G], gq[G];
 #pragma unroll
       for (int g = 0; g < G; ++g) { gs[g] = 0.f; gq[g] = 0.f; }
+      float4 res[HC / 4];                    // residual row slice: all loads in flight before the first use
+#pragma unroll
+      for (int j = 0; j < HC; j += 4)
+        res[j / 4] = p.residual ? __ldg(reinterpret_cast<const float4*>(p.residual + off0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int j = 0; j < HC; j += 4) {
         float4 v = make_float4(acc[j] * wsi, acc[j + 1] * wsi, acc[j + 2] * wsi, acc[j + 3] * wsi);
@@ -549,8 +560,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
         }
         const int64_t off = off0 + j;
-        if (p.residual) {
-          const float4 q = __ldg(reinterpret_cast<const float4*>(p.residual + off));
+        {
+          const float4 q = res[j / 4];
           v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
         }
         if (p.out_act == OUT_LRELU) {
@@ -729,10 +740,14 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
   __half* hi = (__half*)scratch;
   __half* lo = (__half*)((char*)scratch + plane);
   {
-    const int64_t total = Mp * (a.Cin / 8);
-    const int64_t blocks = (total + 255) / 256;
-    tc_prep_kernel<<<(unsigned)(blocks > 148 * 32 ? 148 * 32 : blocks), 256, 0, st>>>(
-        a.in, a.in_scale, a.in_shift, a.in_act, a.mode == CONV_UP ? 1 : 0, a.N, a.H, a.W, a.Cin, hi, lo);
+    const int C8 = a.Cin / 8;
+    CFB_REQUIRE(C8 <= 256 && 256 % C8 == 0, "conv_tc: Cin must be 64 * 2^k (<= 2048)");
+    const int64_t img_px = (int64_t)Hp * Wp;
+    int64_t PB = (int64_t)(256 / C8) * 32;                 // 32 pixels per thread
+    while (PB > 1 && img_px % PB != 0) PB >>= 1;
+    CFB_REQUIRE(PB >= 256 / C8 || img_px % PB == 0, "conv_tc: image size not supported by the operand prep kernel");
+    tc_prep_kernel<<<(unsigned)(Mp / PB), 256, 0, st>>>(a.in, a.in_scale, a.in_shift, a.in_act, a.mode == CONV_UP ? 1 : 0, a.N, a.H,
+                                                        a.W, a.Cin, (int)PB, hi, lo);
     CFB_LAUNCH_CHECK();
   }
   // ---- tensor maps
