@@ -743,9 +743,14 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
     const int C8 = a.Cin / 8;
     CFB_REQUIRE(C8 <= 256 && 256 % C8 == 0, "conv_tc: Cin must be 64 * 2^k (<= 2048)");
     const int64_t img_px = (int64_t)Hp * Wp;
-    int64_t PB = (int64_t)(256 / C8) * 32;                 // 32 pixels per thread
+    // pixels per thread: up to 32 (amortises the per-block affine loads) but never so many that the grid drops
+    // below ~16 blocks per SM -- the small 16x16 / 32x32 layers are latency-bound otherwise
+    const int pstep = 256 / C8;
+    int iters = 32;
+    while (iters > 1 && Mp / ((int64_t)pstep * iters) < 148 * 16) iters >>= 1;
+    int64_t PB = (int64_t)pstep * iters;
     while (PB > 1 && img_px % PB != 0) PB >>= 1;
-    CFB_REQUIRE(PB >= 256 / C8 || img_px % PB == 0, "conv_tc: image size not supported by the operand prep kernel");
+    CFB_REQUIRE(PB >= 1 && img_px % PB == 0 && Mp % PB == 0, "conv_tc: image size not supported by the operand prep kernel");
     tc_prep_kernel<<<(unsigned)(Mp / PB), 256, 0, st>>>(a.in, a.in_scale, a.in_shift, a.in_act, a.mode == CONV_UP ? 1 : 0, a.N, a.H,
                                                         a.W, a.Cin, (int)PB, hi, lo);
     CFB_LAUNCH_CHECK();
