@@ -118,4 +118,8 @@ size_t vq_workspace_bytes(int T, int D, int K);
 int vq_nearest(const float* z, const float* codebook, int T, int D, int K, float beta, int64_t* idx, float* zq,
                float* stats, float* onehot, void* ws, cudaStream_t st);
 
+// tensor-core variant: dots [T,K] = z . E^T already computed (tcgen05 1x1 conv); selects the nearest code per token
+size_t vq_select_workspace_bytes(int T, int K);
+int vq_select_from_dots(const float* z, const float* codebook, const float* dots, int T, int D, int K, float beta, int64_t* idx,
+                        float* zq, float* stats, float* onehot, void* ws, cudaStream_t st);
 }  // namespace cfb

@@ -125,6 +125,7 @@ struct cfb_net {
   std::map<int, FuseW> fuse;          // keyed by feature size
   std::vector<LayerW> layers;
   ConvW feat_emb, idx_lin;
+  ConvW vq_code;                      // codebook as a 1x1 'conv' (distance GEMM of VectorQuantizer.forward on tensor cores)
   NormW idx_norm;
   const float* position_emb = nullptr;
   const float* codebook = nullptr;    // points into slab copy
@@ -232,6 +233,7 @@ static int build_plan(cfb_net* n) {
   gp.push_back({B_NORM, cin, cin, curr});
   gp.push_back({B_CONV, cin, 3, curr});
   build_blocks(n, n->enc, "encoder", ep);
+  mk_conv(n, n->vq_code, "quantize.embedding", c.emb_dim, c.codebook_size, 1, false);
   build_blocks(n, n->gen, "generator", gp);
   if (c.kind == 1) {
     CFB_REQUIRE(c.img_size == 512 && c.emb_dim == 256, "config: CodeFormer is defined for 512x512 / emb 256");
@@ -734,13 +736,32 @@ static int vqae_forward_impl(cfb_net* n, const float* x, float* out, int64_t* id
   const int T = B * z.H * z.W;
   Tensor zq;
   CFB_CHECK(f.alloc(zq, B, z.H, z.W, z.C));
-  void* vws = nullptr;
   int64_t* idx_buf = idx;
   float* stats_buf = stats;
-  CFB_CHECK(f.alloc_raw(&vws, vq_workspace_bytes(T, z.C, c.codebook_size)));
   if (!idx_buf) CFB_CHECK(f.alloc_raw((void**)&idx_buf, (size_t)T * 8));
   if (!stats_buf) CFB_CHECK(f.alloc_raw((void**)&stats_buf, 16));
-  if (!dry) CFB_CHECK(vq_nearest(z.p, n->codebook, T, z.C, c.codebook_size, c.beta, idx_buf, zq.p, stats_buf, onehot, vws, st));
+  bool tc_vq = false;
+  {
+    ConvArgs probe;
+    probe.N = B; probe.H = z.H; probe.W = z.W; probe.Cin = z.C; probe.Ho = z.H; probe.Wo = z.W; probe.Cout = c.codebook_size;
+    probe.ksize = 1; probe.mode = CONV_SAME;
+    tc_vq = n->engine != 1 && n->tc_ok && tc_supported(probe);
+  }
+  if (tc_vq) {
+    // distance GEMM z.E^T on the tcgen05 engine, then the warp-shuffle argmin over the dot products
+    Tensor dots;
+    Fwd::ConvOpt o;
+    CFB_CHECK(f.conv(n->vq_code, z, dots, o));
+    void* vws = nullptr;
+    CFB_CHECK(f.alloc_raw(&vws, vq_select_workspace_bytes(T, c.codebook_size)));
+    if (!dry)
+      CFB_CHECK(vq_select_from_dots(z.p, n->codebook, dots.p, T, z.C, c.codebook_size, c.beta, idx_buf, zq.p, stats_buf, onehot, vws, st));
+    f.release(dots);
+  } else {
+    void* vws = nullptr;
+    CFB_CHECK(f.alloc_raw(&vws, vq_workspace_bytes(T, z.C, c.codebook_size)));
+    if (!dry) CFB_CHECK(vq_nearest(z.p, n->codebook, T, z.C, c.codebook_size, c.beta, idx_buf, zq.p, stats_buf, onehot, vws, st));
+  }
   f.release(z);
   CFB_CHECK(f.generator(zq, out, nullptr, {}, 0.f));
   return 0;
@@ -919,9 +940,27 @@ int cfb_vqae_forward(cfb_net* n, const float* x, float* out, int64_t* idx, float
   API_END(1)
 }
 
+static bool vq_tc_args(cfb::ConvArgs& a, int batch, int h, int w, int dim, int codes) {
+  a = cfb::ConvArgs();
+  a.N = batch; a.H = h; a.W = w; a.Cin = dim; a.Ho = h; a.Wo = w; a.Cout = codes; a.ksize = 1; a.mode = cfb::CONV_SAME;
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return major == 10 && cfb::tc_supported(a);
+}
+
 int64_t cfb_vq_workspace_bytes(int32_t batch, int32_t hw, int32_t dim, int32_t codes) {
   const int64_t T = (int64_t)batch * hw;
-  return (int64_t)cfb::vq_workspace_bytes((int)T, dim, codes) + 2 * ((T * dim * 4 + 1023) / 1024 * 1024) + 4096;
+  const int64_t tok = 2 * ((T * dim * 4 + 1023) / 1024 * 1024);
+  const int64_t simt = (int64_t)cfb::vq_workspace_bytes((int)T, dim, codes);
+  // tensor-core path (16x16-style latents): split codebook + operand planes + the [T,K] dot products
+  const int64_t wsplit = 2 * (int64_t)align256((size_t)codes * dim * 2) + 256;
+  const int64_t planes = 2 * ((T * dim * 2 + 1023) / 1024 * 1024);
+  const int64_t dots = (T * codes * 4 + 1023) / 1024 * 1024;
+  const int64_t tc = wsplit + planes + dots + (int64_t)cfb::vq_select_workspace_bytes((int)T, codes) + 4096;
+  return tok + (simt > tc ? simt : tc) + 8192;
 }
 
 int cfb_vq_nearest(const float* z, const float* codebook, int32_t batch, int32_t h, int32_t w, int32_t dim, int32_t codes,
@@ -938,7 +977,24 @@ int cfb_vq_nearest(const float* z, const float* codebook, int32_t batch, int32_t
   float* zt = (float*)p; p += tb;
   float* zqt = (float*)p; p += tb;
   CFB_CHECK(cfb::nchw_to_nhwc(z, zt, batch, dim, h * w, st));
-  CFB_CHECK(cfb::vq_nearest(zt, codebook, (int)T, dim, codes, beta, idx, zqt, stats, min_encodings, p, st));
+  cfb::ConvArgs a;
+  if (vq_tc_args(a, batch, h, w, dim, codes)) {
+    __half* whi = (__half*)p; p += align256((size_t)codes * dim * 2);
+    __half* wlo = (__half*)p; p += align256((size_t)codes * dim * 2);
+    float* wsc = (float*)p; p += 256;
+    p = (char*)(((uintptr_t)p + 1023) / 1024 * 1024);
+    void* planes = p; p += 2 * (((size_t)T * dim * 2 + 1023) / 1024 * 1024);
+    float* dots = (float*)p; p += ((size_t)T * codes * 4 + 1023) / 1024 * 1024;
+    a.in = zt; a.out = dots; a.wgt_hi = whi; a.wgt_lo = wlo; a.wscale_inv = wsc + 1;
+    int dev = 0, sms = 148;
+    CFB_CUDA(cudaGetDevice(&dev));
+    CFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CFB_CHECK(cfb::tc_split_weights(codebook, whi, wlo, codes, dim, 1, wsc, st));
+    CFB_CHECK(cfb::conv_tc(a, planes, sms, st));
+    CFB_CHECK(cfb::vq_select_from_dots(zt, codebook, dots, (int)T, dim, codes, beta, idx, zqt, stats, min_encodings, p, st));
+  } else {
+    CFB_CHECK(cfb::vq_nearest(zt, codebook, (int)T, dim, codes, beta, idx, zqt, stats, min_encodings, p, st));
+  }
   CFB_CHECK(cfb::nhwc_to_nchw(zqt, z_q, batch, dim, h * w, st));
   return 0;
   API_END(1)

@@ -1141,4 +1141,78 @@ int vq_nearest(const float* z, const float* codebook, int T, int D, int K, float
   return 0;
 }
 
+// ---- VectorQuantizer on the tensor-core path: the distance GEMM z.E^T comes from the tcgen05 engine (1x1 conv with the
+// codebook as weights); this kernel forms d = |z|^2 + |e|^2 - 2 z.e, takes the first minimum (warp shuffle), and emits
+// the straight-through z_q, squared error, distance sum and histogram.  One warp per token, 8 tokens per CTA.
+__global__ void __launch_bounds__(256) vq_select_kernel(const float* __restrict__ z, const float* __restrict__ E,
+                                                        const float* __restrict__ e2, const float* __restrict__ dots, int T,
+                                                        int D, int K, int64_t* __restrict__ idx, float* __restrict__ zq,
+                                                        double* __restrict__ part, unsigned* __restrict__ hist) {
+  __shared__ double red[8][2];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const int tok = blockIdx.x * 8 + w;
+  double se = 0.0, dsum = 0.0;
+  if (tok < T) {
+    float z2 = 0.f;
+    for (int c = l; c < D; c += 32) { const float v = z[(int64_t)tok * D + c]; z2 = fmaf(v, v, z2); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) z2 += __shfl_xor_sync(0xffffffffu, z2, o);
+    float best = INFINITY;
+    int bi = 0x7fffffff;
+    const float* dr = dots + (int64_t)tok * K;
+    for (int k = l; k < K; k += 32) {
+      const float d = (z2 + __ldg(e2 + k)) - 2.f * __ldg(dr + k);
+      dsum += (double)d;
+      if (d < best) { best = d; bi = k; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (od < best || (od == best && oi < bi)) { best = od; bi = oi; }
+    }
+    if (l == 0) { idx[tok] = (int64_t)bi; atomicAdd(hist + bi, 1u); }
+    for (int c = l; c < D; c += 32) {
+      const float zz = z[(int64_t)tok * D + c];
+      const float diff = __ldg(E + (int64_t)bi * D + c) - zz;
+      se += (double)(diff * diff);
+      zq[(int64_t)tok * D + c] = zz + diff;      // z + (z_q - z), vqgan_arch.py:57
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { se += __shfl_xor_sync(0xffffffffu, se, o); dsum += __shfl_xor_sync(0xffffffffu, dsum, o); }
+  if (l == 0) { red[w][0] = se; red[w][1] = dsum; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < 8; ++i) { a += red[i][0]; b += red[i][1]; }
+    part[blockIdx.x * 2] = a; part[blockIdx.x * 2 + 1] = b;
+  }
+}
+
+size_t vq_select_workspace_bytes(int T, int K) {
+  return ((size_t)K * 4 + 255) / 256 * 256 + ((size_t)((T + 7) / 8) * 16 + 255) / 256 * 256 + (size_t)K * 4 + 256;
+}
+int vq_select_from_dots(const float* z, const float* codebook, const float* dots, int T, int D, int K, float beta, int64_t* idx,
+                        float* zq, float* stats, float* onehot, void* ws, cudaStream_t st) {
+  if (T == 0) return 0;
+  char* p = (char*)ws;
+  float* e2 = (float*)p; p += ((size_t)K * 4 + 255) / 256 * 256;
+  double* part = (double*)p; p += ((size_t)((T + 7) / 8) * 16 + 255) / 256 * 256;
+  unsigned* hist = (unsigned*)p;
+  const int ctas = (T + 7) / 8;
+  vq_e2_kernel<<<(K + 7) / 8, 256, 0, st>>>(codebook, e2, hist, K, D);
+  CFB_LAUNCH_CHECK();
+  vq_select_kernel<<<ctas, 256, 0, st>>>(z, codebook, e2, dots, T, D, K, idx, zq, part, hist);
+  CFB_LAUNCH_CHECK();
+  vq_final_kernel<<<1, 256, 0, st>>>(part, hist, ctas, T, D, K, beta, stats);
+  CFB_LAUNCH_CHECK();
+  if (onehot) {
+    CFB_CUDA(cudaMemsetAsync(onehot, 0, (size_t)T * K * sizeof(float), st));
+    onehot_kernel<<<(T + 255) / 256, 256, 0, st>>>(idx, onehot, T, K);
+    CFB_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
 }  // namespace cfb
