@@ -76,6 +76,63 @@ int tc_split_weights(const float* oihw, __half* hi, __half* lo, int Cout, int Ci
   return 0;
 }
 
+// Upsample (nearest x2) followed by a 3x3 conv == four 2x2 convs on the LOW-resolution tensor, one per output parity
+// (py,px): out[2y+py][2x+px] = sum_{dy,dx in {0,1}} W'[py][px][dy][dx] . in[y+dy+py-1][x+dx+px-1], where W' pre-sums the 3x3
+// taps that read the same source pixel (rows: py=0 -> {r0 | r1+r2}, py=1 -> {r0+r1 | r2}; same for columns).  2.25x fewer
+// MACs and the operand planes stay at the low resolution.  Sums are formed in fp32 before the hi/lo split.
+__device__ __forceinline__ void up4_range(int parity, int d, int& lo, int& hi) {
+  if (parity == 0) { lo = d == 0 ? 0 : 1; hi = d == 0 ? 0 : 2; }
+  else { lo = d == 0 ? 0 : 2; hi = d == 0 ? 1 : 2; }
+}
+__device__ __forceinline__ float up4_weight(const float* __restrict__ w, int co, int ci, int Cin, int tap16) {
+  const int ph = tap16 >> 2, py = ph >> 1, px = ph & 1, dy = (tap16 >> 1) & 1, dx = tap16 & 1;
+  int r0, r1, s0, s1;
+  up4_range(py, dy, r0, r1);
+  up4_range(px, dx, s0, s1);
+  float v = 0.f;
+  for (int r = r0; r <= r1; ++r)
+    for (int q = s0; q <= s1; ++q) v += w[(((int64_t)co * Cin + ci) * 3 + r) * 3 + q];
+  return v;
+}
+__global__ void tc_absmax_up4_kernel(const float* __restrict__ w, int Cout, int Cin, unsigned* __restrict__ slot) {
+  const int64_t total = (int64_t)16 * Cout * Cin;
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin), co = (int)((i / Cin) % Cout), tap = (int)(i / ((int64_t)Cout * Cin));
+    m = fmaxf(m, fabsf(up4_weight(w, co, ci, Cin, tap)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(slot, __float_as_uint(m));
+}
+__global__ void tc_split_up4_kernel(const float* __restrict__ w, __half* __restrict__ hi, __half* __restrict__ lo, int Cout,
+                                    int Cin, float* __restrict__ slot) {
+  const float amax = __uint_as_float(reinterpret_cast<const unsigned*>(slot)[0]);
+  int e = 0;
+  if (amax > 0.f && isfinite(amax)) frexpf(amax, &e);
+  const float scale = exp2f((float)(14 - e));
+  const int64_t total = (int64_t)16 * Cout * Cin;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin), co = (int)((i / Cin) % Cout), tap = (int)(i / ((int64_t)Cout * Cin));
+    const float v = up4_weight(w, co, ci, Cin, tap) * scale;
+    const __half h = __float2half_rn(v);
+    hi[i] = h;
+    lo[i] = __float2half_rn(v - __half2float(h));
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) slot[1] = exp2f((float)(e - 14));
+}
+int tc_split_weights_up4(const float* oihw3x3, __half* hi, __half* lo, int Cout, int Cin, float* scale_slot, cudaStream_t st) {
+  const int64_t total = (int64_t)16 * Cout * Cin;
+  const int64_t blocks = (total + 255) / 256;
+  const unsigned g = (unsigned)(blocks > 1024 ? 1024 : blocks);
+  CFB_CUDA(cudaMemsetAsync(scale_slot, 0, 2 * sizeof(float), st));
+  tc_absmax_up4_kernel<<<g, 256, 0, st>>>(oihw3x3, Cout, Cin, reinterpret_cast<unsigned*>(scale_slot));
+  CFB_LAUNCH_CHECK();
+  tc_split_up4_kernel<<<g, 256, 0, st>>>(oihw3x3, hi, lo, Cout, Cin, scale_slot);
+  CFB_LAUNCH_CHECK();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // operand preparation: fp32 NHWC (+ fused GroupNorm affine, SiLU, nearest x2) -> fp16 hi / lo NHWC planes
 // ------------------------------------------------------------------------------------------------------
@@ -242,6 +299,7 @@ struct TcParams {
   int m_tiles, n_tiles;
   int kblocks;            // Cin / 64
   int chunk;              // k-blocks accumulated in TMEM before the partial sum is folded into registers
+  int up4;                // Upsample as four 2x2 convs: m-tile = (low-res tile, output parity), 4 taps, weights [16][Cout][Cin]
   int PW, PH;             // halo engine: input patch (BW+k-1) x (BH+k-1) pixels fetched once per 64-channel block
   const float* bias;
   const float* residual;
@@ -367,9 +425,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       uint32_t aphase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+        const int mtl = p.up4 ? (mt >> 2) : mt;            // low-res tile; (mt & 3) = output parity (py,px)
+        const int par_y = p.up4 ? ((mt & 3) >> 1) : 0, par_x = p.up4 ? (mt & 1) : 0;
         const int per_img = p.tiles_x * p.tiles_y;
-        const int n = mt / per_img;
-        const int rem = mt - n * per_img;
+        const int n = mtl / per_img;
+        const int rem = mtl - n * per_img;
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
         const int y0 = ty * p.BH * p.stride, x0 = tx * p.BW * p.stride;
         if constexpr (HALO) {
@@ -399,8 +459,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           }
         } else {
           for (int tap = 0; tap < p.taps; ++tap) {
-            const int r = (p.taps == 9) ? tap / 3 : 0;
-            const int s = (p.taps == 9) ? tap - r * 3 : 0;
+            // source offset of this tap and its weight slice: 3x3 -> (r,s)-pad; 2x2 parity conv -> (dy+py-1, dx+px-1)
+            int r, s, btap = tap;
+            if (p.up4) { r = (tap >> 1) + par_y; s = (tap & 1) + par_x; btap = (mt & 3) * 4 + tap; }
+            else { r = (p.taps == 9) ? tap / 3 : 0; s = (p.taps == 9) ? tap - r * 3 : 0; }
             for (int kb = 0; kb < p.kblocks; ++kb) {
               mbar_wait(smem_u32(empty + stage), phase ^ 1);
               if (elect_one()) {
@@ -409,8 +471,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
                 tma_load_4d(sa, &tmA_hi, fb, kb * 64, x0 + s - p.pad, y0 + r - p.pad, n);
                 tma_load_4d(sa + TC_A_BYTES, &tmA_lo, fb, kb * 64, x0 + s - p.pad, y0 + r - p.pad, n);
-                tma_load_3d(sa + 2 * TC_A_BYTES, &tmB_hi, fb, kb * 64, nt * BN, tap);
-                tma_load_3d(sa + 2 * TC_A_BYTES + Cfg::B_BYTES, &tmB_lo, fb, kb * 64, nt * BN, tap);
+                tma_load_3d(sa + 2 * TC_A_BYTES, &tmB_hi, fb, kb * 64, nt * BN, btap);
+                tma_load_3d(sa + 2 * TC_A_BYTES + Cfg::B_BYTES, &tmB_lo, fb, kb * 64, nt * BN, btap);
               }
               __syncwarp();
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -536,12 +598,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
       // ---- finalize this tile: scale, bias, residual, activation, SFT, store (fp32 NHWC), GroupNorm partials
       const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      const int mtl = p.up4 ? (mt >> 2) : mt;
       const int per_img = p.tiles_x * p.tiles_y;
-      const int n = mt / per_img;
-      const int rem = mt - n * per_img;
+      const int n = mtl / per_img;
+      const int rem = mtl - n * per_img;
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
       const int h = row / p.BW, w = row - h * p.BW;
-      const int64_t pix = ((int64_t)n * p.Ho + (ty * p.BH + h)) * p.Wo + (tx * p.BW + w);
+      int oy = ty * p.BH + h, ox = tx * p.BW + w;
+      if (p.up4) { oy = 2 * oy + ((mt & 3) >> 1); ox = 2 * ox + (mt & 1); }   // this tile writes one output parity
+      const int64_t pix = ((int64_t)n * p.Ho + oy) * p.Wo + ox;
       const int col0 = nt * BN + cbase;
       const int64_t off0 = pix * p.Cout + col0;
       constexpr int G = (CPG > 0) ? HC / CPG : 1;
@@ -666,14 +731,15 @@ static bool halo_enabled() {
 struct TcGeom { int BW, BH; bool halo; };
 static TcGeom tc_geometry(const ConvArgs& a) {
   TcGeom g;
-  g.halo = halo_enabled() && a.mode != CONV_DOWN && a.Wo % 8 == 0 && a.Ho % 16 == 0;
+  g.halo = halo_enabled() && a.mode == CONV_SAME && a.Wo % 8 == 0 && a.Ho % 16 == 0;
   if (g.halo) { g.BW = 8; g.BH = 16; }
-  else { g.BW = tile_bw(a.Wo); g.BH = 128 / g.BW; }
+  else { g.BW = tile_bw(a.mode == CONV_UP ? a.W : a.Wo); g.BH = 128 / g.BW; }   // Upsample: tiles live on the low-res grid
   return g;
 }
 
 int tc_tiles_per_image(const ConvArgs& a) {
   const TcGeom g = tc_geometry(a);
+  if (a.mode == CONV_UP) return 4 * (a.W / g.BW) * (a.H / g.BH);
   return (a.Wo / g.BW) * (a.Ho / g.BH);
 }
 
@@ -684,15 +750,17 @@ bool tc_supported(const ConvArgs& a) {
   if (a.Wo < 1 || a.Ho < 1) return false;
   const TcGeom g = tc_geometry(a);
   const int BW = g.BW, BH = g.BH;
-  if (128 % BW != 0 || a.Wo % BW != 0) return false;
-  if (a.Ho % BH != 0) return false;
-  if ((int64_t)a.N * (a.Ho / BH) * (a.Wo / BW) * (a.Cout / 64) > 0x7fffffffLL) return false;
+  const int Wt = a.mode == CONV_UP ? a.W : a.Wo, Ht = a.mode == CONV_UP ? a.H : a.Ho;   // grid the tiles live on
+  if (a.mode == CONV_UP && a.ksize != 3) return false;
+  if (128 % BW != 0 || Wt % BW != 0) return false;
+  if (Ht % BH != 0) return false;
+  if ((int64_t)a.N * (a.Ho / BH + 1) * (a.Wo / BW + 1) * (a.Cout / 64) > 0x7fffffffLL) return false;
   return true;
 }
 
 size_t tc_scratch_bytes(const ConvArgs& a) {
   if (!tc_supported(a)) return 0;
-  const int Hp = a.mode == CONV_DOWN ? a.H : a.Ho, Wp = a.mode == CONV_DOWN ? a.W : a.Wo;   // operand plane resolution
+  const int Hp = a.mode == CONV_SAME ? a.Ho : a.H, Wp = a.mode == CONV_SAME ? a.Wo : a.W;   // operand plane = input resolution
   const size_t plane = ((size_t)a.N * Hp * Wp * a.Cin * 2 + 1023) / 1024 * 1024;
   return 2 * plane;
 }
@@ -734,7 +802,7 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
   const int64_t M = (int64_t)a.N * a.Ho * a.Wo;
   if (M == 0) return 0;
   // ---- operand planes (fp16 hi/lo NHWC; at the output resolution, or the input resolution for Downsample)
-  const int Hp = a.mode == CONV_DOWN ? a.H : a.Ho, Wp = a.mode == CONV_DOWN ? a.W : a.Wo;
+  const int Hp = a.mode == CONV_SAME ? a.Ho : a.H, Wp = a.mode == CONV_SAME ? a.Wo : a.W;
   const int64_t Mp = (int64_t)a.N * Hp * Wp;
   const size_t plane = ((size_t)Mp * a.Cin * 2 + 1023) / 1024 * 1024;
   __half* hi = (__half*)scratch;
@@ -751,7 +819,7 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
     int64_t PB = (int64_t)pstep * iters;
     while (PB > 1 && img_px % PB != 0) PB >>= 1;
     CFB_REQUIRE(PB >= 1 && img_px % PB == 0 && Mp % PB == 0, "conv_tc: image size not supported by the operand prep kernel");
-    tc_prep_kernel<<<(unsigned)(Mp / PB), 256, 0, st>>>(a.in, a.in_scale, a.in_shift, a.in_act, a.mode == CONV_UP ? 1 : 0, a.N, a.H,
+    tc_prep_kernel<<<(unsigned)(Mp / PB), 256, 0, st>>>(a.in, a.in_scale, a.in_shift, a.in_act, 0, a.N, a.H,
                                                         a.W, a.Cin, (int)PB, hi, lo);
     CFB_LAUNCH_CHECK();
   }
@@ -771,7 +839,7 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
     CFB_CHECK(make_map(&mA_lo, lo, 4, dims, str, box, sp));
   }
   {
-    const int taps = a.ksize * a.ksize;
+    const int taps = a.mode == CONV_UP ? 16 : a.ksize * a.ksize;
     const uint64_t dims[3] = {(uint64_t)a.Cin, (uint64_t)a.Cout, (uint64_t)taps};
     const uint64_t str[2] = {(uint64_t)a.Cin * 2, (uint64_t)a.Cout * a.Cin * 2};
     const uint32_t box[3] = {64, (uint32_t)BN, 1};
@@ -781,10 +849,13 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
   TcParams p;
   p.N = a.N; p.Ho = a.Ho; p.Wo = a.Wo; p.Cout = a.Cout;
   p.taps = a.ksize * a.ksize; p.pad = a.mode == CONV_DOWN ? 0 : a.ksize / 2; p.stride = a.mode == CONV_DOWN ? 2 : 1;
+  p.up4 = a.mode == CONV_UP ? 1 : 0;
+  if (p.up4) { p.taps = 4; p.pad = 1; }
   p.chunk = tc_chunk_kblocks();
   p.PW = PW; p.PH = PH;
-  p.BW = BW; p.BH = BH; p.tiles_x = a.Wo / BW; p.tiles_y = a.Ho / BH;
-  p.m_tiles = a.N * p.tiles_x * p.tiles_y; p.n_tiles = a.Cout / BN; p.kblocks = a.Cin / 64;
+  p.BW = BW; p.BH = BH;
+  p.tiles_x = (p.up4 ? a.W : a.Wo) / BW; p.tiles_y = (p.up4 ? a.H : a.Ho) / BH;
+  p.m_tiles = a.N * p.tiles_x * p.tiles_y * (p.up4 ? 4 : 1); p.n_tiles = a.Cout / BN; p.kblocks = a.Cin / 64;
   p.bias = a.bias; p.residual = a.residual; p.out_act = a.out_act;
   p.sft_dec = a.sft_dec; p.sft_scale = a.sft_scale; p.sft_w = a.sft_w; p.wscale_inv = a.wscale_inv; p.out = a.out;
   p.gn_part = a.gn_part; p.gn_cpg = a.Cout / 32;

@@ -104,6 +104,10 @@ struct ConvW {
   __half* w_lo = nullptr;
   float* bias = nullptr;
   float* wscale = nullptr;       // 2 floats: [0] scratch |w|max, [1] 2^-k of the fp16 split
+  bool is_up = false;            // conv of an Upsample block: also keep the 4-parity 2x2 weights for the tensor-core engine
+  __half* u_hi = nullptr;        // [16][cout][cin]
+  __half* u_lo = nullptr;
+  float* uscale = nullptr;
 };
 struct NormW { std::string name; int c = 0; const float* gamma = nullptr; const float* beta = nullptr; };
 struct ResW { NormW n1, n2; ConvW c1, c2, co; bool has_out = false; };
@@ -184,7 +188,7 @@ static void build_blocks(cfb_net* n, std::vector<Block>& blocks, const std::stri
         mk_conv(n, b.attn.qkv, p + ".qkv", b.cin, 3 * b.cin, 1);   // q,k,v fused along Cout (special-cased in prepare)
         mk_conv(n, b.attn.proj, p + ".proj_out", b.cin, b.cin, 1);
         break;
-      case B_DOWN: case B_UP: mk_conv(n, b.conv, p + ".conv", b.cin, b.cout, 3); break;
+      case B_DOWN: case B_UP: mk_conv(n, b.conv, p + ".conv", b.cin, b.cout, 3); b.conv.is_up = (b.kind == B_UP); break;
       case B_NORM: mk_norm(n, b.norm, p, b.cin); break;
     }
   }
@@ -328,6 +332,7 @@ static int prepare(cfb_net* n, cudaStream_t st) {
   for (ConvW* c : n->convs) {
     const size_t wn = (size_t)c->cout * c->cin * c->k * c->k;
     total += align256(wn * 4) + 2 * align256(wn * 2) + align256((size_t)c->cout * 4) + 256;
+    if (c->is_up) total += 2 * align256((size_t)16 * c->cout * c->cin * 2) + 256;
   }
   for (auto& v : n->vec_params) total += align256((size_t)v.second.second * 4);
   total += align256((size_t)n->cfg.codebook_size * n->cfg.emb_dim * 4);
@@ -356,6 +361,12 @@ static int prepare(cfb_net* n, cudaStream_t st) {
     c->wscale = (float*)take(8);
     CFB_CHECK(relayout_oihw_to_tck(c->src_w, c->w_f32, c->cout, c->cin, c->k, st));
     CFB_CHECK(tc_split_weights(c->src_w, c->w_hi, c->w_lo, c->cout, c->cin, c->k, c->wscale, st));
+    if (c->is_up) {
+      c->u_hi = (__half*)take((size_t)16 * c->cout * c->cin * 2);
+      c->u_lo = (__half*)take((size_t)16 * c->cout * c->cin * 2);
+      c->uscale = (float*)take(8);
+      CFB_CHECK(tc_split_weights_up4(c->src_w, c->u_hi, c->u_lo, c->cout, c->cin, c->uscale, st));
+    }
     if (c->has_bias) CFB_CUDA(cudaMemcpyAsync(c->bias, c->src_b, (size_t)c->cout * 4, cudaMemcpyDeviceToDevice, st));
     else CFB_CUDA(cudaMemsetAsync(c->bias, 0, (size_t)c->cout * 4, st));
   }
@@ -445,6 +456,7 @@ struct Fwd {
     a.in_scale = o.in_scale; a.in_shift = o.in_shift; a.in_act = o.in_act; a.residual = o.residual;
     a.out_act = o.out_act; a.sft_dec = o.sft_dec; a.sft_scale = o.sft_scale; a.sft_w = o.sft_w; a.out = out.p;
     bool use_tc = engine == 2 || (engine == 0 && n->tc_ok && tc_supported(a));
+    if (use_tc && o.mode == CONV_UP) { a.wgt_hi = w.u_hi; a.wgt_lo = w.u_lo; a.wscale_inv = w.uscale + 1; }
     if (use_tc) {
       CFB_REQUIRE(tc_supported(a), "conv: shape not supported by the tcgen05 engine: " + w.name);
       if (o.want_stats && !o.out_ptr && tc_can_emit_stats(a)) {
@@ -1024,7 +1036,8 @@ int64_t cfb_conv2d_workspace_bytes(int32_t n, int32_t h, int32_t w, int32_t cin,
   a.Ho = mode == cfb::CONV_DOWN ? h / 2 : (mode == cfb::CONV_UP ? h * 2 : h);
   a.Wo = mode == cfb::CONV_DOWN ? w / 2 : (mode == cfb::CONV_UP ? w * 2 : w);
   const size_t wn = (size_t)cout * cin * ksize * ksize;
-  return (int64_t)(align256(wn * 4) + 2 * align256(wn * 2) + 256 + cfb::tc_scratch_bytes(a) + 8192);
+  const size_t wsplit = mode == cfb::CONV_UP ? (size_t)16 * cout * cin : wn;
+  return (int64_t)(align256(wn * 4) + 2 * align256(wsplit * 2) + 256 + cfb::tc_scratch_bytes(a) + 8192);
 }
 
 int cfb_conv2d_nhwc(const float* in, const float* weight_oihw, const float* bias, float* out, int32_t n, int32_t h,
@@ -1044,8 +1057,9 @@ int cfb_conv2d_nhwc(const float* in, const float* weight_oihw, const float* bias
   const size_t wn = (size_t)cout * cin * ksize * ksize;
   char* p = (char*)workspace;
   float* wf = (float*)p; p += align256(wn * 4);
-  __half* whi = (__half*)p; p += align256(wn * 2);
-  __half* wlo = (__half*)p; p += align256(wn * 2);
+  const size_t wsplit = mode == cfb::CONV_UP ? (size_t)16 * cout * cin : wn;
+  __half* whi = (__half*)p; p += align256(wsplit * 2);
+  __half* wlo = (__half*)p; p += align256(wsplit * 2);
   float* wsc = (float*)p; p += 256;
   p = (char*)(((uintptr_t)p + 1023) / 1024 * 1024);
   a.wgt_f32 = wf; a.wgt_hi = whi; a.wgt_lo = wlo; a.wscale_inv = wsc + 1;
@@ -1061,7 +1075,8 @@ int cfb_conv2d_nhwc(const float* in, const float* weight_oihw, const float* bias
     int dev = 0, sms = 148;
     CFB_CUDA(cudaGetDevice(&dev));
     CFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    CFB_CHECK(cfb::tc_split_weights(weight_oihw, whi, wlo, cout, cin, ksize, wsc, st));
+    if (mode == cfb::CONV_UP) CFB_CHECK(cfb::tc_split_weights_up4(weight_oihw, whi, wlo, cout, cin, wsc, st));
+    else CFB_CHECK(cfb::tc_split_weights(weight_oihw, whi, wlo, cout, cin, ksize, wsc, st));
     CFB_CHECK(cfb::conv_tc(a, p, sms, st));
   } else {
     CFB_CHECK(cfb::relayout_oihw_to_tck(weight_oihw, wf, cout, cin, ksize, st));

@@ -220,57 +220,74 @@ int conv_f32(const ConvArgs& a, cudaStream_t st) {
 // =====================================================================================================
 // First conv (3 -> Cout, reads the caller's NCHW image) and last conv (Cin -> 3, writes NCHW).
 // =====================================================================================================
+// Thread = 4 horizontally adjacent pixels x COUT/4 channels (4 threads cover a pixel quad): every input value and every
+// weight read feeds 4 pixels; 16-byte coalesced NHWC stores.
 template <int COUT>
 __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ x, const float* __restrict__ wgt,
                                                          const float* __restrict__ bias, float* __restrict__ out,
                                                          int N, int H, int W) {
-  // 4 threads per pixel, COUT/4 channels each; 64 pixels per CTA
   __shared__ __align__(16) float ws[27 * COUT];
   __shared__ float bs[COUT];
   for (int i = threadIdx.x; i < 27 * COUT; i += 256) ws[i] = wgt[i];
   for (int i = threadIdx.x; i < COUT; i += 256) bs[i] = bias ? bias[i] : 0.f;
   __syncthreads();
   constexpr int CPT = COUT / 4;
-  const int64_t pix = (int64_t)blockIdx.x * 64 + (threadIdx.x >> 2);
-  const int cg = threadIdx.x & 3;
   const int64_t HW = (int64_t)H * W;
-  if (pix >= (int64_t)N * HW) return;
-  const int n = (int)(pix / HW);
-  const int rem = (int)(pix - (int64_t)n * HW);
-  const int y = rem / W, xq = rem - y * W;
-  float acc[CPT];
+  const int64_t quad = (int64_t)blockIdx.x * 64 + (threadIdx.x >> 2);      // 64 pixel quads per CTA
+  const int cg = threadIdx.x & 3;
+  const int64_t pix0 = quad * 4;
+  if (pix0 >= (int64_t)N * HW) return;
+  const int n = (int)(pix0 / HW);
+  const int rem = (int)(pix0 - (int64_t)n * HW);
+  const int y = rem / W, x0 = rem - y * W;                                  // W % 4 == 0: the quad shares a row
+  float acc[4][CPT];
 #pragma unroll
-  for (int j = 0; j < CPT; ++j) acc[j] = bs[cg * CPT + j];
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) acc[p][j] = bs[cg * CPT + j];
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
+    const int iy = y + r - 1;
+    const bool rowok = iy >= 0 && iy < H;
 #pragma unroll
-    for (int s = 0; s < 3; ++s) {
-      const int iy = y + r - 1, ix = xq + s - 1;
-      const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+    for (int c = 0; c < 3; ++c) {
+      float v[6];
+      const float* rp = x + ((int64_t)n * 3 + c) * HW + (int64_t)iy * W;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float v = ok ? __ldg(x + ((int64_t)n * 3 + c) * HW + (int64_t)iy * W + ix) : 0.f;
+      for (int q = 0; q < 6; ++q) {
+        const int ix = x0 + q - 1;
+        v[q] = (rowok && ix >= 0 && ix < W) ? __ldg(rp + ix) : 0.f;
+      }
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
         const float* wr = ws + ((r * 3 + s) * 3 + c) * COUT + cg * CPT;
 #pragma unroll
         for (int j = 0; j < CPT; j += 4) {
           const float4 w4 = *reinterpret_cast<const float4*>(wr + j);
-          acc[j] = fmaf(v, w4.x, acc[j]); acc[j + 1] = fmaf(v, w4.y, acc[j + 1]);
-          acc[j + 2] = fmaf(v, w4.z, acc[j + 2]); acc[j + 3] = fmaf(v, w4.w, acc[j + 3]);
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            acc[p][j] = fmaf(v[p + s], w4.x, acc[p][j]); acc[p][j + 1] = fmaf(v[p + s], w4.y, acc[p][j + 1]);
+            acc[p][j + 2] = fmaf(v[p + s], w4.z, acc[p][j + 2]); acc[p][j + 3] = fmaf(v[p + s], w4.w, acc[p][j + 3]);
+          }
         }
       }
     }
   }
-  float* o = out + pix * COUT + cg * CPT;
 #pragma unroll
-  for (int j = 0; j < CPT; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+  for (int p = 0; p < 4; ++p) {
+    float* o = out + (pix0 + p) * COUT + cg * CPT;
+#pragma unroll
+    for (int j = 0; j < CPT; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(acc[p][j], acc[p][j + 1], acc[p][j + 2], acc[p][j + 3]);
+  }
 }
 
 int conv_first(const float* x, const float* wgt, const float* bias, float* out, int N, int H, int W, int Cout,
                cudaStream_t st) {
   CFB_REQUIRE(Cout == 64, "conv_first: only nf=64 is built");
-  const int64_t pix = (int64_t)N * H * W;
-  if (pix == 0) return 0;
-  conv_first_kernel<64><<<(unsigned)((pix + 63) / 64), 256, 0, st>>>(x, wgt, bias, out, N, H, W);
+  CFB_REQUIRE(W % 4 == 0, "conv_first: W must be a multiple of 4");
+  const int64_t quads = (int64_t)N * H * W / 4;
+  if (quads == 0) return 0;
+  conv_first_kernel<64><<<(unsigned)((quads + 63) / 64), 256, 0, st>>>(x, wgt, bias, out, N, H, W);
   CFB_LAUNCH_CHECK();
   return 0;
 }
