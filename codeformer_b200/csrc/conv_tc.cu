@@ -575,6 +575,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     int slot = 0;
     uint32_t slot_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      const int mtl = p.up4 ? (mt >> 2) : mt;
+      const int per_img = p.tiles_x * p.tiles_y;
+      const int n = mtl / per_img;
+      const int rem = mtl - n * per_img;
+      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+      const int h = row / p.BW, w = row - h * p.BW;
+      int oy = ty * p.BH + h, ox = tx * p.BW + w;
+      if (p.up4) { oy = 2 * oy + ((mt & 3) >> 1); ox = 2 * ox + (mt & 1); }   // this tile writes one output parity
+      const int64_t pix = ((int64_t)n * p.Ho + oy) * p.Wo + ox;
+      const int col0 = nt * BN + cbase;
+      const int64_t off0 = pix * p.Cout + col0;
+      // pull this thread's residual / SFT row slices towards L2 now: they are consumed only after the whole K loop
+      if (p.residual) {
+#pragma unroll
+        for (int j = 0; j < HC; j += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + off0 + j));
+      }
+      if (p.sft_dec) {
+#pragma unroll
+        for (int j = 0; j < HC; j += 32) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.sft_dec + off0 + j));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.sft_scale + off0 + j));
+        }
+      }
       float acc[HC];
 #pragma unroll
       for (int j = 0; j < HC; ++j) acc[j] = 0.f;
@@ -597,18 +621,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (++slot == TC_SLOTS) { slot = 0; slot_phase ^= 1; }
       }
       // ---- finalize this tile: scale, bias, residual, activation, SFT, store (fp32 NHWC), GroupNorm partials
-      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
-      const int mtl = p.up4 ? (mt >> 2) : mt;
-      const int per_img = p.tiles_x * p.tiles_y;
-      const int n = mtl / per_img;
-      const int rem = mtl - n * per_img;
-      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-      const int h = row / p.BW, w = row - h * p.BW;
-      int oy = ty * p.BH + h, ox = tx * p.BW + w;
-      if (p.up4) { oy = 2 * oy + ((mt & 3) >> 1); ox = 2 * ox + (mt & 1); }   // this tile writes one output parity
-      const int64_t pix = ((int64_t)n * p.Ho + oy) * p.Wo + ox;
-      const int col0 = nt * BN + cbase;
-      const int64_t off0 = pix * p.Cout + col0;
       constexpr int G = (CPG > 0) ? HC / CPG : 1;
       float gs[G], gq[G];
 #pragma unroll
