@@ -330,15 +330,16 @@ struct TcCfg {
   static constexpr int SLOT_COLS = 2 * BN;
   static constexpr int SLOTS = 512 / SLOT_COLS;            // 2 (BN=128) or 4 (BN=64)
   static constexpr int TMEM_COLS = 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STG_BYTES = 8 * 4096;               // per-epilogue-warp 32x32-float transpose patches
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + STG_BYTES;
   // halo engine: 16x8-pixel tiles; the (16+2)x(8+2) input patch of one 64-channel block is fetched ONCE (hi and lo
   // planes) and all 9 taps read it through row-shifted UMMA descriptors; weights stream through their own ring.
   static constexpr int H_A_PLANE = 23 * 1024;              // >= 18*10*128 B, 1024-aligned
   static constexpr int H_A_SLOT = 2 * H_A_PLANE;
   static constexpr int H_A_SLOTS = 2;
   static constexpr int H_B_SLOT = 2 * B_BYTES;
-  static constexpr int H_B_SLOTS = (BN == 64) ? 8 : 4;
-  static constexpr int H_SMEM_BYTES = H_A_SLOTS * H_A_SLOT + H_B_SLOTS * H_B_SLOT + 1024 + 256;
+  static constexpr int H_B_SLOTS = (BN == 64) ? 6 : 3;
+  static constexpr int H_SMEM_BYTES = H_A_SLOTS * H_A_SLOT + H_B_SLOTS * H_B_SLOT + 1024 + 256 + STG_BYTES;
 };
 
 // Butterfly reduction of G per-lane group sums over the 32 lanes of a warp: after log2(G) exchange steps every lane
@@ -388,6 +389,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint64_t* afull = bars + 2 * NRING + 2 * TC_SLOTS;
   uint64_t* aempty = afull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 2);
+  uint8_t* stage_buf = reinterpret_cast<uint8_t*>(bars) + 256;      // epilogue transpose patches (16-byte aligned)
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
@@ -620,60 +622,84 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (lane == 0) mbar_arrive(smem_u32(cempty + slot));
         if (++slot == TC_SLOTS) { slot = 0; slot_phase ^= 1; }
       }
-      // ---- finalize this tile: scale, bias, residual, activation, SFT, store (fp32 NHWC), GroupNorm partials
-      constexpr int G = (CPG > 0) ? HC / CPG : 1;
-      float gs[G], gq[G];
+      // ---- finalize this tile: scale, bias, residual, activation, SFT, store (fp32 NHWC), GroupNorm partials.
+      // A TMEM lane owns a pixel ROW, so storing straight from registers would touch 32 different 128-byte lines per
+      // instruction.  Each warp instead transposes 32x32-float blocks through a private 4 KB XOR-swizzled smem patch:
+      // afterwards lane l holds the 16-byte chunk (l & 7) of row (l >> 3) + 4*it, i.e. 8 lanes cover one full 128-byte
+      // line and every global access (residual / SFT loads, the store) is a fully used line.
+      float4* stg = reinterpret_cast<float4*>(stage_buf) + (warp - 2) * 256;     // 32 rows x 8 chunks
+      const int cch = lane & 7, rsub = lane >> 3;
 #pragma unroll
-      for (int g = 0; g < G; ++g) { gs[g] = 0.f; gq[g] = 0.f; }
-      float4 res[HC / 4];                    // residual row slice: all loads in flight before the first use
+      for (int q = 0; q < HC; q += 32) {
 #pragma unroll
-      for (int j = 0; j < HC; j += 4)
-        res[j / 4] = p.residual ? __ldg(reinterpret_cast<const float4*>(p.residual + off0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < 8; ++j)
+          stg[lane * 8 + (j ^ (lane & 7))] =
+              make_float4(acc[q + 4 * j] * wsi, acc[q + 4 * j + 1] * wsi, acc[q + 4 * j + 2] * wsi, acc[q + 4 * j + 3] * wsi);
+        __syncwarp();
+        const int colq = col0 + q + cch * 4;                  // first of this lane's 4 channels
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + colq));
+        float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
 #pragma unroll
-      for (int j = 0; j < HC; j += 4) {
-        float4 v = make_float4(acc[j] * wsi, acc[j + 1] * wsi, acc[j + 2] * wsi, acc[j + 3] * wsi);
-        if (p.bias) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-          v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + rsub;                        // row within this warp's 32-row quadrant
+          float4 v = stg[r * 8 + (cch ^ (r & 7))];
+          const int trow = lg * 32 + r;
+          const int hh = trow / p.BW, ww = trow - hh * p.BW;
+          int oy2 = ty * p.BH + hh, ox2 = tx * p.BW + ww;
+          if (p.up4) { oy2 = 2 * oy2 + ((mt & 3) >> 1); ox2 = 2 * ox2 + (mt & 1); }
+          const int64_t off = (((int64_t)n * p.Ho + oy2) * p.Wo + ox2) * p.Cout + colq;
+          v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+          if (p.residual) {
+            const float4 rr = __ldg(reinterpret_cast<const float4*>(p.residual + off));
+            v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+          }
+          if (p.out_act == OUT_LRELU) {
+            v.x = v.x > 0.f ? v.x : 0.2f * v.x; v.y = v.y > 0.f ? v.y : 0.2f * v.y;
+            v.z = v.z > 0.f ? v.z : 0.2f * v.z; v.w = v.w > 0.f ? v.w : 0.2f * v.w;
+          } else if (p.out_act == OUT_GELU) {
+            v.x = 0.5f * v.x * (1.f + erff(v.x * 0.70710678118654752440f));
+            v.y = 0.5f * v.y * (1.f + erff(v.y * 0.70710678118654752440f));
+            v.z = 0.5f * v.z * (1.f + erff(v.z * 0.70710678118654752440f));
+            v.w = 0.5f * v.w * (1.f + erff(v.w * 0.70710678118654752440f));
+          }
+          if (p.sft_dec) {
+            const float4 d = __ldg(reinterpret_cast<const float4*>(p.sft_dec + off));
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.sft_scale + off));
+            v.x = d.x + p.sft_w * (d.x * sc.x + v.x); v.y = d.y + p.sft_w * (d.y * sc.y + v.y);
+            v.z = d.z + p.sft_w * (d.z * sc.z + v.z); v.w = d.w + p.sft_w * (d.w * sc.w + v.w);
+          }
+          *reinterpret_cast<float4*>(p.out + off) = v;
+          if constexpr (CPG == 2) {
+            s0 += v.x + v.y; q0 += fmaf(v.x, v.x, v.y * v.y);
+            s1 += v.z + v.w; q1 += fmaf(v.z, v.z, v.w * v.w);
+          } else if constexpr (CPG >= 4) {
+            s0 += (v.x + v.y) + (v.z + v.w);
+            q0 += fmaf(v.x, v.x, v.y * v.y) + fmaf(v.z, v.z, v.w * v.w);
+          }
         }
-        const int64_t off = off0 + j;
-        {
-          const float4 q = res[j / 4];
-          v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+        if constexpr (CPG > 0) {
+          // GroupNorm partial sums of the values just stored: reduce over the 4 row-lanes (xor 8, 16) and, for groups
+          // wider than one chunk, over the chunk-lanes of the group; fixed order => deterministic
+          s0 += __shfl_xor_sync(0xffffffffu, s0, 8); q0 += __shfl_xor_sync(0xffffffffu, q0, 8);
+          s0 += __shfl_xor_sync(0xffffffffu, s0, 16); q0 += __shfl_xor_sync(0xffffffffu, q0, 16);
+          if constexpr (CPG == 2) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 8); q1 += __shfl_xor_sync(0xffffffffu, q1, 8);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 16); q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
+          }
+          if constexpr (CPG >= 8) { s0 += __shfl_xor_sync(0xffffffffu, s0, 1); q0 += __shfl_xor_sync(0xffffffffu, q0, 1); }
+          if constexpr (CPG >= 16) { s0 += __shfl_xor_sync(0xffffffffu, s0, 2); q0 += __shfl_xor_sync(0xffffffffu, q0, 2); }
+          constexpr int CL = (CPG >= 4) ? CPG / 4 : 1;         // chunk-lanes per group
+          if (rsub == 0 && (cch & (CL - 1)) == 0) {
+            float* gp = p.gn_part + ((int64_t)mt * 4 + lg) * 64;
+            if constexpr (CPG == 2) {
+              *reinterpret_cast<float4*>(gp + (colq / 2) * 2) = make_float4(s0, q0, s1, q1);
+            } else {
+              *reinterpret_cast<float2*>(gp + (colq / CPG) * 2) = make_float2(s0, q0);
+            }
+          }
         }
-        if (p.out_act == OUT_LRELU) {
-          v.x = v.x > 0.f ? v.x : 0.2f * v.x; v.y = v.y > 0.f ? v.y : 0.2f * v.y;
-          v.z = v.z > 0.f ? v.z : 0.2f * v.z; v.w = v.w > 0.f ? v.w : 0.2f * v.w;
-        } else if (p.out_act == OUT_GELU) {
-          v.x = 0.5f * v.x * (1.f + erff(v.x * 0.70710678118654752440f));
-          v.y = 0.5f * v.y * (1.f + erff(v.y * 0.70710678118654752440f));
-          v.z = 0.5f * v.z * (1.f + erff(v.z * 0.70710678118654752440f));
-          v.w = 0.5f * v.w * (1.f + erff(v.w * 0.70710678118654752440f));
-        }
-        if (p.sft_dec) {
-          const float4 d = __ldg(reinterpret_cast<const float4*>(p.sft_dec + off));
-          const float4 s = __ldg(reinterpret_cast<const float4*>(p.sft_scale + off));
-          v.x = d.x + p.sft_w * (d.x * s.x + v.x); v.y = d.y + p.sft_w * (d.y * s.y + v.y);
-          v.z = d.z + p.sft_w * (d.z * s.z + v.z); v.w = d.w + p.sft_w * (d.w * s.w + v.w);
-        }
-        *reinterpret_cast<float4*>(p.out + off) = v;
-        if constexpr (CPG == 2) {
-          gs[j / 2] += v.x + v.y; gq[j / 2] += fmaf(v.x, v.x, v.y * v.y);
-          gs[j / 2 + 1] += v.z + v.w; gq[j / 2 + 1] += fmaf(v.z, v.z, v.w * v.w);
-        } else if constexpr (CPG >= 4) {
-          gs[j / CPG] += (v.x + v.y) + (v.z + v.w);
-          gq[j / CPG] += fmaf(v.x, v.x, v.y * v.y) + fmaf(v.z, v.z, v.w * v.w);
-        }
-      }
-      if constexpr (CPG > 0) {
-        // sum / sum of squares per group over this warp's 32 pixels -> [m_tile*4 + quadrant][32 groups][2]
-        warp_group_reduce<G>(gs, lane);
-        warp_group_reduce<G>(gq, lane);
-        constexpr int LPG = 32 / G;                       // lanes per group after the butterfly
-        if ((lane & (LPG - 1)) == 0) {
-          const int g = col0 / CPG + lane / LPG;
-          *reinterpret_cast<float2*>(p.gn_part + (((int64_t)mt * 4 + lg) * 32 + g) * 2) = make_float2(gs[0], gq[0]);
-        }
+        __syncwarp();
       }
     }
   }
