@@ -639,21 +639,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int colq = col0 + q + cch * 4;                  // first of this lane's 4 channels
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + colq));
+        // global offsets of the 8 (row, chunk) items of this lane, then ALL residual loads in flight at once
+        int64_t offs[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int trow = lg * 32 + it * 4 + rsub;
+          const int hh = trow / p.BW, ww = trow - hh * p.BW;
+          int oy2 = ty * p.BH + hh, ox2 = tx * p.BW + ww;
+          if (p.up4) { oy2 = 2 * oy2 + ((mt & 3) >> 1); ox2 = 2 * ox2 + (mt & 1); }
+          offs[it] = (((int64_t)n * p.Ho + oy2) * p.Wo + ox2) * p.Cout + colq;
+        }
+        float4 rres[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it)
+          rres[it] = p.residual ? __ldg(reinterpret_cast<const float4*>(p.residual + offs[it])) : make_float4(0.f, 0.f, 0.f, 0.f);
         float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int r = it * 4 + rsub;                        // row within this warp's 32-row quadrant
           float4 v = stg[r * 8 + (cch ^ (r & 7))];
-          const int trow = lg * 32 + r;
-          const int hh = trow / p.BW, ww = trow - hh * p.BW;
-          int oy2 = ty * p.BH + hh, ox2 = tx * p.BW + ww;
-          if (p.up4) { oy2 = 2 * oy2 + ((mt & 3) >> 1); ox2 = 2 * ox2 + (mt & 1); }
-          const int64_t off = (((int64_t)n * p.Ho + oy2) * p.Wo + ox2) * p.Cout + colq;
-          v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-          if (p.residual) {
-            const float4 rr = __ldg(reinterpret_cast<const float4*>(p.residual + off));
-            v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
-          }
+          const int64_t off = offs[it];
+          v.x += bv.x + rres[it].x; v.y += bv.y + rres[it].y; v.z += bv.z + rres[it].z; v.w += bv.w + rres[it].w;
           if (p.out_act == OUT_LRELU) {
             v.x = v.x > 0.f ? v.x : 0.2f * v.x; v.y = v.y > 0.f ? v.y : 0.2f * v.y;
             v.z = v.z > 0.f ? v.z : 0.2f * v.z; v.w = v.w > 0.f ? v.w : 0.2f * v.w;

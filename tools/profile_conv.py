@@ -17,6 +17,7 @@ ap.add_argument('--h', type=int, default=256)
 ap.add_argument('--k', type=int, default=3)
 ap.add_argument('--mode', type=int, default=0)
 ap.add_argument('--reps', type=int, default=4)
+ap.add_argument('--residual', type=int, default=0)
 a = ap.parse_args()
 lib = _lib.load()
 N, H, C1, C2 = a.n, a.h, a.cin, a.cout
@@ -27,9 +28,10 @@ Ho = H // 2 if a.mode == 1 else (H * 2 if a.mode == 2 else H)
 out = torch.empty(N, Ho, Ho, C2, device='cuda')
 wsb = lib.cfb_conv2d_workspace_bytes(N, H, H, C1, C2, a.k, a.mode)
 ws = torch.empty(int(wsb), dtype=torch.uint8, device='cuda')
+res = torch.randn(N, Ho, Ho, C2, device='cuda') if a.residual else None
 st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 for _ in range(a.reps):
     _lib.check(lib.cfb_conv2d_nhwc(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(out), N, H, H, C1, C2, a.k, a.mode,
-                                   None, None, 0, None, 0, 2, _lib.ptr(ws), wsb, st))
+                                   None, None, 0, _lib.ptr(res), 0, 2, _lib.ptr(ws), wsb, st))
 torch.cuda.synchronize()
 print('done')
