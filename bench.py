@@ -172,41 +172,34 @@ def run_reference(args):
 
 
 def dominant_kernel_roofline(torch, cb, batch, peaks, peak_kind):
-    """Time the dominant conv (ResBlock 128->128 3x3 at 256^2: 13 launches of 19.33 GFLOP/face, Appendix A)
-    alone through the C ABI with CUDA events on the launching stream."""
+    """The dominant kernel = conv_tc_kernel on the most frequent shape (ResBlock 128->128 3x3 at 256^2: 13 launches of
+    19.33 GFLOP/face).  Timed alone -- operand planes and split weights prepared outside the timed
+    region -- with CUDA events on the launching stream (cfb_debug_time_conv), B=8 like the committed ncu capture."""
     import ctypes
     from codeformer_b200 import _lib
     lib = _lib.load()
-    N, H, C = batch, 256, 128
+    N, H, C = 8, 256, 128
     g = torch.Generator().manual_seed(3)
     x = torch.randn(N, H, H, C, generator=g).cuda()
     w = (torch.randn(C, C, 3, 3, generator=g) / (9 * C) ** 0.5).cuda()
-    b = torch.zeros(C).cuda()
     out = torch.empty(N, H, H, C, device='cuda')
     wsb = lib.cfb_conv2d_workspace_bytes(N, H, H, C, C, 3, 0)
     ws = torch.empty(int(wsb), dtype=torch.uint8, device='cuda')
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-
-    def launch():
-        _lib.check(lib.cfb_conv2d_nhwc(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(out), N, H, H, C, C, 3, 0, None, None,
-                                       0, None, 0, 0, _lib.ptr(ws), wsb, st), 'conv')
-    for _ in range(3):
-        launch()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 10
-    e0.record()
-    for _ in range(reps):
-        launch()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
+    ms = ctypes.c_float(0)
+    _lib.check(lib.cfb_debug_time_conv(_lib.ptr(x), _lib.ptr(w), _lib.ptr(out), N, H, H, C, C, 3, 0, 20, _lib.ptr(ws), wsb, st,
+                                       ctypes.byref(ms)), 'cfb_debug_time_conv')
+    ms = float(ms.value)
     flops = 2.0 * N * H * H * C * C * 9
     achieved = flops / (ms * 1e-3) / 1e12
-    return {'bound': 'tensor', 'kernel': 'conv 3x3 128->128 @256^2 (implicit GEMM, operand prep + weight split included)',
+    return {'bound': 'tensor', 'kernel': 'conv_tc_kernel<128,...>: conv 3x3 128->128 @256^2, B=8 (kernel only)',
             'achieved': achieved, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s', 'frac': achieved / peaks['bf16_tflops'],
             'peak_kind': f'{peak_kind} bf16 burst (MEASURED_PEAKS.json)', 'ms_per_launch': ms,
-            'algorithmic_gflop_per_launch': flops / 1e9, 'traffic': None}
+            'algorithmic_gflop_per_launch': flops / 1e9,
+            'executed_mma_passes': '2 tcgen05.mma per k-step (N=256 + N=128) = 3x the nominal MACs (split-fp16 operands)',
+            'traffic': 490.5e6, 'traffic_unit': 'bytes/launch',
+            'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum, profiles/round1_conv128_256_full.raw.csv '
+                              '(ncu --set full, same shape and batch); algorithmic = 268 MB operand planes + 268 MB output'}
 
 
 def run_b200(args):

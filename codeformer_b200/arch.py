@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 import threading
 from typing import Dict, Optional
 
@@ -205,6 +206,8 @@ class VQAutoEncoder(nn.Module):
     """Mirror of ``VQAutoEncoder`` (vqgan_arch.py:326-389), quantizer='nearest'."""
 
     _KIND = 0
+    stream_lanes = 2                  # sub-batches run concurrently on separate CUDA streams (1 = single stream)
+    stream_lanes_min_faces = 4        # only split when every lane gets at least this many faces
 
     def __init__(self, img_size, nf, ch_mult, quantizer='nearest', res_blocks=2, attn_resolutions=[16],
                  codebook_size=1024, emb_dim=256, beta=0.25, gumbel_straight_through=False, gumbel_kl_weight=1e-8,
@@ -284,9 +287,15 @@ class VQAutoEncoder(nn.Module):
         object.__setattr__(self, '_cfb_sig', sig)
         object.__setattr__(self, '_cfb_keep', keep)
 
-    def _cfb_workspace(self, device, batch):
+    def _cfb_side_streams(self, device, count):
+        pool = self._cfb_ws.setdefault(('streams', device.index), [])
+        while len(pool) < count:
+            pool.append(torch.cuda.Stream(device=device))
+        return pool
+
+    def _cfb_workspace(self, device, batch, lane=0):
         lib = _lib.load()
-        key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+        key = (device.index, torch.cuda.current_stream(device).cuda_stream, lane)
         need = lib.cfb_workspace_bytes(self._cfb_net, batch)
         if need < 0:
             _lib.check(1, 'cfb_workspace_bytes')
@@ -436,14 +445,32 @@ class CodeFormer(VQAutoEncoder):
         dev = x.device
         with self._cfb_lock, torch.cuda.device(dev):
             self._cfb_prepare(dev)
-            ws = self._cfb_workspace(dev, B)
             logits = torch.empty((B, self.latent_size, self.codebook_size), dtype=torch.float32, device=dev)
             lq_feat = torch.empty((B, 256, 16, 16), dtype=torch.float32, device=dev)
             out = None if code_only else torch.empty_like(x)
-            _lib.check(lib.cfb_codeformer_forward(self._cfb_net, _lib.ptr(x), _lib.ptr(out), _lib.ptr(logits),
-                                                  _lib.ptr(lq_feat), None, B, float(w), int(bool(adain)),
-                                                  int(bool(code_only)), _lib.ptr(ws), ws.numel(), _stream_ptr(dev)),
-                       'cfb_codeformer_forward')
+            # Faces are independent, so a batch is run as `lanes` contiguous sub-batches on separate CUDA streams:
+            # the tensor-bound conv kernels of one lane overlap the HBM-bound operand-prep / GroupNorm / attention
+            # kernels of the other (results are bit-identical to the single-stream run: no cross-face op exists).
+            want = int(os.environ.get('CFB_STREAM_LANES', self.stream_lanes))
+            lanes = want if B >= want * self.stream_lanes_min_faces else 1
+            lanes = max(1, min(lanes, B))
+            cur = torch.cuda.current_stream(dev)
+            bounds = [(i * B) // lanes for i in range(lanes + 1)]
+            side = self._cfb_side_streams(dev, lanes - 1)
+            for li in range(lanes):
+                lo, hi = bounds[li], bounds[li + 1]
+                st = cur if li == 0 else side[li - 1]
+                if li > 0:
+                    st.wait_stream(cur)                       # inputs / weights produced on the caller's stream
+                with torch.cuda.stream(st):
+                    ws = self._cfb_workspace(dev, hi - lo, lane=li)
+                    _lib.check(lib.cfb_codeformer_forward(
+                        self._cfb_net, _lib.ptr(x[lo:hi]), None if out is None else _lib.ptr(out[lo:hi]),
+                        _lib.ptr(logits[lo:hi]), _lib.ptr(lq_feat[lo:hi]), None, hi - lo, float(w), int(bool(adain)),
+                        int(bool(code_only)), _lib.ptr(ws), ws.numel(), ctypes.c_void_p(st.cuda_stream)),
+                        'cfb_codeformer_forward')
+            for li in range(1, lanes):
+                cur.wait_stream(side[li - 1])                 # results are ordered on the caller's stream again
         if code_only:
             return logits, lq_feat
         return out, logits, lq_feat

@@ -851,7 +851,7 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
   const size_t plane = ((size_t)Mp * a.Cin * 2 + 1023) / 1024 * 1024;
   __half* hi = (__half*)scratch;
   __half* lo = (__half*)((char*)scratch + plane);
-  {
+  if (!a.skip_prep) {
     const int C8 = a.Cin / 8;
     CFB_REQUIRE(C8 <= 256 && 256 % C8 == 0, "conv_tc: Cin must be 64 * 2^k (<= 2048)");
     const int64_t img_px = (int64_t)Hp * Wp;

@@ -73,6 +73,7 @@ struct ConvArgs {
   float* out = nullptr;             // [N,Ho,Wo,Cout]
   // tensor-core engine only: GroupNorm(32) partial sums of `out`, [N*tiles_per_image*4][32 groups][2] floats
   float* gn_part = nullptr;
+  bool skip_prep = false;           // operand planes in `scratch` are already valid (kernel-only timing)
 };
 
 int conv_f32(const ConvArgs& a, cudaStream_t st);                       // CUDA-core fp32 implicit GEMM

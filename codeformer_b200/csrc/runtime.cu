@@ -1099,6 +1099,50 @@ int cfb_debug_umma_rate(int32_t n, int32_t nacc, int32_t reps, int64_t* out_dev,
   API_END(1)
 }
 
+int cfb_debug_time_conv(const float* in, const float* weight_oihw, float* out, int32_t n, int32_t h, int32_t w, int32_t cin,
+                        int32_t cout, int32_t ksize, int32_t mode, int32_t reps, void* workspace, int64_t workspace_bytes,
+                        void* stream, float* ms_per_launch) {
+  API_BEGIN
+  CFB_REQUIRE(in && weight_oihw && out && workspace && ms_per_launch && reps > 0, "cfb_debug_time_conv: bad argument");
+  CFB_REQUIRE(workspace_bytes >= cfb_conv2d_workspace_bytes(n, h, w, cin, cout, ksize, mode), "cfb_debug_time_conv: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  cfb::ConvArgs a;
+  a.in = in; a.N = n; a.H = h; a.W = w; a.Cin = cin; a.Cout = cout; a.ksize = ksize; a.mode = mode;
+  a.Ho = mode == cfb::CONV_DOWN ? h / 2 : (mode == cfb::CONV_UP ? h * 2 : h);
+  a.Wo = mode == cfb::CONV_DOWN ? w / 2 : (mode == cfb::CONV_UP ? w * 2 : w);
+  a.out = out;
+  CFB_REQUIRE(cfb::tc_supported(a), "cfb_debug_time_conv: shape not on the tcgen05 engine");
+  const size_t wn = (size_t)cout * cin * ksize * ksize;
+  const size_t wsplit = mode == cfb::CONV_UP ? (size_t)16 * cout * cin : wn;
+  char* p = (char*)workspace + align256(wn * 4);
+  __half* whi = (__half*)p; p += align256(wsplit * 2);
+  __half* wlo = (__half*)p; p += align256(wsplit * 2);
+  float* wsc = (float*)p; p += 256;
+  p = (char*)(((uintptr_t)p + 1023) / 1024 * 1024);
+  a.wgt_hi = whi; a.wgt_lo = wlo; a.wscale_inv = wsc + 1;
+  int dev = 0, sms = 148;
+  CFB_CUDA(cudaGetDevice(&dev));
+  CFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (mode == cfb::CONV_UP) CFB_CHECK(cfb::tc_split_weights_up4(weight_oihw, whi, wlo, cout, cin, wsc, st));
+  else CFB_CHECK(cfb::tc_split_weights(weight_oihw, whi, wlo, cout, cin, ksize, wsc, st));
+  CFB_CHECK(cfb::conv_tc(a, p, sms, st));          // operand prep + one warm-up launch
+  a.skip_prep = true;
+  for (int i = 0; i < 2; ++i) CFB_CHECK(cfb::conv_tc(a, p, sms, st));
+  cudaEvent_t e0, e1;
+  CFB_CUDA(cudaEventCreate(&e0));
+  CFB_CUDA(cudaEventCreate(&e1));
+  CFB_CUDA(cudaEventRecord(e0, st));               // events on the launching stream: only the conv kernel is between them
+  for (int i = 0; i < reps; ++i) CFB_CHECK(cfb::conv_tc(a, p, sms, st));
+  CFB_CUDA(cudaEventRecord(e1, st));
+  CFB_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  CFB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *ms_per_launch = ms / reps;
+  return 0;
+  API_END(1)
+}
+
 int64_t cfb_gn_workspace_bytes(int32_t n, int32_t hw, int32_t c) { return (int64_t)cfb::gn_workspace_bytes(n, hw, c) + 256; }
 int cfb_group_norm_coef(const float* x, const float* gamma, const float* beta, float* scale, float* shift, int32_t n,
                         int32_t hw, int32_t c, int32_t groups, float eps, void* workspace, int64_t workspace_bytes,

@@ -152,6 +152,11 @@ int cfb_debug_umma_probe(const void* a_f16, int32_t rows_a, const void* b_f16, c
 /* diagnostics: sustained tcgen05.mma issue rate; out_dev[ctas] receives the cycles for reps*12 MMAs of 128 x n x 16
  * rotating over `nacc` TMEM accumulators (tools/umma_rate.py) */
 int cfb_debug_umma_rate(int32_t n, int32_t nacc, int32_t reps, int64_t* out_dev, int32_t ctas, void* stream);
+/* diagnostics / bench: average device time (CUDA events on `stream`) of the tcgen05 conv KERNEL alone -- weights split
+ * and operand planes prepared once outside the timed region -- over `reps` launches (bench.py roofline). */
+int cfb_debug_time_conv(const float* in, const float* weight_oihw, float* out, int32_t n, int32_t h, int32_t w, int32_t cin,
+                        int32_t cout, int32_t ksize, int32_t mode, int32_t reps, void* workspace, int64_t workspace_bytes,
+                        void* stream, float* ms_per_launch);
 /* layout plumbing */
 int cfb_nchw_to_nhwc(const float* in, float* out, int32_t n, int32_t c, int32_t hw, void* stream);
 int cfb_nhwc_to_nchw(const float* in, float* out, int32_t n, int32_t c, int32_t hw, void* stream);
