@@ -206,7 +206,8 @@ class VQAutoEncoder(nn.Module):
     """Mirror of ``VQAutoEncoder`` (vqgan_arch.py:326-389), quantizer='nearest'."""
 
     _KIND = 0
-    stream_lanes = 2                  # sub-batches run concurrently on separate CUDA streams (1 = single stream)
+    stream_lanes = 1                  # >1: sub-batches run on separate CUDA streams.  Measured on B200 (B=32): no gain --
+                                      # the persistent conv CTAs own every SM and the chip is power-capped -- so off by default
     stream_lanes_min_faces = 4        # only split when every lane gets at least this many faces
 
     def __init__(self, img_size, nf, ch_mult, quantizer='nearest', res_blocks=2, attn_resolutions=[16],
