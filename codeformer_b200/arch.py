@@ -247,6 +247,7 @@ class VQAutoEncoder(nn.Module):
         object.__setattr__(self, '_cfb_sig', None)
         object.__setattr__(self, '_cfb_keep', None)
         object.__setattr__(self, '_cfb_ws', {})
+        object.__setattr__(self, '_cfb_graphs', {})
 
     def _cfb_config(self) -> '_lib.CfbConfig':
         c = _lib.CfbConfig()
@@ -286,6 +287,7 @@ class VQAutoEncoder(nn.Module):
             _lib.check(lib.cfb_net_set_param(self._cfb_net, k.encode(), _lib.ptr(t), t.numel()), 'cfb_net_set_param')
         _lib.check(lib.cfb_net_prepare(self._cfb_net, _stream_ptr(device)), 'cfb_net_prepare')
         object.__setattr__(self, '_cfb_sig', sig)
+        self._cfb_graphs.clear()                       # captured launch sequences bake in the old weight copies
         object.__setattr__(self, '_cfb_keep', keep)
 
     def _cfb_side_streams(self, device, count):
@@ -325,6 +327,7 @@ class VQAutoEncoder(nn.Module):
         (fp32 CUDA-core implicit GEMM) or 'tc' (tcgen05 only).  Both are CUDA kernels of libcfb200."""
         code = {'auto': 0, 'f32': 1, 'tc': 2}[engine]
         object.__setattr__(self, '_cfb_engine', code)
+        self._cfb_graphs.clear()
         if self._cfb_net is not None:
             _lib.check(_lib.load().cfb_net_set_engine(self._cfb_net, code), 'cfb_net_set_engine')
 
@@ -332,6 +335,10 @@ class VQAutoEncoder(nn.Module):
         """Parity hook (cfb_net_capture): copy the NHWC activation after ``stage`` into ``dst`` on the next forwards."""
         if self._cfb_net is None:
             raise RuntimeError('capture: run one forward (or load weights on the device) first')
+        hooks = getattr(self, '_cfb_hooks', set())
+        (hooks.add if dst is not None else hooks.discard)(stage)
+        object.__setattr__(self, '_cfb_hooks', hooks)
+        self._cfb_graphs.clear()                       # hooks add copies to the launch sequence
         _lib.check(_lib.load().cfb_net_capture(self._cfb_net, stage.encode(), _lib.ptr(dst),
                                                0 if dst is None else dst.numel()), 'cfb_net_capture')
 
@@ -446,6 +453,11 @@ class CodeFormer(VQAutoEncoder):
         dev = x.device
         with self._cfb_lock, torch.cuda.device(dev):
             self._cfb_prepare(dev)
+            if 0 < B <= self.cuda_graph_max_batch and os.environ.get('CFB_CUDA_GRAPH', '1') != '0' \
+                    and not getattr(self, '_cfb_hooks', None) and not torch.cuda.is_current_stream_capturing():
+                res = self._cfb_forward_graphed(x, float(w), bool(adain), bool(code_only))
+                if res is not None:
+                    return res
             logits = torch.empty((B, self.latent_size, self.codebook_size), dtype=torch.float32, device=dev)
             lq_feat = torch.empty((B, 256, 16, 16), dtype=torch.float32, device=dev)
             out = None if code_only else torch.empty_like(x)
@@ -475,6 +487,51 @@ class CodeFormer(VQAutoEncoder):
         if code_only:
             return logits, lq_feat
         return out, logits, lq_feat
+
+    # The reference's callers feed ONE face per call (inference_codeformer.py:197-206); at that size the forward is ~440
+    # small launches and launch latency dominates.  Small batches are therefore replayed from a CUDA graph captured once
+    # per (batch, w, adain, code_only): static input/output buffers, same kernels, same results.
+    cuda_graph_max_batch = 4
+
+    def _cfb_forward_graphed(self, x, w, adain, code_only):
+        lib = _lib.load()
+        dev = x.device
+        B = x.shape[0]
+        key = (dev.index, B, w, adain, code_only)
+        ent = self._cfb_graphs.get(key)
+        if ent is None:
+            if len(self._cfb_graphs) >= 8:                   # callers sweep w: keep the cache bounded
+                self._cfb_graphs.clear()
+            sx = torch.empty_like(x)
+            logits = torch.empty((B, self.latent_size, self.codebook_size), dtype=torch.float32, device=dev)
+            lq = torch.empty((B, 256, 16, 16), dtype=torch.float32, device=dev)
+            out = None if code_only else torch.empty_like(x)
+            ws = torch.empty(int(lib.cfb_workspace_bytes(self._cfb_net, B)), dtype=torch.uint8, device=dev)
+
+            def launch():
+                _lib.check(lib.cfb_codeformer_forward(self._cfb_net, _lib.ptr(sx), _lib.ptr(out), _lib.ptr(logits), _lib.ptr(lq),
+                                                      None, B, w, int(adain), int(code_only), _lib.ptr(ws), ws.numel(),
+                                                      _stream_ptr(dev)), 'cfb_codeformer_forward')
+            sx.copy_(x)
+            launch()                                         # eager warm-up: one-time function attributes, lazy module load
+            torch.cuda.current_stream(dev).synchronize()
+            g = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(g):
+                    launch()
+            except Exception:                                # capture not possible here: keep the plain launch path
+                self._cfb_graphs[key] = False
+                return None
+            ent = (g, sx, out, logits, lq, ws)
+            self._cfb_graphs[key] = ent
+        if ent is False:
+            return None
+        g, sx, out, logits, lq, ws = ent
+        sx.copy_(x)
+        g.replay()
+        if code_only:
+            return logits.clone(), lq.clone()
+        return out.clone(), logits.clone(), lq.clone()
 
     def forward_host(self, x_host, w=0, adain=False, device=None):
         """End-to-end call with HOST tensors (``cfb_codeformer_forward_host``): pinned x -> H2D -> forward ->
