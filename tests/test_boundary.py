@@ -110,3 +110,19 @@ def test_product_never_imports_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 src = open(os.path.join(dp, f)).read()
                 assert 'oracle' not in src.replace('no CPU fallback', ''), f'{f} mentions the oracle'
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason='/root/reference not present (GPU box)')
+def test_install_replaces_entries_of_the_reference_registry():
+    """`install()` must swap the two entries of the reference's own ARCH_REGISTRY in place (registry.py:39 would assert
+    on a second registration), after which the reference's lookup returns the B200 classes."""
+    _, _, _, REG = ref_shim.load()
+    before = REG.get('CodeFormer')
+    try:
+        cb.install(REG)
+        assert REG.get('CodeFormer') is cb.CodeFormer and REG.get('VQAutoEncoder') is cb.VQAutoEncoder
+        net = REG.get('CodeFormer')(dim_embd=512, codebook_size=1024, n_head=8, n_layers=9,
+                                    connect_list=['32', '64', '128', '256'])
+        assert len(net.state_dict()) == 515
+    finally:
+        REG._obj_map['CodeFormer'] = before
