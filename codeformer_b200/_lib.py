@@ -68,8 +68,14 @@ def load():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
-        raise RuntimeError(f'{LIB_PATH} is missing: build it with `python -m codeformer_b200.build` '
-                           '(there is no CPU or PyTorch fallback for this path)')
+        # a fresh checkout has no binary: compile the CUDA sources in-tree (nvcc, sm_100a).  Never a CPU/PyTorch fallback:
+        # if that is impossible the import fails loudly.
+        try:
+            from . import build as _build
+            _build.build(force=True)
+        except Exception as e:  # noqa: BLE001
+            raise RuntimeError(f'{LIB_PATH} is missing and could not be built with nvcc ({e}); there is no CPU or '
+                               'PyTorch fallback for this path -- run `python -m codeformer_b200.build`') from e
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)            # AttributeError if the library does not export a declared symbol
