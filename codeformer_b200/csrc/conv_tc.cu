@@ -309,6 +309,8 @@ struct TcParams {
   float sft_w;
   const float* wscale_inv;  // device scalar: 2^-k of the weight split
   float* out;
+  __half* pl_hi;            // optional: `out` again as fp16 hi / lo planes (operand of a following raw-input conv)
+  __half* pl_lo;
   float* gn_part;           // optional GroupNorm(32) partial sums of `out`: [m_tile*4 + warp][32][2]
   int gn_cpg;               // channels per group = Cout/32
 };
@@ -676,6 +678,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             v.z = d.z + p.sft_w * (d.z * sc.z + v.z); v.w = d.w + p.sft_w * (d.w * sc.w + v.w);
           }
           *reinterpret_cast<float4*>(p.out + off) = v;
+          if (p.pl_hi) {
+            const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+            const __half2 l01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
+            uint2 ph, pl;
+            ph.x = *reinterpret_cast<const uint32_t*>(&h01); ph.y = *reinterpret_cast<const uint32_t*>(&h23);
+            pl.x = *reinterpret_cast<const uint32_t*>(&l01); pl.y = *reinterpret_cast<const uint32_t*>(&l23);
+            *reinterpret_cast<uint2*>(p.pl_hi + off) = ph;
+            *reinterpret_cast<uint2*>(p.pl_lo + off) = pl;
+          }
           if constexpr (CPG == 2) {
             s0 += v.x + v.y; q0 += fmaf(v.x, v.x, v.y * v.y);
             s1 += v.z + v.w; q1 += fmaf(v.z, v.z, v.w * v.w);
@@ -903,6 +915,8 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
   p.bias = a.bias; p.residual = a.residual; p.out_act = a.out_act;
   p.sft_dec = a.sft_dec; p.sft_scale = a.sft_scale; p.sft_w = a.sft_w; p.wscale_inv = a.wscale_inv; p.out = a.out;
   p.gn_part = a.gn_part; p.gn_cpg = a.Cout / 32;
+  p.pl_hi = (__half*)a.out_planes;
+  p.pl_lo = a.out_planes ? (__half*)((char*)a.out_planes + (((size_t)a.N * a.Ho * a.Wo * a.Cout * 2 + 1023) / 1024 * 1024)) : nullptr;
   const int cpg = a.gn_part ? a.Cout / 32 : 0;
   CFB_REQUIRE(!a.gn_part || tc_can_emit_stats(a), "conv_tc: GroupNorm partials are not available for this Cout");
   if (BN == 128) {

@@ -73,6 +73,8 @@ struct ConvArgs {
   float* out = nullptr;             // [N,Ho,Wo,Cout]
   // tensor-core engine only: GroupNorm(32) partial sums of `out`, [N*tiles_per_image*4][32 groups][2] floats
   float* gn_part = nullptr;
+  // tensor-core engine only: also emit `out` as fp16 hi/lo operand planes for a following conv that consumes it raw
+  void* out_planes = nullptr;       // [hi plane | lo plane], each align1024(N*Ho*Wo*Cout*2) bytes
   bool skip_prep = false;           // operand planes in `scratch` are already valid (kernel-only timing)
 };
 

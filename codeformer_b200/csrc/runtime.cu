@@ -90,6 +90,7 @@ struct Tensor {
   bool owned = true;  // false: caller memory or kept-alive tap
   float* gn_part = nullptr;   // GroupNorm partial sums emitted by the producing tensor-core conv (or null)
   int gn_slots = 0;           // partial slots per image
+  void* planes = nullptr;     // fp16 hi/lo operand planes of this tensor emitted by the producing conv (raw values)
   int64_t numel() const { return (int64_t)N * H * W * C; }
 };
 
@@ -419,8 +420,8 @@ struct Fwd {
     return 0;
   }
   void release(Tensor& t) {
-    if (t.owned && t.p) { ar.release(t.p); if (t.gn_part) ar.release(t.gn_part); }
-    t.p = nullptr; t.gn_part = nullptr;
+    if (t.owned && t.p) { ar.release(t.p); if (t.gn_part) ar.release(t.gn_part); if (t.planes) ar.release(t.planes); }
+    t.p = nullptr; t.gn_part = nullptr; t.planes = nullptr;
   }
   void release_raw(void* p) { ar.release(p); }
 
@@ -441,6 +442,7 @@ struct Fwd {
     const float* sft_dec = nullptr; const float* sft_scale = nullptr; float sft_w = 0.f;
     float* out_ptr = nullptr;   // write into caller memory instead of the arena
     bool want_stats = false;    // consumer is a GroupNorm: let the tensor-core epilogue emit the partial sums
+    bool want_planes = false;   // a following conv reads this output raw: emit its fp16 hi/lo operand planes too
   };
 
   int conv(const ConvW& w, const Tensor& in, Tensor& out, const ConvOpt& o) {
@@ -464,11 +466,18 @@ struct Fwd {
         CFB_CHECK(alloc_raw((void**)&out.gn_part, (size_t)in.N * out.gn_slots * 64 * sizeof(float)));
         a.gn_part = out.gn_part;
       }
-      const size_t sb = tc_scratch_bytes(a);
-      void* scratch = nullptr;
-      CFB_CHECK(alloc_raw(&scratch, sb));
+      if (o.want_planes && !o.out_ptr) {
+        const size_t pb = (((size_t)in.N * Ho * Wo * w.cout * 2 + 1023) / 1024 * 1024) * 2;
+        CFB_CHECK(alloc_raw(&out.planes, pb));
+        a.out_planes = out.planes;
+      }
+      // the producer already emitted this input's operand planes and the conv takes it raw: no prep pass
+      const bool reuse = in.planes && !o.in_scale && o.in_act == IN_NONE;
+      void* scratch = in.planes;
+      if (!reuse) CFB_CHECK(alloc_raw(&scratch, tc_scratch_bytes(a)));
+      a.skip_prep = reuse;
       if (!dry) CFB_CHECK(conv_tc(a, scratch, n->sm_count, st));
-      release_raw(scratch);
+      if (!reuse) release_raw(scratch);
     } else {
       if (!dry) CFB_CHECK(conv_f32(a, st));
     }
@@ -493,7 +502,7 @@ struct Fwd {
   }
 
   // ResBlock.forward  vqgan_arch.py:153-164
-  int resblock(const ResW& r, const Tensor& x, Tensor& y) {
+  int resblock(const ResW& r, const Tensor& x, Tensor& y, bool out_planes = false) {
     float *s1, *h1, *s2, *h2;
     CFB_CHECK(gn(r.n1, x, &s1, &h1));
     Tensor h;
@@ -504,6 +513,7 @@ struct Fwd {
     Tensor skip = x; skip.owned = false;
     if (r.has_out) { ConvOpt oo; CFB_CHECK(conv(r.co, x, skip, oo)); }
     ConvOpt o2; o2.in_scale = s2; o2.in_shift = h2; o2.in_act = IN_SILU; o2.residual = skip.p; o2.want_stats = true;
+    o2.want_planes = out_planes;
     CFB_CHECK(conv(r.c2, h, y, o2));
     release_raw(s2); release_raw(h2);
     release(h);
@@ -512,7 +522,7 @@ struct Fwd {
   }
 
   // AttnBlock.forward  vqgan_arch.py:202-226
-  int attnblock(const AttnW& w, const Tensor& x, Tensor& y) {
+  int attnblock(const AttnW& w, const Tensor& x, Tensor& y, bool out_planes = false) {
     CFB_REQUIRE(x.H * x.W == 256, "AttnBlock: built for the 16x16 latent");
     float *s, *h;
     CFB_CHECK(gn(w.n, x, &s, &h));
@@ -527,7 +537,7 @@ struct Fwd {
       CFB_CHECK(attention(qkv.p, qkv.p + C, qkv.p + 2 * C, a.p, x.N, 256, 1, C, 3 * C, 3 * C, 3 * C, C,
                           1.0f / sqrtf((float)C), st));
     release(qkv);
-    ConvOpt op; op.residual = x.p; op.want_stats = true;
+    ConvOpt op; op.residual = x.p; op.want_stats = true; op.want_planes = out_planes;
     CFB_CHECK(conv(w.proj, a, y, op));
     release(a);
     return 0;
@@ -545,10 +555,10 @@ struct Fwd {
       if (!dry) CFB_CHECK(gn_cat_partials(enc_feat.gn_part, dec.gn_part, cat.gn_part, (int64_t)dec.N * cat.gn_slots, st));
     }
     Tensor e;
-    CFB_CHECK(resblock(f.enc, cat, e));
+    CFB_CHECK(resblock(f.enc, cat, e, true));      // scale.0 / shift.0 both read `e` raw: one set of planes, no prep
     release(cat);
     Tensor s0, sc, h0;
-    ConvOpt ol; ol.out_act = OUT_LRELU;
+    ConvOpt ol; ol.out_act = OUT_LRELU; ol.want_planes = true;      // s0 / h0 feed scale.2 / shift.2 raw
     CFB_CHECK(conv(f.s0, e, s0, ol));
     ConvOpt on;
     CFB_CHECK(conv(f.s2, s0, sc, on));
@@ -569,16 +579,24 @@ struct Fwd {
     if (!dry) CFB_CHECK(conv_first(x_nchw, n->enc[0].conv.w_f32, n->enc[0].conv.bias, x.p, B, c.img_size, c.img_size, c.nf, st));
     CFB_CHECK(capture("enc.0", x));
     float *ps = nullptr, *ph = nullptr;   // pending GroupNorm of a 'norm' block
+    // does the block after i read its input raw through a conv (Down/Upsample conv, or a ResBlock's 1x1 conv_out)?
+    auto next_raw = [](const std::vector<Block>& bl, size_t i) {
+      if (i + 1 >= bl.size()) return false;
+      const Block& nb = bl[i + 1];
+      return nb.kind == B_DOWN || nb.kind == B_UP || (nb.kind == B_RES && nb.res_w.has_out);
+    };
     for (size_t i = 1; i < n->enc.size(); ++i) {
       const Block& b = n->enc[i];
+      const bool pl = next_raw(n->enc, i);
       Tensor y;
       switch (b.kind) {
-        case B_RES: CFB_CHECK(resblock(b.res_w, x, y)); break;
-        case B_ATTN: CFB_CHECK(attnblock(b.attn, x, y)); break;
-        case B_DOWN: { ConvOpt o; o.mode = CONV_DOWN; o.want_stats = true; CFB_CHECK(conv(b.conv, x, y, o)); break; }
+        case B_RES: CFB_CHECK(resblock(b.res_w, x, y, pl)); break;
+        case B_ATTN: CFB_CHECK(attnblock(b.attn, x, y, pl)); break;
+        case B_DOWN: { ConvOpt o; o.mode = CONV_DOWN; o.want_stats = true; o.want_planes = pl; CFB_CHECK(conv(b.conv, x, y, o)); break; }
         case B_NORM: CFB_CHECK(gn(b.norm, x, &ps, &ph)); continue;   // consumed by the next conv
         case B_CONV: {
           ConvOpt o; o.in_scale = ps; o.in_shift = ph;
+          o.want_planes = (i + 1 == n->enc.size()) && n->cfg.kind == 1;   // lq_feat feeds feat_emb raw
           CFB_CHECK(conv(b.conv, x, y, o));
           if (ps) { release_raw(ps); release_raw(ph); ps = ph = nullptr; }
           break;
@@ -600,11 +618,16 @@ struct Fwd {
     float *ps = nullptr, *ph = nullptr;
     for (size_t i = 0; i < n->gen.size(); ++i) {
       const Block& b = n->gen[i];
+      bool pl = false;
+      if (i + 1 < n->gen.size()) {
+        const Block& nb = n->gen[i + 1];
+        pl = nb.kind == B_DOWN || nb.kind == B_UP || (nb.kind == B_RES && nb.res_w.has_out);
+      }
       Tensor y;
       switch (b.kind) {
-        case B_RES: CFB_CHECK(resblock(b.res_w, x, y)); break;
-        case B_ATTN: CFB_CHECK(attnblock(b.attn, x, y)); break;
-        case B_UP: { ConvOpt o; o.mode = CONV_UP; o.want_stats = true; CFB_CHECK(conv(b.conv, x, y, o)); break; }
+        case B_RES: CFB_CHECK(resblock(b.res_w, x, y, pl)); break;
+        case B_ATTN: CFB_CHECK(attnblock(b.attn, x, y, pl)); break;
+        case B_UP: { ConvOpt o; o.mode = CONV_UP; o.want_stats = true; o.want_planes = pl; CFB_CHECK(conv(b.conv, x, y, o)); break; }
         case B_NORM: CFB_CHECK(gn(b.norm, x, &ps, &ph)); continue;
         case B_CONV:
           if (i + 1 == n->gen.size()) {
