@@ -409,7 +409,7 @@ struct Fwd {
   int engine;   // 0 auto, 1 f32, 2 tc
 
   int alloc(Tensor& t, int N, int H, int W, int C) {
-    t.N = N; t.H = H; t.W = W; t.C = C; t.owned = true;
+    t.N = N; t.H = H; t.W = W; t.C = C; t.owned = true; t.gn_part = nullptr; t.gn_slots = 0; t.planes = nullptr;
     t.p = (float*)ar.alloc((size_t)t.numel() * 4);
     CFB_REQUIRE(t.p != nullptr, "workspace too small (use cfb_workspace_bytes)");
     return 0;
@@ -450,7 +450,10 @@ struct Fwd {
     int Ho = in.H, Wo = in.W;
     if (o.mode == CONV_DOWN) { Ho = in.H / 2; Wo = in.W / 2; }
     if (o.mode == CONV_UP) { Ho = in.H * 2; Wo = in.W * 2; }
-    if (o.out_ptr) { out.p = o.out_ptr; out.N = in.N; out.H = Ho; out.W = Wo; out.C = w.cout; out.owned = false; }
+    if (o.out_ptr) {
+      out.p = o.out_ptr; out.N = in.N; out.H = Ho; out.W = Wo; out.C = w.cout; out.owned = false;
+      out.gn_part = nullptr; out.gn_slots = 0; out.planes = nullptr;
+    }
     else CFB_CHECK(alloc(out, in.N, Ho, Wo, w.cout));
     ConvArgs a;
     a.in = in.p; a.N = in.N; a.H = in.H; a.W = in.W; a.Cin = in.C; a.Ho = Ho; a.Wo = Wo; a.Cout = w.cout;
@@ -878,15 +881,27 @@ int64_t cfb_workspace_bytes(cfb_net* n, int32_t batch) {
   API_BEGIN
   if (!n) { cfb::set_error("cfb_workspace_bytes: NULL net"); return -1; }
   std::lock_guard<std::mutex> lk(n->mu);
-  int rc;
-  if (n->cfg.kind == 1)
-    rc = cfb::codeformer_forward_impl(n, (const float*)0x1000, (float*)0x1000, nullptr, (float*)0x1000, nullptr, batch, 1.f, 1,
-                                      0, nullptr, 0, nullptr, true);
-  else
-    rc = cfb::vqae_forward_impl(n, (const float*)0x1000, (float*)0x1000, nullptr, nullptr, nullptr, batch, nullptr, 0, nullptr,
-                                true);
-  if (rc != 0) return -1;
-  return (int64_t)n->arena.high() + 4096;
+  // The arena is first-fit, so the peak depends on the exact allocation sequence, which the call flags change (fusion on
+  // or off, AdaIN, code_only, caller-provided logits or not): size for the worst of all of them (host-only dry runs).
+  size_t high = 0;
+  if (n->cfg.kind == 1) {
+    for (int m = 0; m < 16; ++m) {
+      const float w = (m & 1) ? 1.f : 0.f;
+      float* lg = (m & 8) ? (float*)0x1000 : nullptr;
+      if (cfb::codeformer_forward_impl(n, (const float*)0x1000, (float*)0x1000, lg, (float*)0x1000, nullptr, batch, w, (m >> 1) & 1,
+                                       (m >> 2) & 1, nullptr, 0, nullptr, true) != 0)
+        return -1;
+      if (n->arena.high() > high) high = n->arena.high();
+    }
+  } else {
+    for (int m = 0; m < 2; ++m) {
+      if (cfb::vqae_forward_impl(n, (const float*)0x1000, (float*)0x1000, m ? (int64_t*)0x1000 : nullptr, m ? (float*)0x1000 : nullptr,
+                                 nullptr, batch, nullptr, 0, nullptr, true) != 0)
+        return -1;
+      if (n->arena.high() > high) high = n->arena.high();
+    }
+  }
+  return (int64_t)high + 4096;
   API_END(-1)
 }
 
