@@ -174,3 +174,40 @@ def test_block_by_block_vs_oracle(engine):
     print(f'[{engine}] out {maxabs(out.cpu(), ro):.3e} logits {maxabs(logits.cpu(), rl):.3e}')
     assert torch.equal(logits.argmax(2).cpu(), rl.argmax(2))
     assert worst < 2e-4 and maxabs(out.cpu(), ro) < TOL_OUT
+
+
+def test_full_size_properties_batch32(net_main):
+    """BASELINE.json configs[1] size (batch 32): size-independent properties instead of an oracle run --
+    run-to-run determinism, equivariance under a permutation of the faces, and agreement with the 4-face runs."""
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(32, 3, 512, 512, generator=g).clamp_(-1, 1)
+    x[:4] = faces_input(slice(0, 4))
+    xd = x.cuda()
+    o1, l1, q1 = net_main(xd, w=0.5, adain=True)
+    o2, l2, q2 = net_main(xd, w=0.5, adain=True)
+    assert torch.equal(o1, o2) and torch.equal(l1, l2) and torch.equal(q1, q2), 'forward must be deterministic'
+    perm = torch.randperm(32, generator=g)
+    op, lp, qp = net_main(xd[perm.cuda()], w=0.5, adain=True)
+    assert torch.equal(op, o1[perm.cuda()]) and torch.equal(lp, l1[perm.cuda()]), 'faces must not interact'
+    o4 = net_main(xd[:4], w=0.5, adain=True)[0]
+    assert torch.equal(o4, o1[:4])
+    assert bool(torch.isfinite(o1).all())
+
+
+def test_vq_properties_full_size():
+    """VectorQuantizer at the config-3 size: z_q rows are codebook rows up to the straight-through rounding, re-quantising
+    z_q is idempotent, and the histogram-based perplexity matches the indices."""
+    from tests.util import vq_micro_inputs
+    E, z = vq_micro_inputs('C')
+    vq = cb.VectorQuantizer(1024, 256, 0.25)
+    vq.embedding.weight.data.copy_(E)
+    vq = vq.cuda()
+    zq, loss, st = vq(z.cuda())
+    idx = st['min_encoding_indices'][:, 0]
+    rows = zq.permute(0, 2, 3, 1).reshape(-1, 256)
+    assert float((rows - E.cuda()[idx]).abs().max()) <= 4e-6          # z + (e - z) is a few ulp off e (vqgan_arch.py:57)
+    zq2, _, st2 = vq(zq)
+    assert torch.equal(st2['min_encoding_indices'], st['min_encoding_indices'])
+    counts = torch.bincount(idx, minlength=1024).float() / idx.numel()
+    ppl = torch.exp(-(counts * torch.log(counts + 1e-10)).sum())
+    assert abs(float(ppl) - float(st['perplexity'])) < 1e-3 * float(ppl)
