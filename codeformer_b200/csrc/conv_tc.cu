@@ -771,7 +771,7 @@ static inline int tile_bw(int Wo) { return Wo < 128 ? Wo : 128; }
 static int tc_chunk_kblocks() {
   static int v = [] {
     const char* e = getenv("CFB_TC_CHUNK");
-    int c = e ? atoi(e) : 4;
+    int c = e ? atoi(e) : 8;
     return c < 1 ? 1 : (c > 4096 ? 4096 : c);
   }();
   return v;
