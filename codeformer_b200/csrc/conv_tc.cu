@@ -5,19 +5,24 @@
 //   Fuse_sft convs, Linear    /root/reference/basicsr/archs/codeformer_arch.py:104-106,141-149,183,192
 // as GEMMs  D[M = 128 output pixels, N = Cout tile] += A[M, K] * B[N, K]^T  with K = taps * Cin, on the
 // 5th-generation tensor cores:
-//   * operands are error-compensated fp16 pairs  x = hi + lo  (hi = fp16(x), lo = fp16(x - hi)); every k-block
-//     issues three tcgen05.mma kind::f16:  hi*hi + hi*lo + lo*hi  into ONE fp32 accumulator in TMEM
-//     (>= 21 effective mantissa bits; the 1e-3 parity bar needs >= 16);
-//   * A tiles are fetched by TMA straight from the NHWC activation planes: one 4-D box {64 ch, BW, BH, 1} per
-//     filter tap at shifted (x+s-1, y+r-1) coordinates -- out-of-bounds rows/cols are zero-filled by the TMA
-//     unit, which *is* the conv padding; the box lands in shared memory as 128 rows x 128 B in the 128B-swizzled
-//     K-major layout the UMMA descriptor expects (no im2col buffer anywhere);
+//   * operands are error-compensated fp16 pairs  x = hi + lo  (hi = fp16(x), lo = fp16(x - hi)); the products
+//     hi*hi + hi*lo + lo*hi are formed with TWO tcgen05.mma kind::f16 per k-step: A_hi x [B_hi;B_lo] (one N = 2*BN
+//     operand, the hi and lo weight tiles are adjacent in smem) and A_lo x B_hi, into a "main" and a "cross" half of
+//     an fp32 TMEM slot (>= 21 effective mantissa bits; the 1e-3 parity bar needs >= 16);
+//   * tcgen05.mma truncates when it adds into its accumulator, so a TMEM slot only receives `chunk` k-blocks before the
+//     epilogue warps fold it into fp32 registers with round-to-nearest adds (ring of 2-4 slots: cfull/cempty);
+//   * A tiles are fetched by TMA straight from the NHWC operand planes: one 4-D box {64 ch, BW, BH, 1} per filter tap at
+//     shifted (x+s-1, y+r-1) coordinates -- out-of-bounds rows/cols are zero-filled by the TMA unit, which *is* the conv
+//     padding; the box lands in shared memory as 128 rows x 128 B in the 128B-swizzled K-major layout the UMMA
+//     descriptor expects (no im2col buffer anywhere).  Stride-2 Downsample = TMA traversal strides (elementStrides 2);
+//     Upsample = four 2x2 parity convs on the low-res planes with pre-summed weights;
 //   * B tiles ([tap][Cout][Cin] fp16) by 3-D TMA boxes {64, BN, 1};
-//   * warp-specialised persistent CTAs (1 per SM): warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc),
-//     warps 2..9 = epilogue (tcgen05.ld -> fold partial sums -> bias / residual / activation / SFT -> fp32 NHWC
-//     stores + GroupNorm partial sums); smem ring of STAGES k-blocks (full/empty mbarriers) and a ring of 4 TMEM
-//     partial-sum slots (cfull/cempty) so folding / storing overlaps the MMAs of the following k-blocks / tile;
-//   * stride-2 Downsample uses TMA traversal strides (elementStrides = 2) on the same path.
+//   * warp-specialised persistent CTAs (1 per SM): warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), both kept
+//     converged with elect.sync-predicated issue; warps 2..9 = epilogue (tcgen05.ld -> fold -> per-warp swizzled smem
+//     transpose -> bias / residual / activation / SFT -> coalesced fp32 NHWC stores, optional fp16 hi/lo planes for a
+//     raw-input consumer, GroupNorm(32) partial sums);
+//   * an optional "halo" engine (HALO=true, CFB_TC_HALO=1) fetches each (18x10) input patch once and serves the 9 taps
+//     through row-shifted descriptors (see the comment at tc_geometry for why it is off by default).
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -343,27 +348,6 @@ struct TcCfg {
   static constexpr int H_B_SLOTS = (BN == 64) ? 6 : 3;
   static constexpr int H_SMEM_BYTES = H_A_SLOTS * H_A_SLOT + H_B_SLOTS * H_B_SLOT + 1024 + 256 + STG_BYTES;
 };
-
-// Butterfly reduction of G per-lane group sums over the 32 lanes of a warp: after log2(G) exchange steps every lane
-// owns ONE group (index lane / (32/G)) and the remaining steps are plain xor-reductions.  G-1 + (5-log2 G) shuffles
-// instead of 5*G.  Fixed order => deterministic.
-template <int G>
-__device__ __forceinline__ void warp_group_reduce(float (&v)[G], int lane) {
-  int o = 16;
-#pragma unroll
-  for (int n = G; n > 1; n >>= 1) {
-    const int half = n >> 1;
-    const bool up = (lane & o) != 0;
-#pragma unroll
-    for (int i = 0; i < half; ++i) {
-      const float send = up ? v[i] : v[i + half];
-      const float keep = up ? v[i + half] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-    }
-    o >>= 1;
-  }
-  for (; o >= 1; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
-}
 
 // Accumulation scheme (why the TMEM ring): tcgen05.mma adds into its fp32 accumulator with truncation, so a long
 // K loop into one accumulator drifts by ~(#MMAs)*2^-25 relative (measured 2e-5 at K=4608 -- too much for the
