@@ -304,6 +304,8 @@ struct TcParams {
   int m_tiles, n_tiles;
   int kblocks;            // Cin / 64
   int chunk;              // k-blocks accumulated in TMEM before the partial sum is folded into registers
+  int a_c0, b_c0;         // channel offsets of the A / B operand inside their planes (batched-GEMM mode)
+  int b_batched;          // B operand is a per-image activation plane: third TMA coordinate = image index, not the tap
   int up4;                // Upsample as four 2x2 convs: m-tile = (low-res tile, output parity), 4 taps, weights [16][Cout][Cin]
   int PW, PH;             // halo engine: input patch (BW+k-1) x (BH+k-1) pixels fetched once per 64-channel block
   const float* bias;
@@ -457,10 +459,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 const uint32_t fb = smem_u32(full + stage);
                 mbar_expect_tx(fb, (uint32_t)Cfg::STAGE_BYTES);
                 const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                tma_load_4d(sa, &tmA_hi, fb, kb * 64, x0 + s - p.pad, y0 + r - p.pad, n);
-                tma_load_4d(sa + TC_A_BYTES, &tmA_lo, fb, kb * 64, x0 + s - p.pad, y0 + r - p.pad, n);
-                tma_load_3d(sa + 2 * TC_A_BYTES, &tmB_hi, fb, kb * 64, nt * BN, btap);
-                tma_load_3d(sa + 2 * TC_A_BYTES + Cfg::B_BYTES, &tmB_lo, fb, kb * 64, nt * BN, btap);
+                const int b3 = p.b_batched ? n : btap;
+                tma_load_4d(sa, &tmA_hi, fb, p.a_c0 + kb * 64, x0 + s - p.pad, y0 + r - p.pad, n);
+                tma_load_4d(sa + TC_A_BYTES, &tmA_lo, fb, p.a_c0 + kb * 64, x0 + s - p.pad, y0 + r - p.pad, n);
+                tma_load_3d(sa + 2 * TC_A_BYTES, &tmB_hi, fb, p.b_c0 + kb * 64, nt * BN, b3);
+                tma_load_3d(sa + 2 * TC_A_BYTES + Cfg::B_BYTES, &tmB_lo, fb, p.b_c0 + kb * 64, nt * BN, b3);
               }
               __syncwarp();
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -890,6 +893,7 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
   p.N = a.N; p.Ho = a.Ho; p.Wo = a.Wo; p.Cout = a.Cout;
   p.taps = a.ksize * a.ksize; p.pad = a.mode == CONV_DOWN ? 0 : a.ksize / 2; p.stride = a.mode == CONV_DOWN ? 2 : 1;
   p.up4 = a.mode == CONV_UP ? 1 : 0;
+  p.a_c0 = 0; p.b_c0 = 0; p.b_batched = 0;
   if (p.up4) { p.taps = 4; p.pad = 1; }
   p.chunk = tc_chunk_kblocks();
   p.PW = PW; p.PH = PH;
@@ -918,6 +922,114 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
   return 1;
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// Batched GEMM on the same engine (attention cores): per image n
+//     out[n][t][j] = scale * sum_k A[n][t][a_c0 + k] * B[n][j][b_c0 + k],   t in 0..255 (16x16 tokens), j in 0..Cout-1
+// A and B are fp16 hi/lo operand planes (token-major, channel pitch a_pitch / b_pitch); B is addressed per image
+// through the third TMA coordinate.  Used for  scores = q k^T * C^-1/2  and  out = P v  of AttnBlock
+// (/root/reference/basicsr/archs/vqgan_arch.py:209-222).
+// ------------------------------------------------------------------------------------------------------
+int bmm_tc(const BmmArgs& g, int sm_count, cudaStream_t st) {
+  CFB_REQUIRE(g.K % 64 == 0 && g.Cout % 128 == 0 && g.N >= 0, "bmm_tc: K must be a multiple of 64 and Cout of 128");
+  CFB_REQUIRE(g.a_c0 % 64 == 0 && g.b_c0 % 64 == 0 && g.a_pitch % 8 == 0 && g.b_pitch % 8 == 0, "bmm_tc: unaligned operand slice");
+  if (g.N == 0) return 0;
+  const size_t a_plane = ((size_t)g.N * 256 * g.a_pitch * 2 + 1023) / 1024 * 1024;
+  const size_t b_plane = ((size_t)g.N * g.b_rows * g.b_pitch * 2 + 1023) / 1024 * 1024;
+  CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
+  {
+    const uint64_t dims[4] = {(uint64_t)g.a_pitch, 16, 16, (uint64_t)g.N};
+    const uint64_t str[3] = {(uint64_t)g.a_pitch * 2, (uint64_t)16 * g.a_pitch * 2, (uint64_t)256 * g.a_pitch * 2};
+    const uint32_t box[4] = {64, 16, 8, 1};
+    CFB_CHECK(make_map(&mA_hi, g.a_planes, 4, dims, str, box));
+    CFB_CHECK(make_map(&mA_lo, (const char*)g.a_planes + a_plane, 4, dims, str, box));
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)g.b_pitch, (uint64_t)g.b_rows, (uint64_t)g.N};
+    const uint64_t str[2] = {(uint64_t)g.b_pitch * 2, (uint64_t)g.b_rows * g.b_pitch * 2};
+    const uint32_t box[3] = {64, 128, 1};
+    CFB_CHECK(make_map(&mB_hi, g.b_planes, 3, dims, str, box));
+    CFB_CHECK(make_map(&mB_lo, (const char*)g.b_planes + b_plane, 3, dims, str, box));
+  }
+  TcParams p;
+  p.N = g.N; p.Ho = 16; p.Wo = 16; p.Cout = g.Cout;
+  p.taps = 1; p.pad = 0; p.stride = 1; p.up4 = 0;
+  p.a_c0 = g.a_c0; p.b_c0 = g.b_c0; p.b_batched = 1;
+  p.chunk = tc_chunk_kblocks();
+  p.PW = 0; p.PH = 0;
+  p.BW = 16; p.BH = 8; p.tiles_x = 1; p.tiles_y = 2;
+  p.m_tiles = g.N * 2; p.n_tiles = g.Cout / 128; p.kblocks = g.K / 64;
+  p.bias = nullptr; p.residual = nullptr; p.out_act = OUT_NONE; p.sft_dec = nullptr; p.sft_scale = nullptr; p.sft_w = 0.f;
+  p.wscale_inv = g.scale_dev; p.out = g.out;
+  p.gn_part = nullptr; p.gn_cpg = 0;
+  p.pl_hi = (__half*)g.out_planes;
+  p.pl_lo = g.out_planes ? (__half*)((char*)g.out_planes + (((size_t)g.N * 256 * g.Cout * 2 + 1023) / 1024 * 1024)) : nullptr;
+  return launch_tc<128, 0>(mA_hi, mA_lo, mB_hi, mB_lo, p, sm_count, st);
+}
+
+// softmax over rows of 256 fp32 scores -> fp16 hi/lo operand planes of the probabilities (one warp per row)
+__global__ void __launch_bounds__(256) softmax256_planes_kernel(const float* __restrict__ s, __half* __restrict__ hi,
+                                                                __half* __restrict__ lo, int64_t rows) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int l = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(s + row * 256 + l * 8));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(s + row * 256 + l * 8 + 4));
+  float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  float mx = v[0];
+#pragma unroll
+  for (int j = 1; j < 8; ++j) mx = fmaxf(mx, v[j]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { v[j] = expf(v[j] - mx); sum += v[j]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.f / sum;
+  __align__(16) __half hh[8];
+  __align__(16) __half ll[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float pv = v[j] * inv;
+    hh[j] = __float2half_rn(pv);
+    ll[j] = __float2half_rn(pv - __half2float(hh[j]));
+  }
+  *reinterpret_cast<uint4*>(hi + row * 256 + l * 8) = *reinterpret_cast<const uint4*>(hh);
+  *reinterpret_cast<uint4*>(lo + row * 256 + l * 8) = *reinterpret_cast<const uint4*>(ll);
+}
+int softmax256_planes(const float* scores, void* planes, int64_t rows, cudaStream_t st) {
+  if (rows == 0) return 0;
+  const size_t plane = ((size_t)rows * 256 * 2 + 1023) / 1024 * 1024;
+  softmax256_planes_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(scores, (__half*)planes, (__half*)((char*)planes + plane), rows);
+  CFB_LAUNCH_CHECK();
+  return 0;
+}
+
+// V^T operand planes: in planes [N][256 tokens][pitch] (channels c0..c0+C) -> out planes [N][C][256], hi and lo
+__global__ void transpose_planes_kernel(const __half* __restrict__ in, __half* __restrict__ out, int pitch, int c0, int C) {
+  __shared__ __half tile[32][34];
+  const int n = blockIdx.z, t0 = blockIdx.y * 32, cb = blockIdx.x * 32;
+  const __half* ib = in + (int64_t)n * 256 * pitch;
+  __half* ob = out + (int64_t)n * C * 256;
+  for (int i = threadIdx.y; i < 32; i += 8) tile[i][threadIdx.x] = ib[(int64_t)(t0 + i) * pitch + c0 + cb + threadIdx.x];
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) ob[(int64_t)(cb + i) * 256 + t0 + threadIdx.x] = tile[threadIdx.x][i];
+}
+int transpose_planes(const void* in_planes, int N, int pitch, int c0, int C, void* out_planes, cudaStream_t st) {
+  CFB_REQUIRE(C % 32 == 0, "transpose_planes: C must be a multiple of 32");
+  if (N == 0) return 0;
+  const size_t ip = ((size_t)N * 256 * pitch * 2 + 1023) / 1024 * 1024;
+  const size_t op = ((size_t)N * C * 256 * 2 + 1023) / 1024 * 1024;
+  dim3 grid(C / 32, 8, N);
+  CFB_REQUIRE(N <= 65535, "transpose_planes: batch too large");
+  for (int h = 0; h < 2; ++h) {
+    transpose_planes_kernel<<<grid, dim3(32, 8), 0, st>>>((const __half*)((const char*)in_planes + h * ip),
+                                                          (__half*)((char*)out_planes + h * op), pitch, c0, C);
+    CFB_LAUNCH_CHECK();
+  }
+  return 0;
+}
 
 // ------------------------------------------------------------------------------------------------------
 // Diagnostics: which shared-memory rows does a K-major SWIZZLE_128B UMMA descriptor read when its start address is

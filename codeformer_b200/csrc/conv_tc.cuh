@@ -16,6 +16,18 @@ size_t tc_scratch_bytes(const ConvArgs& a);   // operand (hi/lo fp16 activation 
 bool tc_can_emit_stats(const ConvArgs& a);    // GroupNorm(32) partial sums available from the epilogue for this shape
 int tc_tiles_per_image(const ConvArgs& a);    // 128-pixel tiles per image (GroupNorm partial slots = 4x this)
 int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st);
+// batched GEMM over 16x16-token images on fp16 hi/lo operand planes (attention cores); see conv_tc.cu
+struct BmmArgs {
+  const void* a_planes = nullptr; int a_pitch = 0, a_c0 = 0;   // A: [N][256][a_pitch] hi | lo
+  const void* b_planes = nullptr; int b_pitch = 0, b_c0 = 0, b_rows = 0;   // B: [N][b_rows][b_pitch] hi | lo
+  int N = 0, K = 0, Cout = 0;
+  const float* scale_dev = nullptr;   // device scalar multiplied into the result
+  float* out = nullptr;               // [N][256][Cout] fp32
+  void* out_planes = nullptr;         // optional hi | lo planes of out
+};
+int bmm_tc(const BmmArgs& g, int sm_count, cudaStream_t st);
+int softmax256_planes(const float* scores, void* planes, int64_t rows, cudaStream_t st);
+int transpose_planes(const void* in_planes, int N, int pitch, int c0, int C, void* out_planes, cudaStream_t st);
 // diagnostics (tools/umma_probe.py): row-shifted SWIZZLE_128B descriptor views
 int umma_probe(const void* a_f16, int rowsA, const void* b_f16, const int* cfg_dev, int ncfg, float* out, cudaStream_t st);
 int umma_rate(int N, int nacc, int reps, long long* out_dev, int ctas, cudaStream_t st);

@@ -112,7 +112,7 @@ struct ConvW {
 };
 struct NormW { std::string name; int c = 0; const float* gamma = nullptr; const float* beta = nullptr; };
 struct ResW { NormW n1, n2; ConvW c1, c2, co; bool has_out = false; };
-struct AttnW { NormW n; ConvW qkv, proj; };
+struct AttnW { NormW n; ConvW qkv, proj; float* consts = nullptr; /* device: [0] = C^-1/2, [1] = 1 */ };
 struct FuseW { ResW enc; ConvW s0, s2, h0, h2; };
 struct LayerW { NormW n1, n2; ConvW qk, v, o, l1, l2; };
 struct Block { int kind; int cin, cout, res; ConvW conv; ResW res_w; AttnW attn; NormW norm; };
@@ -340,6 +340,7 @@ static int prepare(cfb_net* n, cudaStream_t st) {
   if (n->cfg.kind == 1) total += align256((size_t)n->cfg.latent_size * n->cfg.dim_embd * 4);
   const size_t scratch = align256((size_t)3 * 512 * 512 * 4) + align256(3 * 512 * 4);
   total += scratch;
+  total += 256 * (n->enc.size() + n->gen.size());      // per-AttnBlock device constants
   if (n->slab_bytes < total) {
     if (n->slab) cudaFree(n->slab);
     n->slab = nullptr; n->slab_bytes = 0;
@@ -394,6 +395,13 @@ static int prepare(cfb_net* n, cudaStream_t st) {
     CFB_CUDA(cudaMemcpyAsync(dst, src, (size_t)ne * 4, cudaMemcpyDeviceToDevice, st));
     n->position_emb = dst;
   }
+  for (std::vector<Block>* bl : {&n->enc, &n->gen})
+    for (Block& b : *bl)
+      if (b.kind == B_ATTN) {
+        b.attn.consts = (float*)take(8);
+        const float hc[2] = {1.0f / sqrtf((float)b.cin), 1.0f};
+        CFB_CUDA(cudaMemcpyAsync(b.attn.consts, hc, sizeof(hc), cudaMemcpyHostToDevice, st));
+      }
   // the qkv scratch is read by kernels enqueued above: the sources must stay valid until they ran
   CFB_CUDA(cudaStreamSynchronize(st));
   n->prepared = true;
@@ -529,16 +537,43 @@ struct Fwd {
     CFB_REQUIRE(x.H * x.W == 256, "AttnBlock: built for the 16x16 latent");
     float *s, *h;
     CFB_CHECK(gn(w.n, x, &s, &h));
+    const int C = x.C;
+    const bool tc_attn = engine != 1 && n->tc_ok && x.H == 16 && x.W == 16 && C % 128 == 0;
     Tensor qkv;
-    ConvOpt o; o.in_scale = s; o.in_shift = h;
+    ConvOpt o; o.in_scale = s; o.in_shift = h; o.want_planes = tc_attn;
     CFB_CHECK(conv(w.qkv, x, qkv, o));
     release_raw(s); release_raw(h);
     Tensor a;
     CFB_CHECK(alloc(a, x.N, x.H, x.W, x.C));
-    const int C = x.C;
-    if (!dry)
-      CFB_CHECK(attention(qkv.p, qkv.p + C, qkv.p + 2 * C, a.p, x.N, 256, 1, C, 3 * C, 3 * C, 3 * C, C,
-                          1.0f / sqrtf((float)C), st));
+    if (tc_attn && qkv.planes) {
+      // attention core on the tcgen05 engine: scores = q k^T C^-1/2 and out = P v as per-image GEMMs on operand planes
+      const int64_t T = (int64_t)x.N * 256;
+      float* scores = nullptr;
+      void *pp = nullptr, *vt = nullptr;
+      CFB_CHECK(alloc_raw((void**)&scores, (size_t)T * 256 * 4));
+      CFB_CHECK(alloc_raw(&pp, 2 * (((size_t)T * 256 * 2 + 1023) / 1024 * 1024)));
+      CFB_CHECK(alloc_raw(&vt, 2 * (((size_t)x.N * C * 256 * 2 + 1023) / 1024 * 1024)));
+      CFB_CHECK(alloc_raw(&a.planes, 2 * (((size_t)T * C * 2 + 1023) / 1024 * 1024)));
+      if (!dry) {
+        BmmArgs g1;
+        g1.a_planes = qkv.planes; g1.a_pitch = 3 * C; g1.a_c0 = 0;
+        g1.b_planes = qkv.planes; g1.b_pitch = 3 * C; g1.b_c0 = C; g1.b_rows = 256;
+        g1.N = x.N; g1.K = C; g1.Cout = 256; g1.scale_dev = w.consts; g1.out = scores;
+        CFB_CHECK(bmm_tc(g1, n->sm_count, st));
+        CFB_CHECK(softmax256_planes(scores, pp, T, st));
+        CFB_CHECK(transpose_planes(qkv.planes, x.N, 3 * C, 2 * C, C, vt, st));
+        BmmArgs g2;
+        g2.a_planes = pp; g2.a_pitch = 256; g2.a_c0 = 0;
+        g2.b_planes = vt; g2.b_pitch = 256; g2.b_c0 = 0; g2.b_rows = C;
+        g2.N = x.N; g2.K = 256; g2.Cout = C; g2.scale_dev = w.consts + 1; g2.out = a.p; g2.out_planes = a.planes;
+        CFB_CHECK(bmm_tc(g2, n->sm_count, st));
+      }
+      release_raw(scores); release_raw(pp); release_raw(vt);
+    } else {
+      if (!dry)
+        CFB_CHECK(attention(qkv.p, qkv.p + C, qkv.p + 2 * C, a.p, x.N, 256, 1, C, 3 * C, 3 * C, 3 * C, C,
+                            1.0f / sqrtf((float)C), st));
+    }
     release(qkv);
     ConvOpt op; op.residual = x.p; op.want_stats = true; op.want_planes = out_planes;
     CFB_CHECK(conv(w.proj, a, y, op));
