@@ -23,6 +23,7 @@ import os
 import threading
 from typing import Dict, Optional
 
+import numpy as np
 import torch
 from torch import nn
 
@@ -532,6 +533,107 @@ class CodeFormer(VQAutoEncoder):
         if code_only:
             return logits.clone(), lq.clone()
         return out.clone(), logits.clone(), lq.clone()
+
+    # ---- the caller's plumbing and per-face loop ----------------------------------
+    def forward_u8(self, faces_bgr, w=0.5, adain=True):
+        """``cfb_codeformer_forward_u8``: DEVICE uint8 [B,512,512,3] HWC BGR faces (``face_helper.cropped_faces`` as they
+        are) -> restored faces, same layout and dtype.  Bit-for-bit the reference chain img2tensor(face/255.) ->
+        normalize(.5,.5) -> net(x, w, adain)[0] -> tensor2img(rgb2bgr, min_max=(-1,1)).astype(uint8)
+        (inference_codeformer.py:199-213) with the conversions fused into the first and last conv."""
+        if not torch.is_tensor(faces_bgr) or not faces_bgr.is_cuda or faces_bgr.dtype != torch.uint8:
+            raise RuntimeError('forward_u8 expects a CUDA uint8 tensor')
+        if faces_bgr.dim() != 4 or tuple(faces_bgr.shape[1:]) != (512, 512, 3):
+            raise RuntimeError(f'forward_u8 expects [B,512,512,3] HWC BGR faces, got {tuple(faces_bgr.shape)}')
+        lib = _lib.load()
+        faces_bgr = faces_bgr.contiguous()
+        B, dev = faces_bgr.shape[0], faces_bgr.device
+        w, adain = float(w), bool(adain)
+        with self._cfb_lock, torch.cuda.device(dev):
+            self._cfb_prepare(dev)
+            if B == 0:
+                return torch.empty_like(faces_bgr)
+
+            def launch(src, dst, ws):
+                _lib.check(lib.cfb_codeformer_forward_u8(self._cfb_net, _lib.ptr(src), _lib.ptr(dst), None, None, None, B, w,
+                                                         int(adain), _lib.ptr(ws), ws.numel(), _stream_ptr(dev)),
+                           'cfb_codeformer_forward_u8')
+            graph_ok = B <= self.cuda_graph_max_batch and os.environ.get('CFB_CUDA_GRAPH', '1') != '0' \
+                and not getattr(self, '_cfb_hooks', None) and not torch.cuda.is_current_stream_capturing()
+            if graph_ok:
+                key = ('u8', dev.index, B, w, adain)
+                ent = self._cfb_graphs.get(key)
+                if ent is None:
+                    if len(self._cfb_graphs) >= 8:
+                        self._cfb_graphs.clear()
+                    src, dst = torch.empty_like(faces_bgr), torch.empty_like(faces_bgr)
+                    ws = torch.empty(int(lib.cfb_workspace_bytes(self._cfb_net, B)), dtype=torch.uint8, device=dev)
+                    src.copy_(faces_bgr)
+                    launch(src, dst, ws)                          # eager warm-up before capture
+                    torch.cuda.current_stream(dev).synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    try:
+                        with torch.cuda.graph(g):
+                            launch(src, dst, ws)
+                        ent = (g, src, dst, ws)
+                    except Exception:
+                        ent = False
+                    self._cfb_graphs[key] = ent
+                if ent:
+                    g, src, dst, _ = ent
+                    src.copy_(faces_bgr)
+                    g.replay()
+                    return dst.clone()
+            out = torch.empty_like(faces_bgr)
+            launch(faces_bgr, out, self._cfb_workspace(dev, B))
+        return out
+
+    def restore_faces(self, faces, w=0.5, adain=True, max_batch=32, device=None, on_error='input'):
+        """Batched front-end for the caller loop ``for cropped_face in face_helper.cropped_faces`` of
+        inference_codeformer.py:197-214 (one face per call there).  ``faces``: a list of uint8 [512,512,3] BGR arrays (or one
+        [B,512,512,3] array / CPU uint8 tensor).  Returns the list of restored uint8 BGR faces in order -- what the loop
+        passes to ``face_helper.add_restored_face``.  Faces go through pinned uint8 staging (0.79 MB per face each way)
+        in chunks of ``max_batch``.  ``on_error='input'`` mirrors the reference's fallback (:209-211: on any failure the
+        restored face is the input face); ``'raise'`` re-raises."""
+        if torch.is_tensor(faces):
+            arr = faces.detach().cpu().numpy()
+        elif isinstance(faces, np.ndarray):
+            arr = faces
+        else:
+            faces = list(faces)
+            arr = np.stack(faces) if faces else np.zeros((0, 512, 512, 3), np.uint8)
+        if arr.ndim == 3:
+            arr = arr[None]
+        if arr.dtype != np.uint8 or arr.ndim != 4 or tuple(arr.shape[1:]) != (512, 512, 3):
+            raise RuntimeError(f'restore_faces expects uint8 [512,512,3] BGR faces, got {arr.dtype} {tuple(arr.shape)}')
+        if on_error not in ('input', 'raise'):
+            raise RuntimeError("on_error must be 'input' or 'raise'")
+        dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        max_batch = max(1, int(max_batch))
+        restored = []
+        self.last_restore_errors = []
+        for lo in range(0, arr.shape[0], max_batch):
+            chunk = np.ascontiguousarray(arr[lo:lo + max_batch])
+            B = chunk.shape[0]
+            try:
+                with torch.cuda.device(dev):
+                    key = ('pin', dev.index, B, threading.get_ident())     # staging is per caller thread (app.py:282)
+                    pin = self._cfb_ws.get(key)
+                    if pin is None:
+                        pin = (torch.empty((B, 512, 512, 3), dtype=torch.uint8, pin_memory=True),
+                               torch.empty((B, 512, 512, 3), dtype=torch.uint8, pin_memory=True))
+                        self._cfb_ws[key] = pin
+                    pin[0].copy_(torch.from_numpy(chunk))
+                    out = self.forward_u8(pin[0].to(dev, non_blocking=True), w=w, adain=adain)
+                    pin[1].copy_(out, non_blocking=True)
+                    torch.cuda.current_stream(dev).synchronize()
+                    res = pin[1].numpy().copy()
+            except RuntimeError as err:
+                if on_error == 'raise':
+                    raise
+                self.last_restore_errors.append((lo, str(err)))
+                res = chunk.copy()
+            restored.extend(res[i] for i in range(B))
+        return restored
 
     def forward_host(self, x_host, w=0, adain=False, device=None):
         """End-to-end call with HOST tensors (``cfb_codeformer_forward_host``): pinned x -> H2D -> forward ->

@@ -85,6 +85,14 @@ int conv_first(const float* x_nchw, const float* wgt, const float* bias, float* 
 // last conv: NHWC [N,H,W,Cin] (+ fused affine) -> NCHW [N,3,H,W], 3x3 p1; weight [9][Cin][3]
 int conv_last(const float* in, const float* in_scale, const float* in_shift, const float* wgt, const float* bias,
               float* out_nchw, int N, int H, int W, int Cin, cudaStream_t st);
+// the same two kernels with the caller's image plumbing fused in (inference_codeformer.py:199-206,
+// basicsr/utils/img_util.py:9-35,38-94): uint8 HWC BGR face in, uint8 HWC BGR restored face out
+int conv_first_u8(const unsigned char* x_bgr_hwc, const float* wgt, const float* bias, float* out, int N, int H, int W,
+                  int Cout, cudaStream_t st);
+int conv_last_u8(const float* in, const float* in_scale, const float* in_shift, const float* wgt, const float* bias,
+                 unsigned char* out_bgr_hwc, int N, int H, int W, int Cin, cudaStream_t st);
+int u8_to_input(const unsigned char* img_bgr_hwc, float* x_nchw, int N, int64_t HW, cudaStream_t st);
+int output_to_u8(const float* x_nchw, unsigned char* img_bgr_hwc, int N, int64_t HW, cudaStream_t st);
 
 // weight re-layout: OIHW -> [taps][Cin][Cout]
 int relayout_oihw_to_tck(const float* oihw, float* out, int Cout, int Cin, int k, cudaStream_t st);

@@ -415,6 +415,9 @@ struct Fwd {
   Arena& ar;
   bool dry;
   int engine;   // 0 auto, 1 f32, 2 tc
+  // caller-side image plumbing fused into the first / last conv (cfb_codeformer_forward_u8): uint8 HWC BGR faces
+  const unsigned char* in_u8 = nullptr;
+  unsigned char* out_u8 = nullptr;
 
   int alloc(Tensor& t, int N, int H, int W, int C) {
     t.N = N; t.H = H; t.W = W; t.C = C; t.owned = true; t.gn_part = nullptr; t.gn_slots = 0; t.planes = nullptr;
@@ -614,7 +617,10 @@ struct Fwd {
     const cfb_config& c = n->cfg;
     Tensor x;
     CFB_CHECK(alloc(x, B, c.img_size, c.img_size, c.nf));
-    if (!dry) CFB_CHECK(conv_first(x_nchw, n->enc[0].conv.w_f32, n->enc[0].conv.bias, x.p, B, c.img_size, c.img_size, c.nf, st));
+    if (!dry) {
+      if (in_u8) CFB_CHECK(conv_first_u8(in_u8, n->enc[0].conv.w_f32, n->enc[0].conv.bias, x.p, B, c.img_size, c.img_size, c.nf, st));
+      else CFB_CHECK(conv_first(x_nchw, n->enc[0].conv.w_f32, n->enc[0].conv.bias, x.p, B, c.img_size, c.img_size, c.nf, st));
+    }
     CFB_CHECK(capture("enc.0", x));
     float *ps = nullptr, *ph = nullptr;   // pending GroupNorm of a 'norm' block
     // does the block after i read its input raw through a conv (Down/Upsample conv, or a ResBlock's 1x1 conv_out)?
@@ -669,7 +675,10 @@ struct Fwd {
         case B_NORM: CFB_CHECK(gn(b.norm, x, &ps, &ph)); continue;
         case B_CONV:
           if (i + 1 == n->gen.size()) {
-            if (!dry) CFB_CHECK(conv_last(x.p, ps, ph, b.conv.w_f32, b.conv.bias, out_nchw, x.N, x.H, x.W, x.C, st));
+            if (!dry) {
+              if (out_u8) CFB_CHECK(conv_last_u8(x.p, ps, ph, b.conv.w_f32, b.conv.bias, out_u8, x.N, x.H, x.W, x.C, st));
+              else CFB_CHECK(conv_last(x.p, ps, ph, b.conv.w_f32, b.conv.bias, out_nchw, x.N, x.H, x.W, x.C, st));
+            }
             if (ps) { release_raw(ps); release_raw(ph); ps = ph = nullptr; }
             release(x);
             return 0;
@@ -758,13 +767,15 @@ static std::vector<int> tap_blocks_of(const cfb_config& c, bool encoder) {
 
 static int codeformer_forward_impl(cfb_net* n, const float* x, float* out, float* logits, float* lq_feat,
                                    int64_t* top_idx, int B, float w, int adain, int code_only, void* ws, int64_t ws_bytes,
-                                   cudaStream_t st, bool dry) {
+                                   cudaStream_t st, bool dry, const unsigned char* x_u8 = nullptr,
+                                   unsigned char* out_u8 = nullptr) {
   CFB_REQUIRE(n->cfg.kind == 1, "net was created as VQAutoEncoder");
   CFB_REQUIRE(dry || n->prepared, "cfb_net_prepare has not been called");
   CFB_REQUIRE(B >= 0, "negative batch");
   if (B == 0) return 0;
   n->arena.reset(ws, (size_t)ws_bytes, dry);
   Fwd f{n, st, n->arena, dry, n->engine};
+  f.in_u8 = x_u8; f.out_u8 = out_u8;
   const cfb_config& c = n->cfg;
   std::map<int, Tensor> taps;
   Tensor lq;
@@ -779,7 +790,7 @@ static int codeformer_forward_impl(cfb_net* n, const float* x, float* out, float
     if (top_idx && !dry) CFB_CHECK(argmax_gather(logits_buf, n->codebook, top_idx, nullptr, T, c.codebook_size, c.emb_dim, st));
     return 0;
   }
-  CFB_REQUIRE(out != nullptr, "out must not be NULL unless code_only");
+  CFB_REQUIRE(out != nullptr || out_u8 != nullptr, "out must not be NULL unless code_only");
   // softmax -> topk(1) -> get_codebook_feat  (:257-259)
   Tensor quant;
   CFB_CHECK(f.alloc(quant, B, lq.H, lq.W, c.emb_dim));
@@ -974,6 +985,53 @@ int cfb_codeformer_forward(cfb_net* n, const float* x, float* out, float* logits
                                               workspace_bytes, (cudaStream_t)stream, false);
   n->last_launches = cfb::launch_count() - before;
   return rc;
+  API_END(1)
+}
+
+int cfb_codeformer_forward_u8(cfb_net* n, const uint8_t* faces_bgr, uint8_t* restored_bgr, float* logits, float* lq_feat,
+                              int64_t* top_idx, int32_t batch, float w, int32_t adain, void* workspace,
+                              int64_t workspace_bytes, void* stream) {
+  API_BEGIN
+  CFB_REQUIRE(n, "cfb_codeformer_forward_u8: NULL net");
+  if (batch == 0) return 0;
+  CFB_REQUIRE(faces_bgr && restored_bgr, "cfb_codeformer_forward_u8: NULL image pointer");
+  std::lock_guard<std::mutex> lk(n->mu);
+  const int64_t before = cfb::launch_count();
+  const int rc = cfb::codeformer_forward_impl(n, nullptr, nullptr, logits, lq_feat, top_idx, batch, w, adain, 0, workspace,
+                                              workspace_bytes, (cudaStream_t)stream, false, faces_bgr, restored_bgr);
+  n->last_launches = cfb::launch_count() - before;
+  return rc;
+  API_END(1)
+}
+
+int cfb_codeformer_restore_host(cfb_net* n, const uint8_t* faces_host, uint8_t* restored_host, int32_t batch, float w,
+                                int32_t adain, void* dev_scratch, int64_t dev_scratch_bytes, void* workspace,
+                                int64_t workspace_bytes, void* stream) {
+  API_BEGIN
+  CFB_REQUIRE(n && faces_host && restored_host && dev_scratch, "cfb_codeformer_restore_host: NULL argument");
+  CFB_REQUIRE(dev_scratch_bytes >= cfb_host_io_bytes(n, batch), "dev_scratch too small (cfb_host_io_bytes)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t img = (size_t)batch * 3 * n->cfg.img_size * n->cfg.img_size;
+  uint8_t* din = (uint8_t*)dev_scratch;
+  uint8_t* dout = din + (img + 1023) / 1024 * 1024;
+  CFB_CUDA(cudaMemcpyAsync(din, faces_host, img, cudaMemcpyHostToDevice, st));
+  CFB_CHECK(cfb_codeformer_forward_u8(n, din, dout, nullptr, nullptr, nullptr, batch, w, adain, workspace, workspace_bytes, stream));
+  CFB_CUDA(cudaMemcpyAsync(restored_host, dout, img, cudaMemcpyDeviceToHost, st));
+  CFB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+  API_END(1)
+}
+
+int cfb_u8_to_input(const uint8_t* img_bgr_hwc, float* x_nchw, int32_t n, int32_t hw, void* stream) {
+  API_BEGIN
+  CFB_REQUIRE((img_bgr_hwc && x_nchw) || n == 0, "cfb_u8_to_input: NULL argument");
+  return cfb::u8_to_input(img_bgr_hwc, x_nchw, n, hw, (cudaStream_t)stream);
+  API_END(1)
+}
+int cfb_output_to_u8(const float* x_nchw, uint8_t* img_bgr_hwc, int32_t n, int32_t hw, void* stream) {
+  API_BEGIN
+  CFB_REQUIRE((img_bgr_hwc && x_nchw) || n == 0, "cfb_output_to_u8: NULL argument");
+  return cfb::output_to_u8(x_nchw, img_bgr_hwc, n, hw, (cudaStream_t)stream);
   API_END(1)
 }
 

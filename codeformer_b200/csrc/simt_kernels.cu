@@ -222,12 +222,28 @@ int conv_f32(const ConvArgs& a, cudaStream_t st) {
 // =====================================================================================================
 // Thread = 4 horizontally adjacent pixels x COUT/4 channels (4 threads cover a pixel quad): every input value and every
 // weight read feeds 4 pixels; 16-byte coalesced NHWC stores.
-template <int COUT>
+// The caller's image plumbing, bit for bit (inference_codeformer.py:199-200 + basicsr/utils/img_util.py:22-29):
+//   t = float32(u8 / 255.)  [numpy float64 division, then astype float32];  x = (t - 0.5) / 0.5  [torchvision normalize, fp32]
+__device__ __forceinline__ float u8_to_model_input(int u) {
+  const float t = (float)((double)u / 255.0);
+  return __fdiv_rn(__fsub_rn(t, 0.5f), 0.5f);
+}
+// and back (basicsr/utils/img_util.py:66-67,87-90 with min_max=(-1,1)): clamp, (x+1)/2, *255 in fp32, round half to even
+__device__ __forceinline__ unsigned model_output_to_u8(float v) {
+  float t = fminf(fmaxf(v, -1.f), 1.f);
+  t = __fdiv_rn(__fadd_rn(t, 1.f), 2.f);
+  return (unsigned)rintf(__fmul_rn(t, 255.f));
+}
+
+// U8 = true: x is the caller's uint8 HWC BGR face [N][H][W][3]; the normalisation above is a 256-entry table.
+template <int COUT, bool U8>
 __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ x, const float* __restrict__ wgt,
                                                          const float* __restrict__ bias, float* __restrict__ out,
                                                          int N, int H, int W) {
   __shared__ __align__(16) float ws[27 * COUT];
   __shared__ float bs[COUT];
+  __shared__ float lut[U8 ? 256 : 1];
+  if constexpr (U8) lut[threadIdx.x] = u8_to_model_input(threadIdx.x);
   for (int i = threadIdx.x; i < 27 * COUT; i += 256) ws[i] = wgt[i];
   for (int i = threadIdx.x; i < COUT; i += 256) bs[i] = bias ? bias[i] : 0.f;
   __syncthreads();
@@ -252,11 +268,20 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       float v[6];
-      const float* rp = x + ((int64_t)n * 3 + c) * HW + (int64_t)iy * W;
+      if constexpr (U8) {
+        const unsigned char* rp8 = reinterpret_cast<const unsigned char*>(x) + ((int64_t)n * HW + (int64_t)iy * W) * 3 + (2 - c);
 #pragma unroll
-      for (int q = 0; q < 6; ++q) {
-        const int ix = x0 + q - 1;
-        v[q] = (rowok && ix >= 0 && ix < W) ? __ldg(rp + ix) : 0.f;
+        for (int q = 0; q < 6; ++q) {
+          const int ix = x0 + q - 1;
+          v[q] = (rowok && ix >= 0 && ix < W) ? lut[__ldg(rp8 + ix * 3)] : 0.f;
+        }
+      } else {
+        const float* rp = x + ((int64_t)n * 3 + c) * HW + (int64_t)iy * W;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          const int ix = x0 + q - 1;
+          v[q] = (rowok && ix >= 0 && ix < W) ? __ldg(rp + ix) : 0.f;
+        }
       }
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
@@ -287,12 +312,24 @@ int conv_first(const float* x, const float* wgt, const float* bias, float* out, 
   CFB_REQUIRE(W % 4 == 0, "conv_first: W must be a multiple of 4");
   const int64_t quads = (int64_t)N * H * W / 4;
   if (quads == 0) return 0;
-  conv_first_kernel<64><<<(unsigned)((quads + 63) / 64), 256, 0, st>>>(x, wgt, bias, out, N, H, W);
+  conv_first_kernel<64, false><<<(unsigned)((quads + 63) / 64), 256, 0, st>>>(x, wgt, bias, out, N, H, W);
+  CFB_LAUNCH_CHECK();
+  return 0;
+}
+int conv_first_u8(const unsigned char* x_bgr_hwc, const float* wgt, const float* bias, float* out, int N, int H, int W,
+                  int Cout, cudaStream_t st) {
+  CFB_REQUIRE(Cout == 64, "conv_first: only nf=64 is built");
+  CFB_REQUIRE(W % 4 == 0, "conv_first: W must be a multiple of 4");
+  const int64_t quads = (int64_t)N * H * W / 4;
+  if (quads == 0) return 0;
+  conv_first_kernel<64, true><<<(unsigned)((quads + 63) / 64), 256, 0, st>>>(reinterpret_cast<const float*>(x_bgr_hwc), wgt,
+                                                                             bias, out, N, H, W);
   CFB_LAUNCH_CHECK();
   return 0;
 }
 
 // 4 horizontally adjacent output pixels per thread: every weight read from shared memory feeds 4 pixels.
+template <bool U8>
 __global__ void __launch_bounds__(256) conv_last_kernel(const float* __restrict__ in, const float* __restrict__ in_scale,
                                                         const float* __restrict__ in_shift, const float* __restrict__ wgt,
                                                         const float* __restrict__ bias, float* __restrict__ out, int N,
@@ -352,10 +389,22 @@ __global__ void __launch_bounds__(256) conv_last_kernel(const float* __restrict_
       }
     }
   }
-  float* o = out + (int64_t)n * 3 * HW + rem;
+  if constexpr (U8) {
+    // uint8 HWC BGR: 4 pixels = 12 contiguous bytes
+    unsigned b[12];
 #pragma unroll
-  for (int k = 0; k < 3; ++k)
-    *reinterpret_cast<float4*>(o + k * HW) = make_float4(acc[0][k], acc[1][k], acc[2][k], acc[3][k]);
+    for (int p = 0; p < 4; ++p) {
+      b[p * 3 + 0] = model_output_to_u8(acc[p][2]); b[p * 3 + 1] = model_output_to_u8(acc[p][1]); b[p * 3 + 2] = model_output_to_u8(acc[p][0]);
+    }
+    unsigned* o8 = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(out) + ((int64_t)n * HW + rem) * 3);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o8[k] = b[k * 4] | (b[k * 4 + 1] << 8) | (b[k * 4 + 2] << 16) | (b[k * 4 + 3] << 24);
+  } else {
+    float* o = out + (int64_t)n * 3 * HW + rem;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      *reinterpret_cast<float4*>(o + k * HW) = make_float4(acc[0][k], acc[1][k], acc[2][k], acc[3][k]);
+  }
 }
 
 int conv_last(const float* in, const float* in_scale, const float* in_shift, const float* wgt, const float* bias,
@@ -365,7 +414,53 @@ int conv_last(const float* in, const float* in_scale, const float* in_shift, con
   if (N == 0) return 0;
   const size_t smem = (size_t)(9 * Cin * 4 + 2 * Cin) * sizeof(float);
   CFB_REQUIRE(smem <= 48 * 1024, "conv_last: Cin too large");
-  conv_last_kernel<<<(unsigned)(N * HW / 1024), 256, smem, st>>>(in, in_scale, in_shift, wgt, bias, out, N, H, W, Cin);
+  conv_last_kernel<false><<<(unsigned)(N * HW / 1024), 256, smem, st>>>(in, in_scale, in_shift, wgt, bias, out, N, H, W, Cin);
+  CFB_LAUNCH_CHECK();
+  return 0;
+}
+int conv_last_u8(const float* in, const float* in_scale, const float* in_shift, const float* wgt, const float* bias,
+                 unsigned char* out_bgr_hwc, int N, int H, int W, int Cin, cudaStream_t st) {
+  const int64_t HW = (int64_t)H * W;
+  CFB_REQUIRE(HW % 1024 == 0 && W % 4 == 0 && Cin % 4 == 0, "conv_last: H*W must be a multiple of 1024, W and Cin of 4");
+  if (N == 0) return 0;
+  const size_t smem = (size_t)(9 * Cin * 4 + 2 * Cin) * sizeof(float);
+  CFB_REQUIRE(smem <= 48 * 1024, "conv_last: Cin too large");
+  conv_last_kernel<true><<<(unsigned)(N * HW / 1024), 256, smem, st>>>(in, in_scale, in_shift, wgt, bias,
+                                                                        reinterpret_cast<float*>(out_bgr_hwc), N, H, W, Cin);
+  CFB_LAUNCH_CHECK();
+  return 0;
+}
+
+// stand-alone plumbing (unit parity + callers that want the fp32 tensor): uint8 HWC BGR <-> fp32 NCHW RGB in [-1,1]
+__global__ void u8_to_input_kernel(const unsigned char* __restrict__ img, float* __restrict__ x, int64_t HW, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / (3 * HW);
+    const int64_t r = i - n * 3 * HW;
+    const int c = (int)(r / HW);
+    const int64_t px = r - (int64_t)c * HW;
+    x[i] = u8_to_model_input(img[(n * HW + px) * 3 + (2 - c)]);
+  }
+}
+__global__ void output_to_u8_kernel(const float* __restrict__ x, unsigned char* __restrict__ img, int64_t HW, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / (3 * HW);
+    const int64_t r = i - n * 3 * HW;
+    const int64_t px = r / 3;
+    const int k = (int)(r - px * 3);
+    img[i] = (unsigned char)model_output_to_u8(x[(n * 3 + (2 - k)) * HW + px]);
+  }
+}
+int u8_to_input(const unsigned char* img_bgr_hwc, float* x_nchw, int N, int64_t HW, cudaStream_t st) {
+  const int64_t total = (int64_t)N * 3 * HW;
+  if (total == 0) return 0;
+  u8_to_input_kernel<<<(unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256), 256, 0, st>>>(img_bgr_hwc, x_nchw, HW, total);
+  CFB_LAUNCH_CHECK();
+  return 0;
+}
+int output_to_u8(const float* x_nchw, unsigned char* img_bgr_hwc, int N, int64_t HW, cudaStream_t st) {
+  const int64_t total = (int64_t)N * 3 * HW;
+  if (total == 0) return 0;
+  output_to_u8_kernel<<<(unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256), 256, 0, st>>>(x_nchw, img_bgr_hwc, HW, total);
   CFB_LAUNCH_CHECK();
   return 0;
 }

@@ -95,6 +95,22 @@ int cfb_codeformer_forward_host(cfb_net* net, const float* x_host, float* out_ho
                                 void* dev_scratch, int64_t dev_scratch_bytes,
                                 void* workspace, int64_t workspace_bytes, void* stream);
 
+/* f1: the forward with the caller's image plumbing fused into the first and last conv.
+ * faces_bgr / restored_bgr: DEVICE uint8 [batch,512,512,3] HWC BGR, i.e. face_helper.cropped_faces as they are
+ * (inference_codeformer.py:197).  Replaces img2tensor(face/255.) + normalize(0.5,0.5) -> net(x,w,adain)[0] ->
+ * tensor2img(rgb2bgr, min_max=(-1,1)).astype(uint8)   (inference_codeformer.py:199-213, basicsr/utils/img_util.py:9-35,38-94)
+ * with the same fp32 arithmetic and rounding (round-half-even).  logits / lq_feat / top_idx are optional. */
+int cfb_codeformer_forward_u8(cfb_net* net, const uint8_t* faces_bgr, uint8_t* restored_bgr, float* logits, float* lq_feat,
+                              int64_t* top_idx, int32_t batch, float w, int32_t adain,
+                              void* workspace, int64_t workspace_bytes, void* stream);
+/* the same with HOST uint8 buffers (0.79 MB per face each way instead of 3.1 MB): H2D, forward, D2H, stream sync.
+ * dev_scratch >= cfb_host_io_bytes(net, batch). */
+int cfb_codeformer_restore_host(cfb_net* net, const uint8_t* faces_host, uint8_t* restored_host, int32_t batch, float w,
+                                int32_t adain, void* dev_scratch, int64_t dev_scratch_bytes,
+                                void* workspace, int64_t workspace_bytes, void* stream);
+/* the plumbing alone (unit parity): uint8 HWC BGR [n,hw,3] <-> fp32 NCHW RGB [n,3,hw] in [-1,1] */
+int cfb_u8_to_input(const uint8_t* img_bgr_hwc, float* x_nchw, int32_t n, int32_t hw, void* stream);
+int cfb_output_to_u8(const float* x_nchw, uint8_t* img_bgr_hwc, int32_t n, int32_t hw, void* stream);
 /* ---- VQAutoEncoder.forward (vqgan_arch.py:385-389) ----
  * out [B,3,512,512]; idx [B*256] int64; stats[4] = {codebook_loss, perplexity, mean_distance, 0};
  * min_encodings [B*256,K] one-hot fp32 or NULL (materialised only when asked). */

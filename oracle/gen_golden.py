@@ -13,6 +13,10 @@ Files
                             `out` kept at stride 4 to stay small, logits argmax + lq_feat full
   vqae.npz                  face 0, VQAutoEncoder.forward: out (stride 4), indices, loss, perplexity, mean_distance
   vq_micro.npz              VectorQuantizer.forward on the config-3 inputs (seeded), indices + z_q samples + stats
+  plumbing.npz              the caller's image plumbing (section 8 f1): img2tensor(face/255.)+normalize and
+                            tensor2img(min_max=(-1,1)).astype(uint8) of the reference on a u8 face that holds every byte
+                            value in every channel and on an fp32 tensor that holds every rounding half-way point
+                            (`python oracle/gen_golden.py plumbing` regenerates only this file)
 """
 import os
 import sys
@@ -56,7 +60,31 @@ def vq_micro_inputs(case):
     return E, z
 
 
+def gen_plumbing():
+    ref_shim.load()
+    from basicsr.utils import img2tensor, tensor2img                      # basicsr/utils/img_util.py:9,38
+    from torchvision.transforms.functional import normalize               # inference_codeformer.py:7
+    rng = np.random.default_rng(7)
+    face = rng.integers(0, 256, (64, 64, 3), dtype=np.uint8)              # BGR, as face_helper.cropped_faces
+    ramp = np.arange(256, dtype=np.uint8).reshape(16, 16)
+    face[:16, :16, 0], face[:16, :16, 1], face[:16, :16, 2] = ramp, ramp[::-1], ramp.T
+    t = img2tensor(face / 255., bgr2rgb=True, float32=True)               # inference_codeformer.py:199
+    normalize(t, (0.5, 0.5, 0.5), (0.5, 0.5, 0.5), inplace=True)          # :200
+    out = (rng.standard_normal((1, 3, 64, 64)) * 0.7).astype(np.float32)  # some values beyond +-1: exercises the clamp
+    k = np.arange(0, 255)
+    half = ((k + 0.5) / 255 * 2 - 1).astype(np.float32)                   # (v+1)/2*255 = k + 0.5
+    out.reshape(-1)[:255] = half
+    out.reshape(-1)[255:510] = np.nextafter(half, np.float32(2))
+    out.reshape(-1)[510:765] = np.nextafter(half, np.float32(-2))
+    restored = tensor2img(torch.from_numpy(out.copy()), rgb2bgr=True, min_max=(-1, 1)).astype('uint8')   # :206,213
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, 'plumbing.npz'), face_bgr=face, x=t.numpy(), out=out, restored_bgr=restored)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == 'plumbing':
+        gen_plumbing()
+        return
     torch.set_num_threads(os.cpu_count())
     CodeFormer, VQAE, VQ, _ = ref_shim.load()
     os.makedirs(OUT, exist_ok=True)
@@ -108,6 +136,7 @@ def main():
                         f'{case}_perplexity': st['perplexity'].numpy(), f'{case}_mean_distance': st['mean_distance'].numpy(),
                         f'{case}_zq_b0': zq[0].numpy()})
         np.savez_compressed(os.path.join(OUT, 'vq_micro.npz'), **mic)
+    gen_plumbing()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, 'KiB')
 

@@ -82,3 +82,30 @@ def test_oracle_equals_live_reference_small():
     t = torch.randn(256, 2, 512)
     pos = torch.randn(256, 2, 512) * 0.02
     assert maxabs(layer(t, query_pos=pos), O.transformer_layer(sd, 'L', t, pos, 8)) < 5e-6
+
+
+def test_plumbing_matches_reference_golden():
+    """img2tensor+normalize and tensor2img of the reference, bit for bit (tests/golden/plumbing.npz)."""
+    from oracle import plumbing_oracle as P
+    g = golden('plumbing.npz')
+    assert sorted(np.unique(g['face_bgr'])) == list(range(256))            # every byte value is exercised
+    assert np.array_equal(P.face_to_input(g['face_bgr'][None])[0], g['x'])
+    assert np.array_equal(P.output_to_face(g['out'])[0], g['restored_bgr'])
+    # round trip of the fallback path (inference_codeformer.py:209-211): plumbing back and forth is the identity on u8
+    assert np.array_equal(P.output_to_face(P.face_to_input(g['face_bgr'][None])), g['face_bgr'][None])
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason='/root/reference not present (GPU box)')
+def test_plumbing_equals_live_reference():
+    from oracle import plumbing_oracle as P
+    ref_shim.load()
+    from basicsr.utils import img2tensor, tensor2img
+    from torchvision.transforms.functional import normalize
+    rng = np.random.default_rng(11)
+    face = rng.integers(0, 256, (32, 48, 3), dtype=np.uint8)
+    t = img2tensor(face / 255., bgr2rgb=True, float32=True)
+    normalize(t, (0.5, 0.5, 0.5), (0.5, 0.5, 0.5), inplace=True)
+    assert np.array_equal(t.numpy(), P.face_to_input(face[None])[0])
+    out = torch.from_numpy((rng.standard_normal((1, 3, 32, 48)) * 0.8).astype(np.float32))
+    r = tensor2img(out.clone(), rgb2bgr=True, min_max=(-1, 1)).astype('uint8')
+    assert np.array_equal(r, P.output_to_face(out.numpy())[0])
