@@ -56,6 +56,7 @@ SIGNATURES = {
     'cfb_layer_norm': (c_int, [_P, _P, _P, _P, _P, _P, c_int32, c_int32, c_int32, _P]),
     'cfb_adain_nhwc': (c_int, [_P, _P, _P, c_int32, c_int32, c_int32, _P]),
     'cfb_debug_umma_probe': (c_int, [_P, c_int32, _P, _P, c_int32, _P, _P]),
+    'cfb_debug_umma_pair': (c_int, [c_int32, c_int32, _P, _P, c_int32, _P]),
     'cfb_debug_umma_rate': (c_int, [c_int32, c_int32, c_int32, _P, c_int32, _P]),
     'cfb_debug_time_conv': (c_int, [_P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P, c_int64,
                                    _P, POINTER(c_float)]),

@@ -1174,4 +1174,111 @@ int umma_rate(int N, int nacc, int reps, long long* out_dev, int ctas, cudaStrea
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Diagnostics: CTA-pair MMA (tcgen05.mma.cta_group::2, M = 256 over two SMs of a TPC).  Each CTA holds its own 128 A
+// rows and HALF of the B rows; the leader issues, the commit is multicast to both CTAs.  Checks which accumulator
+// columns the two B halves land in and measures the sustained rate (tools/umma_pair.py).
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                  uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum)
+      : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+    umma_pair_kernel(int N, int reps, float* __restrict__ vals, long long* __restrict__ info) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // A: 128 rows x 64 fp16 (16 KB); B: N/2 rows x 64 fp16 (<= 16 KB)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * 16384);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  // A = rank + 1 everywhere; B half of this CTA = 1.0 (rank 0) / 2.0 (rank 1): D[row, col] = K * (rank_of_row + 1) * b(col)
+  const uint32_t av = rank == 0 ? 0x3c003c00u : 0x40004000u;   // fp16 1.0 / 2.0
+  const uint32_t bv = rank == 0 ? 0x3c003c00u : 0x40004000u;
+  for (int i = threadIdx.x; i < 16384 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = av;
+  for (int i = threadIdx.x; i < 16384 / 4; i += 128) reinterpret_cast<uint32_t*>(smem + 16384)[i] = bv;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  cluster_sync_all();          // both CTAs: operands written, TMEM allocated, barriers initialised
+  long long cyc = 0;
+  if (warp == 0) {
+    const long long t0 = clock64();
+    if (rank == 0) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const uint32_t a0 = desc_lo(smem_u32(smem)), b0 = desc_lo(smem_u32(smem + 16384));
+      if (elect_one()) {
+        for (int r = 0; r < reps; ++r) {
+#pragma unroll 1
+          for (int i = 0; i < 4; ++i)
+            tc_mma_f16_pair_w(tmem_base, a0 + 2 * i, DESC_HI_SW128, b0 + 2 * i, DESC_HI_SW128, idesc, (r | i) ? 1u : 0u);
+        }
+        tc_commit_pair(smem_u32(bar), (uint16_t)3);
+      }
+      __syncwarp();
+    }
+    mbar_wait(smem_u32(bar), 0);
+    cyc = clock64() - t0;
+  }
+  __syncthreads();
+  tc_fence_after();
+  {
+    // every warp reads its 32 TMEM lanes; lane 0 of warp 0 / warp 3 reports four probe columns
+    uint32_t r0[32], r1[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16), r0);
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(N - 32), r1);
+    tmem_ld_wait();
+    if ((threadIdx.x & 31) == 0 && (warp == 0 || warp == 3)) {
+      float* o = vals + ((pair * 2 + rank) * 2 + (warp == 3)) * 4;
+      o[0] = __uint_as_float(r0[0]); o[1] = __uint_as_float(r0[31]); o[2] = __uint_as_float(r1[0]); o[3] = __uint_as_float(r1[31]);
+    }
+  }
+  if (threadIdx.x == 0) { info[(pair * 2 + rank) * 2] = cyc; info[(pair * 2 + rank) * 2 + 1] = (long long)tmem_base; }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+}
+
+int umma_pair(int N, int reps, float* vals_dev, long long* info_dev, int ctas, cudaStream_t st) {
+  CFB_REQUIRE((N == 64 || N == 128 || N == 256) && reps >= 1 && ctas >= 2 && ctas % 2 == 0, "umma_pair: bad configuration");
+  const int smem = 2 * 16384 + 1024 + 64;
+  static bool done = false;
+  if (!done) { CFB_CUDA(cudaFuncSetAttribute(umma_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); done = true; }
+  umma_pair_kernel<<<ctas, 128, smem, st>>>(N, reps, vals_dev, info_dev);
+  CFB_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace cfb

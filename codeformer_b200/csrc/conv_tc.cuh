@@ -30,5 +30,6 @@ int softmax256_planes(const float* scores, void* planes, int64_t rows, cudaStrea
 int transpose_planes(const void* in_planes, int N, int pitch, int c0, int C, void* out_planes, cudaStream_t st);
 // diagnostics (tools/umma_probe.py): row-shifted SWIZZLE_128B descriptor views
 int umma_probe(const void* a_f16, int rowsA, const void* b_f16, const int* cfg_dev, int ncfg, float* out, cudaStream_t st);
+int umma_pair(int N, int reps, float* vals_dev, long long* info_dev, int ctas, cudaStream_t st);
 int umma_rate(int N, int nacc, int reps, long long* out_dev, int ctas, cudaStream_t st);
 }  // namespace cfb

@@ -1230,6 +1230,12 @@ int cfb_debug_umma_rate(int32_t n, int32_t nacc, int32_t reps, int64_t* out_dev,
   API_END(1)
 }
 
+int cfb_debug_umma_pair(int32_t n, int32_t reps, float* vals_dev, int64_t* info_dev, int32_t ctas, void* stream) {
+  API_BEGIN
+  return cfb::umma_pair(n, reps, vals_dev, (long long*)info_dev, ctas, (cudaStream_t)stream);
+  API_END(1)
+}
+
 int cfb_debug_time_conv(const float* in, const float* weight_oihw, float* out, int32_t n, int32_t h, int32_t w, int32_t cin,
                         int32_t cout, int32_t ksize, int32_t mode, int32_t reps, void* workspace, int64_t workspace_bytes,
                         void* stream, float* ms_per_launch) {

@@ -167,6 +167,8 @@ int cfb_debug_umma_probe(const void* a_f16, int32_t rows_a, const void* b_f16, c
                          float* out, void* stream);
 /* diagnostics: sustained tcgen05.mma issue rate; out_dev[ctas] receives the cycles for reps*12 MMAs of 128 x n x 16
  * rotating over `nacc` TMEM accumulators (tools/umma_rate.py) */
+/* CTA-pair probe (tcgen05.mma.cta_group::2): vals [ctas][2][4] accumulator samples, info [ctas][2] = cycles, tmem base */
+int cfb_debug_umma_pair(int32_t n, int32_t reps, float* vals_dev, int64_t* info_dev, int32_t ctas, void* stream);
 int cfb_debug_umma_rate(int32_t n, int32_t nacc, int32_t reps, int64_t* out_dev, int32_t ctas, void* stream);
 /* diagnostics / bench: average device time (CUDA events on `stream`) of the tcgen05 conv KERNEL alone -- weights split
  * and operand planes prepared once outside the timed region -- over `reps` launches (bench.py roofline). */
