@@ -293,6 +293,72 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                  uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum)
+      : "memory");
+}
+
+
+// ---- CTA-pair (cta_group::2) plumbing ----
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {      // shared::cta -> shared::cluster of `rank`
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// wait on a LOCAL barrier whose arrivals may come from the peer CTA (cluster-scope acquire)
+__device__ __forceinline__ void mbar_wait_cl(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+// TMA loads of a CTA pair: data lands in the issuing CTA's shared memory, the byte count is signalled on `cluster_bar`,
+// which may live in the peer (leader) CTA
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------
@@ -341,6 +407,14 @@ struct TcCfg {
   static constexpr int TMEM_COLS = 512;
   static constexpr int STG_BYTES = 8 * 4096;               // per-epilogue-warp 32x32-float transpose patches
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + STG_BYTES;
+  // CTA-pair engine (cta_group::2, M = 256 over the two SMs of a TPC): each CTA stages its own A tile (hi, lo) and HALF of
+  // every B operand: X = its half of [B_hi;B_lo] (rank 0: B_hi, rank 1: B_lo -> accumulator columns [0,BN) | [BN,2BN)) and
+  // Y = its half of B_hi for the A_lo x B_hi pass (rank r: rows [r*BN/2, +BN/2))
+  static constexpr int P_BX_BYTES = BN * 128;
+  static constexpr int P_BY_BYTES = BN * 64;
+  static constexpr int P_STAGE_BYTES = 2 * TC_A_BYTES + P_BX_BYTES + P_BY_BYTES;
+  static constexpr int P_STAGES = (BN == 64) ? 4 : 3;
+  static constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + 1024 + 256 + STG_BYTES;
   // halo engine: 16x8-pixel tiles; the (16+2)x(8+2) input patch of one 64-channel block is fetched ONCE (hi and lo
   // planes) and all 9 taps read it through row-shifted UMMA descriptors; weights stream through their own ring.
   static constexpr int H_A_PLANE = 23 * 1024;              // >= 18*10*128 B, 1024-aligned
@@ -349,6 +423,10 @@ struct TcCfg {
   static constexpr int H_B_SLOT = 2 * B_BYTES;
   static constexpr int H_B_SLOTS = (BN == 64) ? 6 : 3;
   static constexpr int H_SMEM_BYTES = H_A_SLOTS * H_A_SLOT + H_B_SLOTS * H_B_SLOT + 1024 + 256 + STG_BYTES;
+  // halo engine in CTA-pair mode: B slots hold this CTA's halves (X | Y, see above)
+  static constexpr int HP_B_SLOT = P_BX_BYTES + P_BY_BYTES;
+  static constexpr int HP_B_SLOTS = (BN == 64) ? 8 : 4;
+  static constexpr int HP_SMEM_BYTES = H_A_SLOTS * H_A_SLOT + HP_B_SLOTS * HP_B_SLOT + 1024 + 256 + STG_BYTES;
 };
 
 // Accumulation scheme (why the TMEM ring): tcgen05.mma adds into its fp32 accumulator with truncation, so a long
@@ -357,19 +435,30 @@ struct TcCfg {
 // cross terms (lo*hi, hi*lo) are issued first while the slot is still tiny, and the epilogue warps fold every
 // finished slot into fp32 registers with round-to-nearest adds while the tensor core fills the next slot.
 // CPG > 0: the epilogue also emits GroupNorm(32) partial sums of the stored tile (CPG = Cout/32 channels per group).
-template <int BN, int CPG, bool HALO>
+// PAIR: two CTAs of a cluster (one TPC) work on two adjacent m-tiles with shared weights through tcgen05.mma.cta_group::2
+// (M = 256): no single-CTA instruction floor (profiles/round1_umma_pair_probe.txt: N=128 at 100 % of the tensor rate vs
+// 60 %) and each SM stages / reads only half of every B operand.  Rank 0 (leader) issues all MMAs; its `full` and `cempty`
+// barriers collect the TMA bytes / epilogue arrivals of both CTAs; `empty` and `cfull` are signalled in both CTAs by
+// multicast commits.
+template <int BN, int CPG, bool HALO, bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const TcParams p) {
+               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+               const __grid_constant__ CUtensorMap tmB_half, const TcParams p) {
   using Cfg = TcCfg<BN>;
-  constexpr int STAGES = Cfg::STAGES;
+  constexpr int STAGES = PAIR ? Cfg::P_STAGES : Cfg::STAGES;
+  constexpr int STAGE_BYTES = PAIR ? Cfg::P_STAGE_BYTES : Cfg::STAGE_BYTES;
   constexpr int TC_SLOTS = Cfg::SLOTS;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int first_tile = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   // ring "full/empty": per-tap engine = STAGES k-block stages; halo engine = weight (B) slots.  "afull/aempty": halo A slots.
-  constexpr int NRING = HALO ? Cfg::H_B_SLOTS : STAGES;
+  constexpr int NRING = HALO ? (PAIR ? Cfg::HP_B_SLOTS : Cfg::H_B_SLOTS) : STAGES;
+  constexpr int RING_BYTES = HALO ? (PAIR ? Cfg::HP_B_SLOT : Cfg::H_B_SLOT) : STAGE_BYTES;
   uint8_t* ring_base = HALO ? smem + Cfg::H_A_SLOTS * Cfg::H_A_SLOT : smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_base + NRING * (HALO ? Cfg::H_B_SLOT : Cfg::STAGE_BYTES));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring_base + NRING * RING_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + NRING;
   uint64_t* cfull = bars + 2 * NRING;
@@ -389,22 +478,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_hi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_lo) : "memory");
     for (int s = 0; s < NRING; ++s) { mbar_init(smem_u32(full + s), 1); mbar_init(smem_u32(empty + s), 1); }
-    for (int a = 0; a < TC_SLOTS; ++a) { mbar_init(smem_u32(cfull + a), 1); mbar_init(smem_u32(cempty + a), TC_EPI_WARPS); }
+    for (int a = 0; a < TC_SLOTS; ++a) {
+      mbar_init(smem_u32(cfull + a), 1);
+      mbar_init(smem_u32(cempty + a), PAIR ? 2 * TC_EPI_WARPS : TC_EPI_WARPS);   // pair: the epilogue warps of both CTAs
+    }
+    if constexpr (PAIR) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_half) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)Cfg::TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)Cfg::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)Cfg::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();      // both CTAs: barriers initialised, TMEM allocated
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  // pair mode enumerates PAIRS of m-tiles: pm -> m-tiles (2pm, 2pm+1); Upsample keeps both CTAs on the same output
+  // parity (shared weights): pm -> parity pm&3 of low-res tiles 2(pm>>2), 2(pm>>2)+1
+  const int total_tiles = PAIR ? (p.m_tiles >> 1) * p.n_tiles : p.m_tiles * p.n_tiles;
   const int nk = p.taps * p.kblocks;
+  auto mtile_of = [&](int pm) -> int {
+    if constexpr (PAIR) return p.up4 ? (((((pm >> 2) << 1) + (int)rank) << 2) | (pm & 3)) : (pm * 2 + (int)rank);
+    else return pm;
+  };
 
   if (warp == 0) {
     // ============================ TMA producer (warp converged, one elected lane issues) ============================
@@ -413,8 +520,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       uint32_t phase = 0;
       int aslot = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      const uint32_t rank0 = 0u;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+        const int pm = tile / p.n_tiles, nt = tile - pm * p.n_tiles;
+        const int mt = mtile_of(pm);
         const int mtl = p.up4 ? (mt >> 2) : mt;            // low-res tile; (mt & 3) = output parity (py,px)
         const int par_y = p.up4 ? ((mt & 3) >> 1) : 0, par_x = p.up4 ? (mt & 1) : 0;
         const int per_img = p.tiles_x * p.tiles_y;
@@ -426,22 +535,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(smem_u32(aempty + aslot), aphase ^ 1);
             if (elect_one()) {
-              const uint32_t ab = smem_u32(afull + aslot);
-              mbar_expect_tx(ab, (uint32_t)(2 * p.PW * p.PH * 128));
               const uint32_t sa = smem_u32(smem + aslot * Cfg::H_A_SLOT);
-              tma_load_4d(sa, &tmA_hi, ab, kb * 64, x0 - p.pad, y0 - p.pad, n);
-              tma_load_4d(sa + Cfg::H_A_PLANE, &tmA_lo, ab, kb * 64, x0 - p.pad, y0 - p.pad, n);
+              if constexpr (PAIR) {
+                if (rank == 0) mbar_expect_tx(smem_u32(afull + aslot), (uint32_t)(4 * p.PW * p.PH * 128));   // both CTAs' patches
+                const uint32_t ab = map_to_cta(smem_u32(afull + aslot), rank0);
+                tma_load_4d_pair(sa, &tmA_hi, ab, kb * 64, x0 - p.pad, y0 - p.pad, n);
+                tma_load_4d_pair(sa + Cfg::H_A_PLANE, &tmA_lo, ab, kb * 64, x0 - p.pad, y0 - p.pad, n);
+              } else {
+                const uint32_t ab = smem_u32(afull + aslot);
+                mbar_expect_tx(ab, (uint32_t)(2 * p.PW * p.PH * 128));
+                tma_load_4d(sa, &tmA_hi, ab, kb * 64, x0 - p.pad, y0 - p.pad, n);
+                tma_load_4d(sa + Cfg::H_A_PLANE, &tmA_lo, ab, kb * 64, x0 - p.pad, y0 - p.pad, n);
+              }
             }
             __syncwarp();
             if (++aslot == Cfg::H_A_SLOTS) { aslot = 0; aphase ^= 1; }
             for (int tap = 0; tap < p.taps; ++tap) {
+              const int btap = p.up4 ? (mt & 3) * 4 + tap : tap;      // Upsample: weight slice of this output parity
               mbar_wait(smem_u32(empty + stage), phase ^ 1);
               if (elect_one()) {
-                const uint32_t fb = smem_u32(full + stage);
-                mbar_expect_tx(fb, (uint32_t)Cfg::H_B_SLOT);
-                const uint32_t sb = smem_u32(ring_base + stage * Cfg::H_B_SLOT);
-                tma_load_3d(sb, &tmB_hi, fb, kb * 64, nt * BN, tap);
-                tma_load_3d(sb + Cfg::B_BYTES, &tmB_lo, fb, kb * 64, nt * BN, tap);
+                const uint32_t sb = smem_u32(ring_base + stage * RING_BYTES);
+                if constexpr (PAIR) {
+                  if (rank == 0) mbar_expect_tx(smem_u32(full + stage), (uint32_t)(2 * Cfg::HP_B_SLOT));
+                  const uint32_t fb = map_to_cta(smem_u32(full + stage), rank0);
+                  tma_load_3d_pair(sb, rank == 0 ? &tmB_hi : &tmB_lo, fb, kb * 64, nt * BN, btap);
+                  tma_load_3d_pair(sb + Cfg::P_BX_BYTES, &tmB_half, fb, kb * 64, nt * BN + (int)rank * (BN / 2), btap);
+                } else {
+                  const uint32_t fb = smem_u32(full + stage);
+                  mbar_expect_tx(fb, (uint32_t)Cfg::H_B_SLOT);
+                  tma_load_3d(sb, &tmB_hi, fb, kb * 64, nt * BN, btap);
+                  tma_load_3d(sb + Cfg::B_BYTES, &tmB_lo, fb, kb * 64, nt * BN, btap);
+                }
               }
               __syncwarp();
               if (++stage == NRING) { stage = 0; phase ^= 1; }
@@ -456,14 +580,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             for (int kb = 0; kb < p.kblocks; ++kb) {
               mbar_wait(smem_u32(empty + stage), phase ^ 1);
               if (elect_one()) {
-                const uint32_t fb = smem_u32(full + stage);
-                mbar_expect_tx(fb, (uint32_t)Cfg::STAGE_BYTES);
-                const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
                 const int b3 = p.b_batched ? n : btap;
-                tma_load_4d(sa, &tmA_hi, fb, p.a_c0 + kb * 64, x0 + s - p.pad, y0 + r - p.pad, n);
-                tma_load_4d(sa + TC_A_BYTES, &tmA_lo, fb, p.a_c0 + kb * 64, x0 + s - p.pad, y0 + r - p.pad, n);
-                tma_load_3d(sa + 2 * TC_A_BYTES, &tmB_hi, fb, p.b_c0 + kb * 64, nt * BN, b3);
-                tma_load_3d(sa + 2 * TC_A_BYTES + Cfg::B_BYTES, &tmB_lo, fb, p.b_c0 + kb * 64, nt * BN, b3);
+                if constexpr (PAIR) {
+                  // the leader's `full` barrier counts the bytes of both CTAs
+                  if (rank == 0) mbar_expect_tx(smem_u32(full + stage), (uint32_t)(2 * Cfg::P_STAGE_BYTES));
+                  const uint32_t fb = map_to_cta(smem_u32(full + stage), rank0);
+                  tma_load_4d_pair(sa, &tmA_hi, fb, p.a_c0 + kb * 64, x0 + s - p.pad, y0 + r - p.pad, n);
+                  tma_load_4d_pair(sa + TC_A_BYTES, &tmA_lo, fb, p.a_c0 + kb * 64, x0 + s - p.pad, y0 + r - p.pad, n);
+                  tma_load_3d_pair(sa + 2 * TC_A_BYTES, rank == 0 ? &tmB_hi : &tmB_lo, fb, p.b_c0 + kb * 64, nt * BN, b3);
+                  tma_load_3d_pair(sa + 2 * TC_A_BYTES + Cfg::P_BX_BYTES, &tmB_half, fb, p.b_c0 + kb * 64,
+                                   nt * BN + (int)rank * (BN / 2), b3);
+                } else {
+                  const uint32_t fb = smem_u32(full + stage);
+                  mbar_expect_tx(fb, (uint32_t)Cfg::STAGE_BYTES);
+                  tma_load_4d(sa, &tmA_hi, fb, p.a_c0 + kb * 64, x0 + s - p.pad, y0 + r - p.pad, n);
+                  tma_load_4d(sa + TC_A_BYTES, &tmA_lo, fb, p.a_c0 + kb * 64, x0 + s - p.pad, y0 + r - p.pad, n);
+                  tma_load_3d(sa + 2 * TC_A_BYTES, &tmB_hi, fb, p.b_c0 + kb * 64, nt * BN, b3);
+                  tma_load_3d(sa + 2 * TC_A_BYTES + Cfg::B_BYTES, &tmB_lo, fb, p.b_c0 + kb * 64, nt * BN, b3);
+                }
               }
               __syncwarp();
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -491,14 +626,62 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const uint32_t a_desc_hi = (uint32_t)((p.PW * 128) >> 4) | (1u << 14) | (2u << 29);
         int aslot = 0;
         uint32_t aphase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        if constexpr (PAIR) {
+          constexpr uint32_t pdesc2 = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+          constexpr uint32_t pdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+          if (rank == 0) {
+            for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+              const int par = p.up4 ? ((tile / p.n_tiles) & 3) : 0;      // output parity of this (pair of) tile(s)
+              const int par_y = par >> 1, par_x = par & 1;
+              int it = 0;
+              for (int kb = 0; kb < p.kblocks; ++kb) {
+                mbar_wait_cl(smem_u32(afull + aslot), aphase);
+                const uint32_t a_hi0 = smem_u32(smem + aslot * Cfg::H_A_SLOT), a_lo0 = a_hi0 + Cfg::H_A_PLANE;
+                for (int tap = 0; tap < p.taps; ++tap, ++it) {
+                  int r = (p.taps == 9) ? tap / 3 : 0;
+                  int sft = (p.taps == 9) ? tap - r * 3 : 0;
+                  if (p.up4) { r = (tap >> 1) + par_y; sft = (tap & 1) + par_x; }
+                  const bool first = (it % p.chunk) == 0;
+                  if (first) mbar_wait_cl(smem_u32(cempty + slot), slot_phase ^ 1);
+                  mbar_wait_cl(smem_u32(full + stage), phase);
+                  tc_fence_after();
+                  if (elect_one()) {
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(slot * Cfg::SLOT_COLS);
+                    const uint32_t aoff = (uint32_t)((r * p.PW + sft) * 128);
+                    const uint32_t ah = desc_lo(a_hi0 + aoff), al = desc_lo(a_lo0 + aoff);
+                    const uint32_t sb = smem_u32(ring_base + stage * RING_BYTES);
+                    const uint32_t bx = desc_lo(sb), by = desc_lo(sb + Cfg::P_BX_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                      tc_mma_f16_pair_w(d_tmem, ah + 2 * k, a_desc_hi, bx + 2 * k, DESC_HI_SW128, pdesc2, (!first || k > 0) ? 1u : 0u);
+                      tc_mma_f16_pair_w(d_tmem + BN, al + 2 * k, a_desc_hi, by + 2 * k, DESC_HI_SW128, pdesc, 1u);
+                    }
+                    tc_commit_pair(smem_u32(empty + stage), (uint16_t)3);
+                    if ((it % p.chunk) == p.chunk - 1 || it == nk - 1) tc_commit_pair(smem_u32(cfull + slot), (uint16_t)3);
+                    if (tap == p.taps - 1) tc_commit_pair(smem_u32(aempty + aslot), (uint16_t)3);
+                  }
+                  __syncwarp();
+                  if (++stage == NRING) { stage = 0; phase ^= 1; }
+                  if ((it % p.chunk) == p.chunk - 1 || it == nk - 1) {
+                    if (++slot == TC_SLOTS) { slot = 0; slot_phase ^= 1; }
+                  }
+                }
+                if (++aslot == Cfg::H_A_SLOTS) { aslot = 0; aphase ^= 1; }
+              }
+            }
+          }
+        } else {
+        for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+          const int par = p.up4 ? ((tile / p.n_tiles) & 3) : 0;
+          const int par_y = par >> 1, par_x = par & 1;
           int it = 0;
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(smem_u32(afull + aslot), aphase);
             const uint32_t a_hi0 = smem_u32(smem + aslot * Cfg::H_A_SLOT), a_lo0 = a_hi0 + Cfg::H_A_PLANE;
             for (int tap = 0; tap < p.taps; ++tap, ++it) {
-              const int r = (p.taps == 9) ? tap / 3 : 0;
-              const int sft = (p.taps == 9) ? tap - r * 3 : 0;
+              int r = (p.taps == 9) ? tap / 3 : 0;
+              int sft = (p.taps == 9) ? tap - r * 3 : 0;
+              if (p.up4) { r = (tap >> 1) + par_y; sft = (tap & 1) + par_x; }
               const bool first = (it % p.chunk) == 0;
               if (first) mbar_wait(smem_u32(cempty + slot), slot_phase ^ 1);
               mbar_wait(smem_u32(full + stage), phase);
@@ -507,7 +690,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 const uint32_t d_tmem = tmem_base + (uint32_t)(slot * Cfg::SLOT_COLS);
                 const uint32_t aoff = (uint32_t)((r * p.PW + sft) * 128);
                 const uint32_t ah = desc_lo(a_hi0 + aoff), al = desc_lo(a_lo0 + aoff);
-                const uint32_t bh = desc_lo(smem_u32(ring_base + stage * Cfg::H_B_SLOT));   // [B_hi ; B_lo] contiguous rows
+                const uint32_t bh = desc_lo(smem_u32(ring_base + stage * RING_BYTES));   // [B_hi ; B_lo] contiguous rows
                 // 64-wide k-block = 4 x UMMA_K(16): +32 B (= +2 in the >>4 address field) inside the swizzle atom.
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -527,8 +710,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             if (++aslot == Cfg::H_A_SLOTS) { aslot = 0; aphase ^= 1; }
           }
         }
+        }
+      } else if constexpr (PAIR) {
+        // M = 256 over the pair; per CTA half operands: X (this CTA's half of [B_hi;B_lo]) and Y (its half of B_hi)
+        constexpr uint32_t pdesc2 = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);   // N = 2*BN
+        constexpr uint32_t pdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);          // N = BN
+        if (rank == 0) {
+          for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+            for (int it0 = 0; it0 < nk; it0 += p.chunk) {
+              mbar_wait_cl(smem_u32(cempty + slot), slot_phase ^ 1);
+              const int it1 = (it0 + p.chunk < nk) ? it0 + p.chunk : nk;
+              for (int it = it0; it < it1; ++it) {
+                mbar_wait_cl(smem_u32(full + stage), phase);
+                tc_fence_after();
+                if (elect_one()) {
+                  const uint32_t d_tmem = tmem_base + (uint32_t)(slot * Cfg::SLOT_COLS);
+                  const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                  const uint32_t ah = desc_lo(sa), al = desc_lo(sa + TC_A_BYTES);
+                  const uint32_t bx = desc_lo(sa + 2 * TC_A_BYTES), by = desc_lo(sa + 2 * TC_A_BYTES + Cfg::P_BX_BYTES);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    tc_mma_f16_pair_w(d_tmem, ah + 2 * k, DESC_HI_SW128, bx + 2 * k, DESC_HI_SW128, pdesc2, (it > it0 || k > 0) ? 1u : 0u);
+                    tc_mma_f16_pair_w(d_tmem + BN, al + 2 * k, DESC_HI_SW128, by + 2 * k, DESC_HI_SW128, pdesc, 1u);
+                  }
+                  tc_commit_pair(smem_u32(empty + stage), (uint16_t)3);             // stage reusable in BOTH CTAs
+                  if (it == it1 - 1) tc_commit_pair(smem_u32(cfull + slot), (uint16_t)3);   // both epilogues fold their rows
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+              }
+              if (++slot == TC_SLOTS) { slot = 0; slot_phase ^= 1; }
+            }
+          }
+        }
       } else {
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
           for (int it0 = 0; it0 < nk; it0 += p.chunk) {
             mbar_wait(smem_u32(cempty + slot), slot_phase ^ 1);
             const int it1 = (it0 + p.chunk < nk) ? it0 + p.chunk : nk;
@@ -537,7 +753,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               tc_fence_after();
               if (elect_one()) {
                 const uint32_t d_tmem = tmem_base + (uint32_t)(slot * Cfg::SLOT_COLS);
-                const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
                 const uint32_t ah = desc_lo(sa), al = desc_lo(sa + TC_A_BYTES), bh = desc_lo(sa + 2 * TC_A_BYTES);   // [B_hi;B_lo]
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -565,8 +781,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const float wsi = __ldg(p.wscale_inv);
     int slot = 0;
     uint32_t slot_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+    const uint32_t cempty_leader = PAIR ? map_to_cta(smem_u32(cempty), 0u) : 0u;
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+      const int pm = tile / p.n_tiles, nt = tile - pm * p.n_tiles;
+      const int mt = mtile_of(pm);
       const int mtl = p.up4 ? (mt >> 2) : mt;
       const int per_img = p.tiles_x * p.tiles_y;
       const int n = mtl / per_img;
@@ -608,7 +826,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(cempty + slot));
+        if (lane == 0) {
+          if constexpr (PAIR) mbar_arrive_cluster(cempty_leader + (uint32_t)(slot * 8));
+          else mbar_arrive(smem_u32(cempty + slot));
+        }
         if (++slot == TC_SLOTS) { slot = 0; slot_phase ^= 1; }
       }
       // ---- finalize this tile: scale, bias, residual, activation, SFT, store (fp32 NHWC), GroupNorm partials.
@@ -711,10 +932,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();      // the peer may still read this CTA's operands / signal its barriers
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
-                 : "memory");
+    if constexpr (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
+                   : "memory");
   }
 }
 
@@ -764,17 +990,26 @@ static int tc_chunk_kblocks() {
   return v;
 }
 
-// halo engine (one patch fetch per 64-channel block, taps via shifted descriptors): stride-1 convs on 16x8 tiles.
-// Measured on B200 (profiles/round1_*): correct, halves L2->SM traffic, but the row-shifted A views make the
-// tensor core's A fetch ~10-25 % slower and the MMA A-fetch floor is the binding limit => OFF by default; CFB_TC_HALO=1 enables.
+// CTA-pair engine on unless CFB_TC_PAIR=0 (experiments / A-B timing)
+static bool pair_enabled() {
+  static const bool v = [] { const char* e = getenv("CFB_TC_PAIR"); return !(e && atoi(e) == 0); }();
+  return v;
+}
+// halo engine (one patch fetch per 64-channel block, taps via shifted descriptors): 3x3 stride-1 convs and the 2x2 parity
+// convs of Upsample, on 8x16-pixel tiles.  Measured on B200 (profiles/round1_*): with single-CTA MMAs it is SLOWER than the
+// per-tap engine (the row-shifted A views make the A fetch 10-25 % slower and the single-CTA MMA floor is the limit); in
+// CTA-pair mode the MMA has headroom and the step is power-capped, so the halved L2->SM traffic wins (+13 % on the dominant
+// conv, +5 % on the step).  It is therefore used exactly when the pair engine is (CFB_TC_HALO=0 / CFB_TC_PAIR=0 switch it off).
 static bool halo_enabled() {
-  static bool v = [] { const char* e = getenv("CFB_TC_HALO"); return e && atoi(e) != 0; }();
+  static bool v = [] { const char* e = getenv("CFB_TC_HALO"); return !(e && atoi(e) == 0); }();
   return v;
 }
 struct TcGeom { int BW, BH; bool halo; };
 static TcGeom tc_geometry(const ConvArgs& a) {
   TcGeom g;
-  g.halo = halo_enabled() && a.mode == CONV_SAME && a.Wo % 8 == 0 && a.Ho % 16 == 0;
+  const int Wt = a.mode == CONV_UP ? a.W : a.Wo, Ht = a.mode == CONV_UP ? a.H : a.Ho;   // grid the tiles live on
+  g.halo = halo_enabled() && pair_enabled() && a.ksize == 3 && (a.mode == CONV_SAME || a.mode == CONV_UP) && Wt % 8 == 0 &&
+           Ht % 16 == 0;
   if (g.halo) { g.BW = 8; g.BH = 16; }
   else { g.BW = tile_bw(a.mode == CONV_UP ? a.W : a.Wo); g.BH = 128 / g.BW; }   // Upsample: tiles live on the low-res grid
   return g;
@@ -808,28 +1043,52 @@ size_t tc_scratch_bytes(const ConvArgs& a) {
   return 2 * plane;
 }
 
-template <int BN, int CPG, bool HALO>
-static int launch_tc2(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
-                      const TcParams& p, int sm_count, cudaStream_t st) {
+// pair mode needs both CTAs of a pair on m-tiles that share the weight slice: an even number of m-tiles
+// (Upsample: of low-resolution tiles, i.e. m_tiles % 8 == 0)
+static bool pair_ok(const TcParams& p) {
+  if (!pair_enabled()) return false;
+  return p.up4 ? (p.m_tiles % 8 == 0) : (p.m_tiles % 2 == 0);
+}
+
+struct TcMaps { CUtensorMap a_hi, a_lo, b_hi, b_lo, b_half; };
+
+template <int BN, int CPG, bool HALO, bool PAIR>
+static int launch_tc2(const TcMaps& m, const TcParams& p, int sm_count, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
-  constexpr int SMEM = HALO ? Cfg::H_SMEM_BYTES : Cfg::SMEM_BYTES;
+  constexpr int SMEM = HALO ? (PAIR ? Cfg::HP_SMEM_BYTES : Cfg::H_SMEM_BYTES) : (PAIR ? Cfg::P_SMEM_BYTES : Cfg::SMEM_BYTES);
   static_assert(SMEM <= 232448, "shared memory budget");
   static bool attr_done = false;
   if (!attr_done) {
-    CFB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, CPG, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    CFB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, CPG, HALO, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_done = true;
   }
-  const int total = p.m_tiles * p.n_tiles;
-  const int grid = total < sm_count ? total : sm_count;
-  conv_tc_kernel<BN, CPG, HALO><<<grid, TC_THREADS, SMEM, st>>>(a_hi, a_lo, b_hi, b_lo, p);
-  CFB_LAUNCH_CHECK();
+  if constexpr (PAIR) {
+    const int pairs = (p.m_tiles / 2) * p.n_tiles;
+    const int max_pairs = sm_count / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * (pairs < max_pairs ? pairs : max_pairs)));
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CFB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, CPG, HALO, PAIR>, m.a_hi, m.a_lo, m.b_hi, m.b_lo, m.b_half, p));
+    count_launch();
+  } else {
+    const int total = p.m_tiles * p.n_tiles;
+    const int grid = total < sm_count ? total : sm_count;
+    conv_tc_kernel<BN, CPG, HALO, PAIR><<<grid, TC_THREADS, SMEM, st>>>(m.a_hi, m.a_lo, m.b_hi, m.b_lo, m.b_half, p);
+    CFB_LAUNCH_CHECK();
+  }
   return 0;
 }
 template <int BN, int CPG>
-static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
-                     const TcParams& p, int sm_count, cudaStream_t st) {
-  if (p.PW > 0) return launch_tc2<BN, CPG, true>(a_hi, a_lo, b_hi, b_lo, p, sm_count, st);
-  return launch_tc2<BN, CPG, false>(a_hi, a_lo, b_hi, b_lo, p, sm_count, st);
+static int launch_tc(const TcMaps& m, const TcParams& p, int sm_count, cudaStream_t st) {
+  if (p.PW > 0) return pair_ok(p) ? launch_tc2<BN, CPG, true, true>(m, p, sm_count, st) : launch_tc2<BN, CPG, true, false>(m, p, sm_count, st);
+  if (pair_ok(p)) return launch_tc2<BN, CPG, false, true>(m, p, sm_count, st);
+  return launch_tc2<BN, CPG, false, false>(m, p, sm_count, st);
 }
 
 // GroupNorm partial sums can be emitted for (BN=64, Cout=64) and (BN=128, Cout in {128,256,512})
@@ -871,7 +1130,8 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
   const int BW = geo.BW, BH = geo.BH;
   const int PW = geo.halo ? BW + a.ksize - 1 : 0, PH = geo.halo ? BH + a.ksize - 1 : 0;
   const int BN = (a.Cout % 128 == 0) ? 128 : 64;
-  CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
+  TcMaps mp;
+  CUtensorMap &mA_hi = mp.a_hi, &mA_lo = mp.a_lo, &mB_hi = mp.b_hi, &mB_lo = mp.b_lo;
   {
     const int sp = a.mode == CONV_DOWN ? 2 : 1;
     const uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)Wp, (uint64_t)Hp, (uint64_t)a.N};
@@ -888,6 +1148,8 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
     const uint32_t box[3] = {64, (uint32_t)BN, 1};
     CFB_CHECK(make_map(&mB_hi, a.wgt_hi, 3, dims, str, box));
     CFB_CHECK(make_map(&mB_lo, a.wgt_lo, 3, dims, str, box));
+    const uint32_t hbox[3] = {64, (uint32_t)(BN / 2), 1};      // CTA-pair engine: each CTA stages half of B_hi again
+    CFB_CHECK(make_map(&mp.b_half, a.wgt_hi, 3, dims, str, hbox));
   }
   TcParams p;
   p.N = a.N; p.Ho = a.Ho; p.Wo = a.Wo; p.Cout = a.Cout;
@@ -900,6 +1162,7 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
   p.BW = BW; p.BH = BH;
   p.tiles_x = (p.up4 ? a.W : a.Wo) / BW; p.tiles_y = (p.up4 ? a.H : a.Ho) / BH;
   p.m_tiles = a.N * p.tiles_x * p.tiles_y * (p.up4 ? 4 : 1); p.n_tiles = a.Cout / BN; p.kblocks = a.Cin / 64;
+  if (p.taps * p.kblocks <= 12) p.chunk = p.taps * p.kblocks;   // short K (Cin = 64): one partial sum, no 8+1 split
   p.bias = a.bias; p.residual = a.residual; p.out_act = a.out_act;
   p.sft_dec = a.sft_dec; p.sft_scale = a.sft_scale; p.sft_w = a.sft_w; p.wscale_inv = a.wscale_inv; p.out = a.out;
   p.gn_part = a.gn_part; p.gn_cpg = a.Cout / 32;
@@ -909,14 +1172,14 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
   CFB_REQUIRE(!a.gn_part || tc_can_emit_stats(a), "conv_tc: GroupNorm partials are not available for this Cout");
   if (BN == 128) {
     switch (cpg) {
-      case 0: return launch_tc<128, 0>(mA_hi, mA_lo, mB_hi, mB_lo, p, sm_count, st);
-      case 4: return launch_tc<128, 4>(mA_hi, mA_lo, mB_hi, mB_lo, p, sm_count, st);
-      case 8: return launch_tc<128, 8>(mA_hi, mA_lo, mB_hi, mB_lo, p, sm_count, st);
-      case 16: return launch_tc<128, 16>(mA_hi, mA_lo, mB_hi, mB_lo, p, sm_count, st);
+      case 0: return launch_tc<128, 0>(mp, p, sm_count, st);
+      case 4: return launch_tc<128, 4>(mp, p, sm_count, st);
+      case 8: return launch_tc<128, 8>(mp, p, sm_count, st);
+      case 16: return launch_tc<128, 16>(mp, p, sm_count, st);
     }
   } else {
-    if (cpg == 0) return launch_tc<64, 0>(mA_hi, mA_lo, mB_hi, mB_lo, p, sm_count, st);
-    if (cpg == 2) return launch_tc<64, 2>(mA_hi, mA_lo, mB_hi, mB_lo, p, sm_count, st);
+    if (cpg == 0) return launch_tc<64, 0>(mp, p, sm_count, st);
+    if (cpg == 2) return launch_tc<64, 2>(mp, p, sm_count, st);
   }
   CFB_REQUIRE(false, "conv_tc: no kernel variant for this configuration");
   return 1;
@@ -936,7 +1199,8 @@ int bmm_tc(const BmmArgs& g, int sm_count, cudaStream_t st) {
   if (g.N == 0) return 0;
   const size_t a_plane = ((size_t)g.N * 256 * g.a_pitch * 2 + 1023) / 1024 * 1024;
   const size_t b_plane = ((size_t)g.N * g.b_rows * g.b_pitch * 2 + 1023) / 1024 * 1024;
-  CUtensorMap mA_hi, mA_lo, mB_hi, mB_lo;
+  TcMaps mp;
+  CUtensorMap &mA_hi = mp.a_hi, &mA_lo = mp.a_lo, &mB_hi = mp.b_hi, &mB_lo = mp.b_lo;
   {
     const uint64_t dims[4] = {(uint64_t)g.a_pitch, 16, 16, (uint64_t)g.N};
     const uint64_t str[3] = {(uint64_t)g.a_pitch * 2, (uint64_t)16 * g.a_pitch * 2, (uint64_t)256 * g.a_pitch * 2};
@@ -950,6 +1214,8 @@ int bmm_tc(const BmmArgs& g, int sm_count, cudaStream_t st) {
     const uint32_t box[3] = {64, 128, 1};
     CFB_CHECK(make_map(&mB_hi, g.b_planes, 3, dims, str, box));
     CFB_CHECK(make_map(&mB_lo, (const char*)g.b_planes + b_plane, 3, dims, str, box));
+    const uint32_t hbox[3] = {64, 64, 1};
+    CFB_CHECK(make_map(&mp.b_half, g.b_planes, 3, dims, str, hbox));
   }
   TcParams p;
   p.N = g.N; p.Ho = 16; p.Wo = 16; p.Cout = g.Cout;
@@ -964,7 +1230,7 @@ int bmm_tc(const BmmArgs& g, int sm_count, cudaStream_t st) {
   p.gn_part = nullptr; p.gn_cpg = 0;
   p.pl_hi = (__half*)g.out_planes;
   p.pl_lo = g.out_planes ? (__half*)((char*)g.out_planes + (((size_t)g.N * 256 * g.Cout * 2 + 1023) / 1024 * 1024)) : nullptr;
-  return launch_tc<128, 0>(mA_hi, mA_lo, mB_hi, mB_lo, p, sm_count, st);
+  return launch_tc<128, 0>(mp, p, sm_count, st);
 }
 
 // softmax over rows of 256 fp32 scores -> fp16 hi/lo operand planes of the probabilities (one warp per row)
@@ -1179,31 +1445,6 @@ int umma_rate(int N, int nacc, int reps, long long* out_dev, int ctas, cudaStrea
 // rows and HALF of the B rows; the leader issues, the commit is multicast to both CTAs.  Checks which accumulator
 // columns the two B halves land in and measures the sustained rate (tools/umma_pair.py).
 // ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tc_commit_pair(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
-               : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16_pair_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                                  uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-      "setp.ne.b32 p, %6, 0;\n\t"
-      "mov.b64 da, {%1, %2};\n\t"
-      "mov.b64 db, {%3, %4};\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum)
-      : "memory");
-}
-
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
     umma_pair_kernel(int N, int reps, float* __restrict__ vals, long long* __restrict__ info) {
   extern __shared__ uint8_t smem_raw[];
