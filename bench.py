@@ -192,13 +192,14 @@ def dominant_kernel_roofline(torch, cb, batch, peaks, peak_kind):
     ms = float(ms.value)
     flops = 2.0 * N * H * H * C * C * 9
     achieved = flops / (ms * 1e-3) / 1e12
-    return {'bound': 'tensor', 'kernel': 'conv_tc_kernel<128,...>: conv 3x3 128->128 @256^2, B=8 (kernel only)',
+    return {'bound': 'tensor', 'kernel': 'conv_tc_kernel<128,0,halo,pair>: conv 3x3 128->128 @256^2, B=8 (kernel only)',
             'achieved': achieved, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s', 'frac': achieved / peaks['bf16_tflops'],
             'peak_kind': f'{peak_kind} bf16 burst (MEASURED_PEAKS.json)', 'ms_per_launch': ms,
             'algorithmic_gflop_per_launch': flops / 1e9,
-            'executed_mma_passes': '2 tcgen05.mma per k-step (N=256 + N=128) = 3x the nominal MACs (split-fp16 operands)',
-            'traffic': 490.5e6, 'traffic_unit': 'bytes/launch',
-            'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum, profiles/round1_conv128_256_full.raw.csv '
+            'executed_mma_passes': '2 tcgen05.mma.cta_group::2 (M=256) per k-step (N=256 + N=128) = 3x the nominal MACs (split-fp16 '
+                                   'operands); tensor pipe 83.6 % active in the ncu capture',
+            'traffic': 492.1e6, 'traffic_unit': 'bytes/launch',
+            'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum, profiles/round1_conv128_256_pair_full.raw.csv '
                               '(ncu --set full, same shape and batch); algorithmic = 268 MB operand planes + 268 MB output'}
 
 
