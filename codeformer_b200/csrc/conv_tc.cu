@@ -192,6 +192,43 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const float* __restrict__ 
   }
 }
 
+// torch.cat([enc_feat, dec], dim=1) of Fuse_sft_block (codeformer_arch.py:152) written directly as RAW fp16 hi/lo operand
+// planes: the fused ResBlock reads the concatenation only through the tensor engine (conv1 transforms it in-kernel, the
+// 1x1 conv_out takes it raw) and its GroupNorm statistics come from the sources' partial sums, so no fp32 copy is needed.
+__global__ void __launch_bounds__(256) concat_planes_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                            __half* __restrict__ hi, __half* __restrict__ lo, int64_t pixels,
+                                                            int Ca, int Cb) {
+  const int C8 = (Ca + Cb) >> 3;
+  const int64_t total = pixels * C8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t px = i / C8;
+    const int c = (int)(i - px * C8) * 8;
+    const float* src = c < Ca ? a + px * Ca + c : b + px * Cb + (c - Ca);
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(src)), v1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+    const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    __align__(16) __half hh[8];
+    __align__(16) __half ll[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      hh[j] = __float2half_rn(v[j]);
+      ll[j] = __float2half_rn(v[j] - __half2float(hh[j]));
+    }
+    *reinterpret_cast<uint4*>(hi + px * (Ca + Cb) + c) = *reinterpret_cast<const uint4*>(hh);
+    *reinterpret_cast<uint4*>(lo + px * (Ca + Cb) + c) = *reinterpret_cast<const uint4*>(ll);
+  }
+}
+int concat_planes(const float* a, const float* b, void* planes, int64_t pixels, int Ca, int Cb, cudaStream_t st) {
+  CFB_REQUIRE(Ca % 8 == 0 && Cb % 8 == 0, "concat_planes: channel counts must be multiples of 8");
+  if (pixels == 0) return 0;
+  const size_t plane = ((size_t)pixels * (Ca + Cb) * 2 + 1023) / 1024 * 1024;
+  const int64_t total = pixels * ((Ca + Cb) >> 3);
+  const int64_t blocks = (total + 255) / 256;
+  concat_planes_kernel<<<(unsigned)(blocks > 148 * 32 ? 148 * 32 : blocks), 256, 0, st>>>(a, b, (__half*)planes,
+                                                                                         (__half*)((char*)planes + plane), pixels, Ca, Cb);
+  CFB_LAUNCH_CHECK();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // PTX wrappers
 // ------------------------------------------------------------------------------------------------------
@@ -374,6 +411,9 @@ struct TcParams {
   int b_batched;          // B operand is a per-image activation plane: third TMA coordinate = image index, not the tap
   int up4;                // Upsample as four 2x2 convs: m-tile = (low-res tile, output parity), 4 taps, weights [16][Cout][Cin]
   int PW, PH;             // halo engine: input patch (BW+k-1) x (BH+k-1) pixels fetched once per 64-channel block
+  const float* in_scale;    // XF: per-(n, cin) affine of the fused operand transform (GroupNorm folded), and its activation
+  const float* in_shift;
+  int in_act;
   const float* bias;
   const float* residual;
   int out_act;
@@ -390,6 +430,8 @@ struct TcParams {
 
 constexpr int TC_EPI_WARPS = 8;                       // 4 TMEM lane quadrants x 2 column halves
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // warp0 TMA, warp1 MMA, warps 2..9 epilogue
+constexpr int TC_XF_WARPS = 4;                        // XF: warps 10..13 transform the A patches, warp 14 loads them
+constexpr int TC_THREADS_XF = TC_THREADS + 32 * TC_XF_WARPS + 32;
 constexpr int TC_A_BYTES = 128 * 128;                 // 128 pixels x 64 fp16
 
 template <int BN>
@@ -406,7 +448,7 @@ struct TcCfg {
   static constexpr int SLOTS = 512 / SLOT_COLS;            // 2 (BN=128) or 4 (BN=64)
   static constexpr int TMEM_COLS = 512;
   static constexpr int STG_BYTES = 8 * 4096;               // per-epilogue-warp 32x32-float transpose patches
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + STG_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/ + STG_BYTES;
   // CTA-pair engine (cta_group::2, M = 256 over the two SMs of a TPC): each CTA stages its own A tile (hi, lo) and HALF of
   // every B operand: X = its half of [B_hi;B_lo] (rank 0: B_hi, rank 1: B_lo -> accumulator columns [0,BN) | [BN,2BN)) and
   // Y = its half of B_hi for the A_lo x B_hi pass (rank r: rows [r*BN/2, +BN/2))
@@ -414,7 +456,7 @@ struct TcCfg {
   static constexpr int P_BY_BYTES = BN * 64;
   static constexpr int P_STAGE_BYTES = 2 * TC_A_BYTES + P_BX_BYTES + P_BY_BYTES;
   static constexpr int P_STAGES = (BN == 64) ? 4 : 3;
-  static constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + 1024 + 256 + STG_BYTES;
+  static constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + 1024 + 512 + STG_BYTES;
   // halo engine: 16x8-pixel tiles; the (16+2)x(8+2) input patch of one 64-channel block is fetched ONCE (hi and lo
   // planes) and all 9 taps read it through row-shifted UMMA descriptors; weights stream through their own ring.
   static constexpr int H_A_PLANE = 23 * 1024;              // >= 18*10*128 B, 1024-aligned
@@ -422,11 +464,17 @@ struct TcCfg {
   static constexpr int H_A_SLOTS = 2;
   static constexpr int H_B_SLOT = 2 * B_BYTES;
   static constexpr int H_B_SLOTS = (BN == 64) ? 6 : 3;
-  static constexpr int H_SMEM_BYTES = H_A_SLOTS * H_A_SLOT + H_B_SLOTS * H_B_SLOT + 1024 + 256 + STG_BYTES;
+  static constexpr int H_SMEM_BYTES = H_A_SLOTS * H_A_SLOT + H_B_SLOTS * H_B_SLOT + 1024 + 512 + STG_BYTES;
   // halo engine in CTA-pair mode: B slots hold this CTA's halves (X | Y, see above)
   static constexpr int HP_B_SLOT = P_BX_BYTES + P_BY_BYTES;
   static constexpr int HP_B_SLOTS = (BN == 64) ? 8 : 4;
-  static constexpr int HP_SMEM_BYTES = H_A_SLOTS * H_A_SLOT + HP_B_SLOTS * HP_B_SLOT + 1024 + 256 + STG_BYTES;
+  static constexpr int HP_SMEM_BYTES = H_A_SLOTS * H_A_SLOT + HP_B_SLOTS * HP_B_SLOT + 1024 + 512 + STG_BYTES;
+  // fused operand transform (XF, halo + pair only): the A patches arrive as RAW fp16 hi/lo planes of the producing conv's
+  // output and four transform warps apply GroupNorm-affine + SiLU + the hi/lo re-split in place before the MMAs read them;
+  // one more A slot for the short-K (Cin = 64) layers, whose MMA time per patch is below TMA + transform latency
+  static constexpr int X_A_SLOTS = (BN == 64) ? 3 : 2;
+  static constexpr int X_B_SLOTS = 4;
+  static constexpr int X_SMEM_BYTES = X_A_SLOTS * H_A_SLOT + X_B_SLOTS * HP_B_SLOT + 1024 + 512 + STG_BYTES;
 };
 
 // Accumulation scheme (why the TMEM ring): tcgen05.mma adds into its fp32 accumulator with truncation, so a long
@@ -440,12 +488,14 @@ struct TcCfg {
 // 60 %) and each SM stages / reads only half of every B operand.  Rank 0 (leader) issues all MMAs; its `full` and `cempty`
 // barriers collect the TMA bytes / epilogue arrivals of both CTAs; `empty` and `cfull` are signalled in both CTAs by
 // multicast commits.
-template <int BN, int CPG, bool HALO, bool PAIR>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int BN, int CPG, bool HALO, bool PAIR, bool XF>
+__global__ void __launch_bounds__(XF ? TC_THREADS_XF : TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                const __grid_constant__ CUtensorMap tmB_half, const TcParams p) {
+  static_assert(!XF || (HALO && PAIR), "the fused operand transform exists for the halo + pair engine only");
   using Cfg = TcCfg<BN>;
+  constexpr int A_SLOTS = XF ? Cfg::X_A_SLOTS : Cfg::H_A_SLOTS;
   constexpr int STAGES = PAIR ? Cfg::P_STAGES : Cfg::STAGES;
   constexpr int STAGE_BYTES = PAIR ? Cfg::P_STAGE_BYTES : Cfg::STAGE_BYTES;
   constexpr int TC_SLOTS = Cfg::SLOTS;
@@ -455,24 +505,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   // ring "full/empty": per-tap engine = STAGES k-block stages; halo engine = weight (B) slots.  "afull/aempty": halo A slots.
-  constexpr int NRING = HALO ? (PAIR ? Cfg::HP_B_SLOTS : Cfg::H_B_SLOTS) : STAGES;
+  constexpr int NRING = HALO ? (XF ? Cfg::X_B_SLOTS : (PAIR ? Cfg::HP_B_SLOTS : Cfg::H_B_SLOTS)) : STAGES;
   constexpr int RING_BYTES = HALO ? (PAIR ? Cfg::HP_B_SLOT : Cfg::H_B_SLOT) : STAGE_BYTES;
-  uint8_t* ring_base = HALO ? smem + Cfg::H_A_SLOTS * Cfg::H_A_SLOT : smem;
+  uint8_t* ring_base = HALO ? smem + A_SLOTS * Cfg::H_A_SLOT : smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring_base + NRING * RING_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + NRING;
   uint64_t* cfull = bars + 2 * NRING;
   uint64_t* cempty = bars + 2 * NRING + TC_SLOTS;
   uint64_t* afull = bars + 2 * NRING + 2 * TC_SLOTS;
-  uint64_t* aempty = afull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 2);
-  uint8_t* stage_buf = reinterpret_cast<uint8_t*>(bars) + 256;      // epilogue transpose patches (16-byte aligned)
+  uint64_t* aempty = afull + 3;
+  uint64_t* araw = aempty + 3;                       // XF: raw patch landed (TMA -> transform warps), local to each CTA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(araw + 3);
+  uint8_t* stage_buf = reinterpret_cast<uint8_t*>(bars) + 512;      // epilogue transpose patches (16-byte aligned)
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(afull + a), 1); mbar_init(smem_u32(aempty + a), 1); }
+    for (int a = 0; a < 3; ++a) {
+      mbar_init(smem_u32(afull + a), XF ? 2 * TC_XF_WARPS : 1);      // XF: the transform warps of both CTAs arrive on the leader
+      mbar_init(smem_u32(aempty + a), 1);
+      mbar_init(smem_u32(araw + a), 1);
+    }
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_lo) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_hi) : "memory");
@@ -533,6 +588,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int y0 = ty * p.BH * p.stride, x0 = tx * p.BW * p.stride;
         if constexpr (HALO) {
           for (int kb = 0; kb < p.kblocks; ++kb) {
+            if constexpr (!XF) {
             mbar_wait(smem_u32(aempty + aslot), aphase ^ 1);
             if (elect_one()) {
               const uint32_t sa = smem_u32(smem + aslot * Cfg::H_A_SLOT);
@@ -549,7 +605,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               }
             }
             __syncwarp();
-            if (++aslot == Cfg::H_A_SLOTS) { aslot = 0; aphase ^= 1; }
+            if (++aslot == A_SLOTS) { aslot = 0; aphase ^= 1; }
+            }
             for (int tap = 0; tap < p.taps; ++tap) {
               const int btap = p.up4 ? (mt & 3) * 4 + tap : tap;      // Upsample: weight slice of this output parity
               mbar_wait(smem_u32(empty + stage), phase ^ 1);
@@ -666,7 +723,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     if (++slot == TC_SLOTS) { slot = 0; slot_phase ^= 1; }
                   }
                 }
-                if (++aslot == Cfg::H_A_SLOTS) { aslot = 0; aphase ^= 1; }
+                if (++aslot == A_SLOTS) { aslot = 0; aphase ^= 1; }
               }
             }
           }
@@ -707,7 +764,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 if (++slot == TC_SLOTS) { slot = 0; slot_phase ^= 1; }
               }
             }
-            if (++aslot == Cfg::H_A_SLOTS) { aslot = 0; aphase ^= 1; }
+            if (++aslot == A_SLOTS) { aslot = 0; aphase ^= 1; }
           }
         }
         }
@@ -768,6 +825,110 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
             if (++slot == TC_SLOTS) { slot = 0; slot_phase ^= 1; }
           }
+        }
+      }
+    }
+  } else if (XF && warp == 2 + TC_EPI_WARPS + TC_XF_WARPS) {
+    // ============================ XF: A-patch loader (own warp: patches must be requested a whole patch ahead) ==========
+    if constexpr (XF) {
+      int aslot = 0;
+      uint32_t aphase = 0;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+        const int mt = mtile_of(tile / p.n_tiles);
+        const int per_img = p.tiles_x * p.tiles_y;
+        const int n = mt / per_img;
+        const int rem = mt - n * per_img;
+        const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+        const int y0 = ty * p.BH, x0 = tx * p.BW;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(smem_u32(aempty + aslot), aphase ^ 1);       // every MMA that read this slot has completed
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(smem + aslot * Cfg::H_A_SLOT);
+            const uint32_t rb = smem_u32(araw + aslot);
+            mbar_expect_tx(rb, (uint32_t)(2 * p.PW * p.PH * 128));
+            tma_load_4d(sa, &tmA_hi, rb, kb * 64, x0 - p.pad, y0 - p.pad, n);
+            tma_load_4d(sa + Cfg::H_A_PLANE, &tmA_lo, rb, kb * 64, x0 - p.pad, y0 - p.pad, n);
+          }
+          __syncwarp();
+          if (++aslot == A_SLOTS) { aslot = 0; aphase ^= 1; }
+        }
+      }
+    }
+  } else if (XF && warp >= 2 + TC_EPI_WARPS) {
+    // ============================ XF: operand transform (warps 10..13) ============================
+    // raw patch (fp16 hi + lo of the producing conv's output, zero outside the image) -> y = act(x * scale[n,c] + shift[n,c])
+    // (GroupNorm folded into scale/shift, vqgan_arch.py:14-15,153-160) -> fp16 hi/lo of y, written back IN PLACE in the
+    // 128B-swizzled layout the MMA descriptors expect; pixels outside the image stay exactly zero (the conv pads the
+    // NORMALISED tensor).  fence.proxy.async publishes the generic-proxy writes to the tensor core.
+    if constexpr (XF) {
+      const int t = (int)threadIdx.x - 32 * (2 + TC_EPI_WARPS);      // 0..127
+      const int chunk = t & 7, r0 = t >> 3;                          // 16-byte chunk (8 channels) of a patch row; first row
+      const uint32_t afull_leader = map_to_cta(smem_u32(afull), 0u);
+      constexpr int XF_PW = 10, XF_ROWS = 10 * 18;                   // halo patch of an 8 x 16 tile and a 3 x 3 filter
+      const bool silu = p.in_act == IN_SILU;
+      const int Hin = p.tiles_y * p.BH, Win = p.tiles_x * p.BW;
+      const int Cin = p.kblocks * 64;
+      int aslot = 0;
+      uint32_t aphase = 0;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+        const int mt = mtile_of(tile / p.n_tiles);
+        const int per_img = p.tiles_x * p.tiles_y;
+        const int n = mt / per_img;
+        const int rem = mt - n * per_img;
+        const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+        const int y0 = ty * p.BH - p.pad, x0 = tx * p.BW - p.pad;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          float sc[8], sh[8];
+          {
+            const float* sp = p.in_scale + (int64_t)n * Cin + kb * 64 + chunk * 8;
+            const float* hp = p.in_shift + (int64_t)n * Cin + kb * 64 + chunk * 8;
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(sp)), s1 = __ldg(reinterpret_cast<const float4*>(sp + 4));
+            const float4 h0 = __ldg(reinterpret_cast<const float4*>(hp)), h1 = __ldg(reinterpret_cast<const float4*>(hp + 4));
+            sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+            sh[0] = h0.x; sh[1] = h0.y; sh[2] = h0.z; sh[3] = h0.w; sh[4] = h1.x; sh[5] = h1.y; sh[6] = h1.z; sh[7] = h1.w;
+          }
+          mbar_wait(smem_u32(araw + aslot), aphase);
+          uint8_t* hi_base = smem + aslot * Cfg::H_A_SLOT;
+          uint8_t* lo_base = hi_base + Cfg::H_A_PLANE;
+          // 10 x 18 patch rows, 16 rows per pass: fully unrolled so the independent rows overlap their latencies
+#pragma unroll
+          for (int it = 0; it < (XF_ROWS + 15) / 16; ++it) {
+            const int r = r0 + it * 16;
+            if (r < XF_ROWS) {
+              const int py = r / XF_PW, px = r - py * XF_PW;
+              const bool inside = (unsigned)(y0 + py) < (unsigned)Hin && (unsigned)(x0 + px) < (unsigned)Win;
+              const uint32_t off = (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
+              uint4 hv = make_uint4(0u, 0u, 0u, 0u), lv = make_uint4(0u, 0u, 0u, 0u);
+              if (inside) {
+                const uint4 hr = *reinterpret_cast<const uint4*>(hi_base + off);
+                const uint4 lr = *reinterpret_cast<const uint4*>(lo_base + off);
+                const __half2* h2 = reinterpret_cast<const __half2*>(&hr);
+                const __half2* l2 = reinterpret_cast<const __half2*>(&lr);
+                __half2* oh = reinterpret_cast<__half2*>(&hv);
+                __half2* ol = reinterpret_cast<__half2*>(&lv);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 a = __half22float2(h2[j]), b = __half22float2(l2[j]);
+                  float v0 = fmaf(a.x + b.x, sc[2 * j], sh[2 * j]);
+                  float v1 = fmaf(a.y + b.y, sc[2 * j + 1], sh[2 * j + 1]);
+                  if (silu) {      // x * sigmoid(x) with the fast exp / reciprocal: ~2^-21 relative, below the hi/lo operand error
+                    v0 = __fdividef(v0, 1.f + __expf(-v0));
+                    v1 = __fdividef(v1, 1.f + __expf(-v1));
+                  }
+                  const __half2 hh = __floats2half2_rn(v0, v1);
+                  const float2 hf = __half22float2(hh);
+                  oh[j] = hh;
+                  ol[j] = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+                }
+              }
+              *reinterpret_cast<uint4*>(hi_base + off) = hv;
+              *reinterpret_cast<uint4*>(lo_base + off) = lv;
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(afull_leader + (uint32_t)(aslot * 8));
+          if (++aslot == A_SLOTS) { aslot = 0; aphase ^= 1; }
         }
       }
     }
@@ -885,7 +1046,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             v.x = d.x + p.sft_w * (d.x * sc.x + v.x); v.y = d.y + p.sft_w * (d.y * sc.y + v.y);
             v.z = d.z + p.sft_w * (d.z * sc.z + v.z); v.w = d.w + p.sft_w * (d.w * sc.w + v.w);
           }
-          *reinterpret_cast<float4*>(p.out + off) = v;
+          if (p.out) *reinterpret_cast<float4*>(p.out + off) = v;      // null: only the operand planes are consumed
           if (p.pl_hi) {
             const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
             const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
@@ -1036,6 +1197,20 @@ bool tc_supported(const ConvArgs& a) {
   return true;
 }
 
+// fused operand transform: available for 3x3 stride-1 convs on the halo + pair engine, USED where it measured faster than
+// prep pass + conv (profiles/round1_xform_launch_summary_b8.md): 128-wide output tiles with >= 2 k-blocks at >= 64x64 --
+// there the MMAs of one patch (6.9k cycles) cover TMA + transform.  The Cin = 64 layers (4.1k cycles of MMA per patch)
+// and the 16x16 / 32x32 layers (one or two tiles per SM: latency exposed) lose.  CFB_TC_XFORM=0 disables, =2 forces all.
+bool tc_can_xform(const ConvArgs& a) {
+  static const int mode = [] { const char* e = getenv("CFB_TC_XFORM"); return e ? atoi(e) : 1; }();
+  if (mode == 0 || !tc_supported(a) || a.mode != CONV_SAME || a.ksize != 3) return false;
+  if (mode == 1 && !(a.Cout % 128 == 0 && a.Cin >= 128 && (int64_t)a.Ho * a.Wo >= 4096)) return false;
+  const TcGeom g = tc_geometry(a);
+  if (!g.halo) return false;
+  const int64_t m_tiles = (int64_t)a.N * (a.Wo / g.BW) * (a.Ho / g.BH);
+  return m_tiles % 2 == 0;
+}
+
 size_t tc_scratch_bytes(const ConvArgs& a) {
   if (!tc_supported(a)) return 0;
   const int Hp = a.mode == CONV_SAME ? a.Ho : a.H, Wp = a.mode == CONV_SAME ? a.Wo : a.W;   // operand plane = input resolution
@@ -1052,14 +1227,16 @@ static bool pair_ok(const TcParams& p) {
 
 struct TcMaps { CUtensorMap a_hi, a_lo, b_hi, b_lo, b_half; };
 
-template <int BN, int CPG, bool HALO, bool PAIR>
+template <int BN, int CPG, bool HALO, bool PAIR, bool XF = false>
 static int launch_tc2(const TcMaps& m, const TcParams& p, int sm_count, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
-  constexpr int SMEM = HALO ? (PAIR ? Cfg::HP_SMEM_BYTES : Cfg::H_SMEM_BYTES) : (PAIR ? Cfg::P_SMEM_BYTES : Cfg::SMEM_BYTES);
+  constexpr int SMEM = XF ? Cfg::X_SMEM_BYTES
+                          : (HALO ? (PAIR ? Cfg::HP_SMEM_BYTES : Cfg::H_SMEM_BYTES) : (PAIR ? Cfg::P_SMEM_BYTES : Cfg::SMEM_BYTES));
+  constexpr int THREADS = XF ? TC_THREADS_XF : TC_THREADS;
   static_assert(SMEM <= 232448, "shared memory budget");
   static bool attr_done = false;
   if (!attr_done) {
-    CFB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, CPG, HALO, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    CFB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, CPG, HALO, PAIR, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_done = true;
   }
   if constexpr (PAIR) {
@@ -1067,25 +1244,29 @@ static int launch_tc2(const TcMaps& m, const TcParams& p, int sm_count, cudaStre
     const int max_pairs = sm_count / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(2 * (pairs < max_pairs ? pairs : max_pairs)));
-    cfg.blockDim = dim3(TC_THREADS);
+    cfg.blockDim = dim3(THREADS);
     cfg.dynamicSmemBytes = SMEM;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    CFB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, CPG, HALO, PAIR>, m.a_hi, m.a_lo, m.b_hi, m.b_lo, m.b_half, p));
+    CFB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, CPG, HALO, PAIR, XF>, m.a_hi, m.a_lo, m.b_hi, m.b_lo, m.b_half, p));
     count_launch();
   } else {
     const int total = p.m_tiles * p.n_tiles;
     const int grid = total < sm_count ? total : sm_count;
-    conv_tc_kernel<BN, CPG, HALO, PAIR><<<grid, TC_THREADS, SMEM, st>>>(m.a_hi, m.a_lo, m.b_hi, m.b_lo, m.b_half, p);
+    conv_tc_kernel<BN, CPG, HALO, PAIR, XF><<<grid, THREADS, SMEM, st>>>(m.a_hi, m.a_lo, m.b_hi, m.b_lo, m.b_half, p);
     CFB_LAUNCH_CHECK();
   }
   return 0;
 }
 template <int BN, int CPG>
 static int launch_tc(const TcMaps& m, const TcParams& p, int sm_count, cudaStream_t st) {
+  if (p.in_scale) {      // fused operand transform: conv_tc() only asks for it when tc_can_xform() holds
+    CFB_REQUIRE(p.PW == 10 && p.PH == 18 && pair_ok(p), "conv_tc: fused operand transform needs the halo + pair engine");
+    return launch_tc2<BN, CPG, true, true, true>(m, p, sm_count, st);
+  }
   if (p.PW > 0) return pair_ok(p) ? launch_tc2<BN, CPG, true, true>(m, p, sm_count, st) : launch_tc2<BN, CPG, true, false>(m, p, sm_count, st);
   if (pair_ok(p)) return launch_tc2<BN, CPG, false, true>(m, p, sm_count, st);
   return launch_tc2<BN, CPG, false, false>(m, p, sm_count, st);
@@ -1163,6 +1344,11 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
   p.tiles_x = (p.up4 ? a.W : a.Wo) / BW; p.tiles_y = (p.up4 ? a.H : a.Ho) / BH;
   p.m_tiles = a.N * p.tiles_x * p.tiles_y * (p.up4 ? 4 : 1); p.n_tiles = a.Cout / BN; p.kblocks = a.Cin / 64;
   if (p.taps * p.kblocks <= 12) p.chunk = p.taps * p.kblocks;   // short K (Cin = 64): one partial sum, no 8+1 split
+  p.in_scale = nullptr; p.in_shift = nullptr; p.in_act = IN_NONE;
+  if (a.xform) {
+    CFB_REQUIRE(a.skip_prep && a.in_scale && a.in_shift && tc_can_xform(a), "conv_tc: fused operand transform not available for this conv");
+    p.in_scale = a.in_scale; p.in_shift = a.in_shift; p.in_act = a.in_act;
+  }
   p.bias = a.bias; p.residual = a.residual; p.out_act = a.out_act;
   p.sft_dec = a.sft_dec; p.sft_scale = a.sft_scale; p.sft_w = a.sft_w; p.wscale_inv = a.wscale_inv; p.out = a.out;
   p.gn_part = a.gn_part; p.gn_cpg = a.Cout / 32;
@@ -1225,6 +1411,7 @@ int bmm_tc(const BmmArgs& g, int sm_count, cudaStream_t st) {
   p.PW = 0; p.PH = 0;
   p.BW = 16; p.BH = 8; p.tiles_x = 1; p.tiles_y = 2;
   p.m_tiles = g.N * 2; p.n_tiles = g.Cout / 128; p.kblocks = g.K / 64;
+  p.in_scale = nullptr; p.in_shift = nullptr; p.in_act = IN_NONE;
   p.bias = nullptr; p.residual = nullptr; p.out_act = OUT_NONE; p.sft_dec = nullptr; p.sft_scale = nullptr; p.sft_w = 0.f;
   p.wscale_inv = g.scale_dev; p.out = g.out;
   p.gn_part = nullptr; p.gn_cpg = 0;

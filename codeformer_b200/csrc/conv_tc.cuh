@@ -12,6 +12,7 @@ int tc_split_weights(const float* oihw, __half* hi, __half* lo, int Cout, int Ci
 // Upsample convs: pre-summed 2x2 parity weights [16][Cout][Cin] (hi/lo) -- pass these as wgt_hi/wgt_lo/wscale_inv with mode CONV_UP
 int tc_split_weights_up4(const float* oihw3x3, __half* hi, __half* lo, int Cout, int Cin, float* scale_slot, cudaStream_t st);
 bool tc_supported(const ConvArgs& a);
+bool tc_can_xform(const ConvArgs& a);
 size_t tc_scratch_bytes(const ConvArgs& a);   // operand (hi/lo fp16 activation planes) staging
 bool tc_can_emit_stats(const ConvArgs& a);    // GroupNorm(32) partial sums available from the epilogue for this shape
 int tc_tiles_per_image(const ConvArgs& a);    // 128-pixel tiles per image (GroupNorm partial slots = 4x this)
@@ -26,6 +27,7 @@ struct BmmArgs {
   void* out_planes = nullptr;         // optional hi | lo planes of out
 };
 int bmm_tc(const BmmArgs& g, int sm_count, cudaStream_t st);
+int concat_planes(const float* a, const float* b, void* planes, int64_t pixels, int Ca, int Cb, cudaStream_t st);
 int softmax256_planes(const float* scores, void* planes, int64_t rows, cudaStream_t st);
 int transpose_planes(const void* in_planes, int N, int pitch, int c0, int C, void* out_planes, cudaStream_t st);
 // diagnostics (tools/umma_probe.py): row-shifted SWIZZLE_128B descriptor views

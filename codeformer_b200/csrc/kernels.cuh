@@ -76,6 +76,7 @@ struct ConvArgs {
   // tensor-core engine only: also emit `out` as fp16 hi/lo operand planes for a following conv that consumes it raw
   void* out_planes = nullptr;       // [hi plane | lo plane], each align1024(N*Ho*Wo*Cout*2) bytes
   bool skip_prep = false;           // operand planes in `scratch` are already valid (kernel-only timing)
+  bool xform = false;      // tensor engine: `in` planes are RAW; apply in_scale/in_shift/in_act inside the conv kernel (tc_can_xform)
 };
 
 int conv_f32(const ConvArgs& a, cudaStream_t st);                       // CUDA-core fp32 implicit GEMM

@@ -431,7 +431,11 @@ struct Fwd {
     return 0;
   }
   void release(Tensor& t) {
-    if (t.owned && t.p) { ar.release(t.p); if (t.gn_part) ar.release(t.gn_part); if (t.planes) ar.release(t.planes); }
+    if (t.owned) {
+      if (t.p) ar.release(t.p);
+      if (t.gn_part) ar.release(t.gn_part);
+      if (t.planes) ar.release(t.planes);
+    }
     t.p = nullptr; t.gn_part = nullptr; t.planes = nullptr;
   }
   void release_raw(void* p) { ar.release(p); }
@@ -454,6 +458,7 @@ struct Fwd {
     float* out_ptr = nullptr;   // write into caller memory instead of the arena
     bool want_stats = false;    // consumer is a GroupNorm: let the tensor-core epilogue emit the partial sums
     bool want_planes = false;   // a following conv reads this output raw: emit its fp16 hi/lo operand planes too
+    bool planes_only = false;   // the fp32 tensor itself is never read (ResBlock h: statistics + planes suffice): skip its store
   };
 
   int conv(const ConvW& w, const Tensor& in, Tensor& out, const ConvOpt& o) {
@@ -461,17 +466,24 @@ struct Fwd {
     int Ho = in.H, Wo = in.W;
     if (o.mode == CONV_DOWN) { Ho = in.H / 2; Wo = in.W / 2; }
     if (o.mode == CONV_UP) { Ho = in.H * 2; Wo = in.W * 2; }
-    if (o.out_ptr) {
-      out.p = o.out_ptr; out.N = in.N; out.H = Ho; out.W = Wo; out.C = w.cout; out.owned = false;
-      out.gn_part = nullptr; out.gn_slots = 0; out.planes = nullptr;
-    }
-    else CFB_CHECK(alloc(out, in.N, Ho, Wo, w.cout));
     ConvArgs a;
     a.in = in.p; a.N = in.N; a.H = in.H; a.W = in.W; a.Cin = in.C; a.Ho = Ho; a.Wo = Wo; a.Cout = w.cout;
     a.ksize = w.k; a.mode = o.mode; a.wgt_f32 = w.w_f32; a.wgt_hi = w.w_hi; a.wgt_lo = w.w_lo; a.wscale_inv = w.wscale + 1; a.bias = w.bias;
     a.in_scale = o.in_scale; a.in_shift = o.in_shift; a.in_act = o.in_act; a.residual = o.residual;
-    a.out_act = o.out_act; a.sft_dec = o.sft_dec; a.sft_scale = o.sft_scale; a.sft_w = o.sft_w; a.out = out.p;
+    a.out_act = o.out_act; a.sft_dec = o.sft_dec; a.sft_scale = o.sft_scale; a.sft_w = o.sft_w;
     bool use_tc = engine == 2 || (engine == 0 && n->tc_ok && tc_supported(a));
+    // planes-only output: legal when this conv emits both the GroupNorm partial sums and the operand planes
+    const bool no_f32 = o.planes_only && use_tc && !o.out_ptr && o.want_stats && o.want_planes && tc_supported(a) && tc_can_emit_stats(a);
+    if (o.out_ptr) {
+      out.p = o.out_ptr; out.N = in.N; out.H = Ho; out.W = Wo; out.C = w.cout; out.owned = false;
+      out.gn_part = nullptr; out.gn_slots = 0; out.planes = nullptr;
+    } else if (no_f32) {
+      out.p = nullptr; out.N = in.N; out.H = Ho; out.W = Wo; out.C = w.cout; out.owned = true;
+      out.gn_part = nullptr; out.gn_slots = 0; out.planes = nullptr;
+    } else {
+      CFB_CHECK(alloc(out, in.N, Ho, Wo, w.cout));
+    }
+    a.out = out.p;
     if (use_tc && o.mode == CONV_UP) { a.wgt_hi = w.u_hi; a.wgt_lo = w.u_lo; a.wscale_inv = w.uscale + 1; }
     if (use_tc) {
       CFB_REQUIRE(tc_supported(a), "conv: shape not supported by the tcgen05 engine: " + w.name);
@@ -485,14 +497,20 @@ struct Fwd {
         CFB_CHECK(alloc_raw(&out.planes, pb));
         a.out_planes = out.planes;
       }
-      // the producer already emitted this input's operand planes and the conv takes it raw: no prep pass
-      const bool reuse = in.planes && !o.in_scale && o.in_act == IN_NONE;
+      // the producer already emitted this input's RAW operand planes: a conv that takes it raw needs no prep pass, and a
+      // GroupNorm + SiLU conv on the halo + pair engine applies the affine / activation inside the kernel (tc_can_xform)
+      const bool raw = in.planes && !o.in_scale && o.in_act == IN_NONE;
+      const bool xf = in.planes && o.in_scale && o.in_shift && tc_can_xform(a);
+      const bool reuse = raw || xf;
       void* scratch = in.planes;
       if (!reuse) CFB_CHECK(alloc_raw(&scratch, tc_scratch_bytes(a)));
+      CFB_REQUIRE(in.p != nullptr || reuse, "conv: planes-only input without a planes consumer: " + w.name);
       a.skip_prep = reuse;
+      a.xform = xf;
       if (!dry) CFB_CHECK(conv_tc(a, scratch, n->sm_count, st));
       if (!reuse) release_raw(scratch);
     } else {
+      CFB_REQUIRE(in.p != nullptr && out.p != nullptr, "conv: planes-only tensor reached the fp32 engine: " + w.name);
       if (!dry) CFB_CHECK(conv_f32(a, st));
     }
     return 0;
@@ -501,6 +519,7 @@ struct Fwd {
   // GroupNorm(32, C, 1e-6) statistics -> scale/shift [N,C]
   int gn(const NormW& w, const Tensor& x, float** scale, float** shift) {
     CFB_REQUIRE(x.C == w.c, "norm: channel mismatch for " + w.name);
+    CFB_REQUIRE(x.p || x.gn_part, "norm: planes-only tensor without partial sums for " + w.name);
     CFB_CHECK(alloc_raw((void**)scale, (size_t)x.N * x.C * 4));
     CFB_CHECK(alloc_raw((void**)shift, (size_t)x.N * x.C * 4));
     if (x.gn_part) {   // statistics already reduced per tile by the producing conv's epilogue
@@ -521,6 +540,9 @@ struct Fwd {
     CFB_CHECK(gn(r.n1, x, &s1, &h1));
     Tensor h;
     ConvOpt o1; o1.in_scale = s1; o1.in_shift = h1; o1.in_act = IN_SILU; o1.want_stats = true;
+    // if conv2 runs the fused operand transform, h is only ever read through its raw planes (+ the epilogue's statistics)
+    o1.want_planes = xf_ok(x.N, x.H, x.W, r.c2);
+    o1.planes_only = o1.want_planes && n->captures.empty();
     CFB_CHECK(conv(r.c1, x, h, o1));
     release_raw(s1); release_raw(h1);
     CFB_CHECK(gn(r.n2, h, &s2, &h2));
@@ -587,9 +609,25 @@ struct Fwd {
   // Fuse_sft_block.forward  codeformer_arch.py:151-157
   int fuse(const FuseW& f, const Tensor& enc_feat, const Tensor& dec, float wgt, Tensor& y) {
     Tensor cat;
-    CFB_CHECK(alloc(cat, dec.N, dec.H, dec.W, enc_feat.C + dec.C));
-    if (!dry) CFB_CHECK(concat_channels(enc_feat.p, dec.p, cat.p, (int64_t)dec.N * dec.H * dec.W, enc_feat.C, dec.C, st));
-    if (enc_feat.gn_part && dec.gn_part && enc_feat.gn_slots == dec.gn_slots && enc_feat.C == dec.C) {
+    const bool stats_from_parts = enc_feat.gn_part && dec.gn_part && enc_feat.gn_slots == dec.gn_slots && enc_feat.C == dec.C;
+    bool planes_cat = false;
+    if (stats_from_parts && n->captures.empty() && (engine == 2 || (engine == 0 && n->tc_ok))) {
+      ConvArgs a1;      // conv1 of the fused ResBlock: does it run the in-kernel operand transform?
+      a1.N = dec.N; a1.H = dec.H; a1.W = dec.W; a1.Cin = f.enc.c1.cin; a1.Ho = dec.H; a1.Wo = dec.W; a1.Cout = f.enc.c1.cout;
+      a1.ksize = f.enc.c1.k; a1.mode = CONV_SAME;
+      planes_cat = f.enc.has_out && tc_can_xform(a1);
+    }
+    if (planes_cat) {
+      // the concatenation exists only as raw operand planes (no fp32 copy, no prep pass)
+      cat.p = nullptr; cat.N = dec.N; cat.H = dec.H; cat.W = dec.W; cat.C = enc_feat.C + dec.C; cat.owned = true;
+      cat.gn_part = nullptr; cat.gn_slots = 0; cat.planes = nullptr;
+      CFB_CHECK(alloc_raw(&cat.planes, 2 * (((size_t)cat.numel() * 2 + 1023) / 1024 * 1024)));
+      if (!dry) CFB_CHECK(concat_planes(enc_feat.p, dec.p, cat.planes, (int64_t)dec.N * dec.H * dec.W, enc_feat.C, dec.C, st));
+    } else {
+      CFB_CHECK(alloc(cat, dec.N, dec.H, dec.W, enc_feat.C + dec.C));
+      if (!dry) CFB_CHECK(concat_channels(enc_feat.p, dec.p, cat.p, (int64_t)dec.N * dec.H * dec.W, enc_feat.C, dec.C, st));
+    }
+    if (stats_from_parts) {
       // GroupNorm statistics of the concatenation follow from the two sources' partial sums (no extra pass)
       cat.gn_slots = dec.gn_slots;
       CFB_CHECK(alloc_raw((void**)&cat.gn_part, (size_t)dec.N * cat.gn_slots * 64 * sizeof(float)));
@@ -606,10 +644,31 @@ struct Fwd {
     release(s0);
     CFB_CHECK(conv(f.h0, e, h0, ol));
     release(e);
-    ConvOpt of; of.sft_dec = dec.p; of.sft_scale = sc.p; of.sft_w = wgt; of.want_stats = true;
+    ConvOpt of; of.sft_dec = dec.p; of.sft_scale = sc.p; of.sft_w = wgt; of.want_stats = true; of.want_planes = true;
     CFB_CHECK(conv(f.h2, h0, y, of));
     release(h0); release(sc);
     return 0;
+  }
+
+  // Does the consumer of block i's output read it through the tensor engine's operand planes?  Down/Upsample convs and a
+  // ResBlock's 1x1 conv_out take them raw; a ResBlock's conv1 and a norm -> conv pair apply GroupNorm + SiLU to the raw
+  // planes inside the conv kernel (fused operand transform).  `last_is_simt`: the final conv of the Generator is the
+  // CUDA-core conv_last.
+  bool xf_ok(int N, int H, int W, const ConvW& w) const {
+    if (!(engine == 2 || (engine == 0 && n->tc_ok))) return false;
+    ConvArgs a;
+    a.N = N; a.H = H; a.W = W; a.Ho = H; a.Wo = W; a.Cin = w.cin; a.Cout = w.cout; a.ksize = w.k; a.mode = CONV_SAME;
+    return tc_can_xform(a);
+  }
+  // (N, H, W): shape of block i's output
+  bool next_takes_planes(const std::vector<Block>& bl, size_t i, bool last_is_simt, int N, int H, int W) const {
+    if (i + 1 >= bl.size()) return false;
+    const Block& nb = bl[i + 1];
+    if (nb.kind == B_DOWN || nb.kind == B_UP) return true;
+    if (nb.kind == B_RES) return nb.res_w.has_out || xf_ok(N, H, W, nb.res_w.c1);
+    if (nb.kind == B_NORM && i + 2 < bl.size() && bl[i + 2].kind == B_CONV)
+      return !(last_is_simt && i + 3 == bl.size()) && xf_ok(N, H, W, bl[i + 2].conv);
+    return false;
   }
 
   // Encoder.forward (+ the taps of codeformer_arch.py:226-230).  x_nchw is the caller's image.
@@ -623,15 +682,10 @@ struct Fwd {
     }
     CFB_CHECK(capture("enc.0", x));
     float *ps = nullptr, *ph = nullptr;   // pending GroupNorm of a 'norm' block
-    // does the block after i read its input raw through a conv (Down/Upsample conv, or a ResBlock's 1x1 conv_out)?
-    auto next_raw = [](const std::vector<Block>& bl, size_t i) {
-      if (i + 1 >= bl.size()) return false;
-      const Block& nb = bl[i + 1];
-      return nb.kind == B_DOWN || nb.kind == B_UP || (nb.kind == B_RES && nb.res_w.has_out);
-    };
     for (size_t i = 1; i < n->enc.size(); ++i) {
       const Block& b = n->enc[i];
-      const bool pl = next_raw(n->enc, i);
+      const int oh = b.kind == B_DOWN ? x.H / 2 : x.H, ow = b.kind == B_DOWN ? x.W / 2 : x.W;
+      const bool pl = next_takes_planes(n->enc, i, false, x.N, oh, ow);
       Tensor y;
       switch (b.kind) {
         case B_RES: CFB_CHECK(resblock(b.res_w, x, y, pl)); break;
@@ -662,11 +716,11 @@ struct Fwd {
     float *ps = nullptr, *ph = nullptr;
     for (size_t i = 0; i < n->gen.size(); ++i) {
       const Block& b = n->gen[i];
-      bool pl = false;
-      if (i + 1 < n->gen.size()) {
-        const Block& nb = n->gen[i + 1];
-        pl = nb.kind == B_DOWN || nb.kind == B_UP || (nb.kind == B_RES && nb.res_w.has_out);
-      }
+      const int oh = b.kind == B_UP ? x.H * 2 : x.H, ow = b.kind == B_UP ? x.W * 2 : x.W;
+      bool pl = next_takes_planes(n->gen, i, true, x.N, oh, ow);
+      if (taps && w > 0.f)
+        for (int fb : fuse_blocks)
+          if ((int)i == fb) pl = false;      // consumed by the fusion (concat + SFT read fp32); the fused output emits its own
       Tensor y;
       switch (b.kind) {
         case B_RES: CFB_CHECK(resblock(b.res_w, x, y, pl)); break;
@@ -683,7 +737,7 @@ struct Fwd {
             release(x);
             return 0;
           } else {
-            ConvOpt o; o.in_scale = ps; o.in_shift = ph; o.want_stats = true;
+            ConvOpt o; o.in_scale = ps; o.in_shift = ph; o.want_stats = true; o.want_planes = pl;
             CFB_CHECK(conv(b.conv, x, y, o));
             if (ps) { release_raw(ps); release_raw(ph); ps = ph = nullptr; }
           }
