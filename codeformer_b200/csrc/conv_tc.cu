@@ -21,8 +21,14 @@
 //     converged with elect.sync-predicated issue; warps 2..9 = epilogue (tcgen05.ld -> fold -> per-warp swizzled smem
 //     transpose -> bias / residual / activation / SFT -> coalesced fp32 NHWC stores, optional fp16 hi/lo planes for a
 //     raw-input consumer, GroupNorm(32) partial sums);
-//   * an optional "halo" engine (HALO=true, CFB_TC_HALO=1) fetches each (18x10) input patch once and serves the 9 taps
-//     through row-shifted descriptors (see the comment at tc_geometry for why it is off by default).
+//   * default engine = CTA PAIR + HALO (PAIR / HALO template flags): two CTAs of a cluster (one TPC) own adjacent 8x16-pixel
+//     tiles and share the weights through tcgen05.mma.cta_group::2 (M = 256): no single-CTA instruction floor, each CTA
+//     stages half of every B operand, commits are multicast to both CTAs, both CTAs' TMA bytes are counted on the leader's
+//     mbarrier; the (10x18) input patch of a 64-channel block is fetched ONCE and the taps read it through row-shifted
+//     128B-swizzled descriptors (see the comments at TcCfg and tc_geometry; probes in tools/umma_*.py);
+//   * optional in-kernel operand transform (XF): the patches arrive as RAW planes emitted by the producing conv's epilogue
+//     and four transform warps apply GroupNorm-affine + SiLU + the hi/lo re-split in place before the MMAs read them
+//     (tc_can_xform says where it is used); the same kernel also runs the AttnBlock score / P.V GEMMs (bmm_tc).
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
