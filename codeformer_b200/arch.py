@@ -405,6 +405,21 @@ class _FuseSft(_ParamsOnly):
         self.shift = nn.ModuleDict({'0': _Conv(c, c, 3), '2': _Conv(c, c, 3)})
 
 
+def restore_chunks(n_faces, max_batch):
+    """Chunk plan of ``CodeFormer.restore_faces``: consecutive [lo, hi) ranges of <= max_batch faces; a chunk of >= 16 faces
+    is split in two so the host-side staging of one half overlaps the GPU work of the other."""
+    bounds = []
+    max_batch = max(1, int(max_batch))
+    for lo in range(0, n_faces, max_batch):
+        hi = min(n_faces, lo + max_batch)
+        if hi - lo >= 16:
+            mid = lo + (hi - lo + 1) // 2
+            bounds += [(lo, mid), (mid, hi)]
+        else:
+            bounds.append((lo, hi))
+    return bounds
+
+
 @ARCH_REGISTRY.register()
 class CodeFormer(VQAutoEncoder):
     """Mirror of ``CodeFormer`` (codeformer_arch.py:160-280)."""
@@ -612,14 +627,7 @@ class CodeFormer(VQAutoEncoder):
         self.last_restore_errors = []
         # chunks of <= max_batch faces; a chunk of >= 16 is split in two so that the host-side staging copies of one half
         # overlap the GPU work of the other (per-face GPU time is flat above 16 faces)
-        bounds = []
-        for lo in range(0, arr.shape[0], max_batch):
-            hi = min(arr.shape[0], lo + max_batch)
-            if hi - lo >= 16:
-                mid = lo + (hi - lo + 1) // 2
-                bounds += [(lo, mid), (mid, hi)]
-            else:
-                bounds.append((lo, hi))
+        bounds = restore_chunks(arr.shape[0], max_batch)
         results = [None] * len(bounds)
         pending = []                                   # (chunk index, pinned output, event) in flight on the stream
 

@@ -56,3 +56,17 @@ def test_two_rank_gloo_gather_is_bit_identical(batch):
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, port, batch, ret), nprocs=2, join=True)
     assert ret[0] and ret[1]
+
+
+def test_restore_faces_chunk_plan():
+    """Host logic of the batched caller loop: chunks cover every face once, in order, within max_batch."""
+    from codeformer_b200.arch import restore_chunks
+    assert restore_chunks(0, 32) == []
+    assert restore_chunks(7, 3) == [(0, 3), (3, 6), (6, 7)]
+    assert restore_chunks(32, 32) == [(0, 16), (16, 32)]
+    assert restore_chunks(33, 32) == [(0, 16), (16, 32), (32, 33)]
+    for n in (1, 5, 15, 16, 17, 31, 64, 100):
+        for mb in (1, 4, 16, 32):
+            b = restore_chunks(n, mb)
+            assert b[0][0] == 0 and b[-1][1] == n and all(x[1] == y[0] for x, y in zip(b, b[1:]))
+            assert all(0 < hi - lo <= mb for lo, hi in b)
