@@ -60,6 +60,9 @@ SIGNATURES = {
     'cfb_debug_umma_rate': (c_int, [c_int32, c_int32, c_int32, _P, c_int32, _P]),
     'cfb_debug_time_conv': (c_int, [_P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P, c_int64,
                                    _P, POINTER(c_float)]),
+    'cfb_check_async_status': (c_int, []),
+    'cfb_debug_set_wait_limit': (c_int, [c_int64]),
+    'cfb_debug_inject_fault': (c_int, [c_int32]),
     'cfb_nchw_to_nhwc': (c_int, [_P, _P, c_int32, c_int32, c_int32, _P]),
     'cfb_nhwc_to_nchw': (c_int, [_P, _P, c_int32, c_int32, c_int32, _P]),
 }
@@ -74,10 +77,11 @@ def load():
         return _lib
     if not os.path.exists(LIB_PATH):
         # a fresh checkout has no binary: compile the CUDA sources in-tree (nvcc, sm_100a).  Never a CPU/PyTorch fallback:
-        # if that is impossible the import fails loudly.
+        # if that is impossible the import fails loudly.  build() serialises concurrent importers (torchrun ranks, xdist
+        # workers) on a file lock and publishes the library with an atomic rename.
         try:
             from . import build as _build
-            _build.build(force=True)
+            _build.build(force=False)
         except Exception as e:  # noqa: BLE001
             raise RuntimeError(f'{LIB_PATH} is missing and could not be built with nvcc ({e}); there is no CPU or '
                                'PyTorch fallback for this path -- run `python -m codeformer_b200.build`') from e

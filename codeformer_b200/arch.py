@@ -348,9 +348,10 @@ class VQAutoEncoder(nn.Module):
         return 0 if self._cfb_net is None else int(_lib.load().cfb_last_launch_count(self._cfb_net))
 
     # ---- VQAutoEncoder.forward  vqgan_arch.py:385-389 -------------------------------------------
-    def forward(self, x, return_min_encodings=False):
-        """-> (x_hat [B,3,H,W], codebook_loss, {perplexity, min_encodings, min_encoding_indices, mean_distance}).
-        ``min_encodings`` (the [B*256, K] one-hot, 4 MB per face) is materialised only on request."""
+    def forward(self, x, return_min_encodings=True):
+        """-> (x_hat [B,3,H,W], codebook_loss, {perplexity, min_encodings, min_encoding_indices, mean_distance}), exactly
+        the reference's tuple (vqgan_arch.py:65-70,385-389).  ``min_encodings`` is the [B*256, K] one-hot (1 MB per face);
+        callers that only index ``[0]`` (scripts/inference_vqgan.py:46) may pass ``return_min_encodings=False`` to skip it."""
         x = self._check_input(x)
         lib = _lib.load()
         B = x.shape[0]
@@ -508,16 +509,17 @@ class CodeFormer(VQAutoEncoder):
     # small launches and launch latency dominates.  Small batches are therefore replayed from a CUDA graph captured once
     # per (batch, w, adain, code_only): static input/output buffers, same kernels, same results.
     cuda_graph_max_batch = 4
+    cuda_graph_cache_size = 6
 
     def _cfb_forward_graphed(self, x, w, adain, code_only):
         lib = _lib.load()
         dev = x.device
         B = x.shape[0]
         key = (dev.index, B, w, adain, code_only)
-        ent = self._cfb_graphs.get(key)
+        ent = self._cfb_graphs.pop(key, None)                # re-inserted below: dict order = least recently used first
         if ent is None:
-            if len(self._cfb_graphs) >= 8:                   # callers sweep w: keep the cache bounded
-                self._cfb_graphs.clear()
+            while len(self._cfb_graphs) >= self.cuda_graph_cache_size:      # callers sweep w (Gradio slider): evict the LRU
+                self._cfb_graphs.pop(next(iter(self._cfb_graphs)))          # entry only; each pins one workspace
             sx = torch.empty_like(x)
             logits = torch.empty((B, self.latent_size, self.codebook_size), dtype=torch.float32, device=dev)
             lq = torch.empty((B, 256, 16, 16), dtype=torch.float32, device=dev)
@@ -539,7 +541,7 @@ class CodeFormer(VQAutoEncoder):
                 self._cfb_graphs[key] = False
                 return None
             ent = (g, sx, out, logits, lq, ws)
-            self._cfb_graphs[key] = ent
+        self._cfb_graphs[key] = ent
         if ent is False:
             return None
         g, sx, out, logits, lq, ws = ent
@@ -576,10 +578,10 @@ class CodeFormer(VQAutoEncoder):
                 and not getattr(self, '_cfb_hooks', None) and not torch.cuda.is_current_stream_capturing()
             if graph_ok:
                 key = ('u8', dev.index, B, w, adain)
-                ent = self._cfb_graphs.get(key)
+                ent = self._cfb_graphs.pop(key, None)
                 if ent is None:
-                    if len(self._cfb_graphs) >= 8:
-                        self._cfb_graphs.clear()
+                    while len(self._cfb_graphs) >= self.cuda_graph_cache_size:
+                        self._cfb_graphs.pop(next(iter(self._cfb_graphs)))
                     src, dst = torch.empty_like(faces_bgr), torch.empty_like(faces_bgr)
                     ws = torch.empty(int(lib.cfb_workspace_bytes(self._cfb_net, B)), dtype=torch.uint8, device=dev)
                     src.copy_(faces_bgr)
@@ -592,7 +594,7 @@ class CodeFormer(VQAutoEncoder):
                         ent = (g, src, dst, ws)
                     except Exception:
                         ent = False
-                    self._cfb_graphs[key] = ent
+                self._cfb_graphs[key] = ent
                 if ent:
                     g, src, dst, _ = ent
                     src.copy_(faces_bgr)
@@ -637,6 +639,9 @@ class CodeFormer(VQAutoEncoder):
                 lo, hi = bounds[k]
                 try:
                     ev.synchronize()
+                    # kernels report a pipeline time-out / fp16 operand overflow through a status word instead of
+                    # trapping: turn it into the exception the reference's per-face fallback expects
+                    _lib.check(_lib.load().cfb_check_async_status(), 'restore_faces')
                     results[k] = pout.numpy().copy()
                 except RuntimeError as err:
                     if on_error == 'raise':

@@ -16,17 +16,39 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, '..', 'include', 'cfb200.h'), __file__]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cu', '.cuh'))] + \
+           [os.path.join(HERE, '..', 'include', 'cfb200.h'), __file__]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
 def build(force=False, verbose=False):
+    """Compile the three translation units and link libcfb200.so.  Safe to call from several processes at once: the build
+    runs under an exclusive file lock, objects go to a per-process directory and the library is published with os.replace
+    (a concurrent CDLL never sees a half-written file)."""
+    import fcntl
+    import shutil
+    import tempfile
     if not force and not needs_build():
         return LIB
+    with open(os.path.join(HERE, '.build.lock'), 'w') as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():      # another process built it while we waited for the lock
+                return LIB
+            tmp = tempfile.mkdtemp(prefix='cfb_build_', dir=CSRC)
+            try:
+                return _build_locked(tmp, verbose)
+            finally:
+                shutil.rmtree(tmp, ignore_errors=True)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(objdir, verbose):
     objs = []
     procs = []
     for s in SOURCES:
-        o = os.path.join(CSRC, s.replace('.cu', '.o'))
+        o = os.path.join(objdir, s.replace('.cu', '.o'))
         cmd = [NVCC] + FLAGS + ['-c', os.path.join(CSRC, s), '-o', o]
         if verbose:
             print(' '.join(cmd), flush=True)
@@ -40,8 +62,10 @@ def build(force=False, verbose=False):
         fail = fail or p.returncode != 0
     if fail:
         raise RuntimeError('nvcc failed')
-    cmd = [NVCC, '-shared', '-o', LIB] + objs + ['-lcudart']
+    staged = os.path.join(objdir, 'libcfb200.so')
+    cmd = [NVCC, '-shared', '-o', staged] + objs + ['-lcudart']
     subprocess.check_call(cmd)
+    os.replace(staged, LIB)
     return LIB
 
 

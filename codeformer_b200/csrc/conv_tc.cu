@@ -36,6 +36,7 @@
 
 #include <stdlib.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "conv_tc.cuh"
@@ -144,6 +145,8 @@ int tc_split_weights_up4(const float* oihw3x3, __half* hi, __half* lo, int Cout,
   return 0;
 }
 
+__device__ void report_overflow();       // status word, defined with the barrier helpers below
+
 // ------------------------------------------------------------------------------------------------------
 // operand preparation: fp32 NHWC (+ fused GroupNorm affine, SiLU, nearest x2) -> fp16 hi / lo NHWC planes
 // ------------------------------------------------------------------------------------------------------
@@ -170,6 +173,7 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const float* __restrict__ 
     sv[0] = s0.x; sv[1] = s0.y; sv[2] = s0.z; sv[3] = s0.w; sv[4] = s1.x; sv[5] = s1.y; sv[6] = s1.z; sv[7] = s1.w;
     hv[0] = h0.x; hv[1] = h0.y; hv[2] = h0.z; hv[3] = h0.w; hv[4] = h1.x; hv[5] = h1.y; hv[6] = h1.z; hv[7] = h1.w;
   }
+  float vmax = 0.f;
   for (int pl = threadIdx.x / C8; pl < PB; pl += pstep) {
     const int64_t pix = pix0 + pl;
     const int64_t rem = pix - (int64_t)n * img_px;
@@ -190,12 +194,14 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const float* __restrict__ 
     __align__(16) __half ll[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
+      vmax = fmaxf(vmax, fabsf(v[j]));
       hh[j] = __float2half_rn(v[j]);
       ll[j] = __float2half_rn(v[j] - __half2float(hh[j]));
     }
     *reinterpret_cast<uint4*>(hi + pix * C + c) = *reinterpret_cast<const uint4*>(hh);
     *reinterpret_cast<uint4*>(lo + pix * C + c) = *reinterpret_cast<const uint4*>(ll);
   }
+  if (vmax > 65504.f) report_overflow();       // fp16 operand range guard: reported through the status word, never silent
 }
 
 // torch.cat([enc_feat, dec], dim=1) of Fuse_sft_block (codeformer_arch.py:152) written directly as RAW fp16 hi/lo operand
@@ -206,6 +212,7 @@ __global__ void __launch_bounds__(256) concat_planes_kernel(const float* __restr
                                                             int Ca, int Cb) {
   const int C8 = (Ca + Cb) >> 3;
   const int64_t total = pixels * C8;
+  float vmax = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t px = i / C8;
     const int c = (int)(i - px * C8) * 8;
@@ -216,12 +223,14 @@ __global__ void __launch_bounds__(256) concat_planes_kernel(const float* __restr
     __align__(16) __half ll[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
+      vmax = fmaxf(vmax, fabsf(v[j]));
       hh[j] = __float2half_rn(v[j]);
       ll[j] = __float2half_rn(v[j] - __half2float(hh[j]));
     }
     *reinterpret_cast<uint4*>(hi + px * (Ca + Cb) + c) = *reinterpret_cast<const uint4*>(hh);
     *reinterpret_cast<uint4*>(lo + px * (Ca + Cb) + c) = *reinterpret_cast<const uint4*>(ll);
   }
+  if (vmax > 65504.f) report_overflow();
 }
 int concat_planes(const float* a, const float* b, void* planes, int64_t pixels, int Ca, int Cb, cudaStream_t st) {
   CFB_REQUIRE(Ca % 8 == 0 && Cb % 8 == 0, "concat_planes: channel counts must be multiples of 8");
@@ -249,10 +258,27 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Bounded wait: a protocol bug must surface as a trap (-> cudaError, Python exception), never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// Bounded wait without a trap.  A protocol bug (or an injected fault) must surface as a Python exception, never as a hung
+// GPU and never as a sticky context error (SURVEY.md section 8(b) "Errors": the reference's callers catch RuntimeError and
+// fall back to the input face, inference_codeformer.py:209-211).  On time-out the waiting thread raises the device-wide
+// abort flag and reports through the host-mapped status word; every other wait loop sees the flag after its next failed
+// try_wait and falls through, the roles run their loops to the end without blocking, the kernel exits normally and the host
+// turns the status word into an error (runtime.cu: async_status_check).  The results of that launch are garbage by contract.
+__device__ unsigned g_abort = 0;                 // per device: set on a barrier time-out, cleared by the host when it reports it
+__device__ unsigned* g_status_host = nullptr;    // host-mapped status word (bit 0: barrier time-out, bit 1: fp16 operand overflow)
+__device__ long long g_wait_limit = 4000000000LL;   // cycles (~2 s); the fault-injection test lowers it
+
+__device__ __noinline__ void mbar_timeout() {
+  atomicExch(&g_abort, 1u);
+  if (g_status_host) { atomicOr_system(g_status_host, CFB_STATUS_TIMEOUT); __threadfence_system(); }
+}
+__device__ __noinline__ void report_overflow() {
+  if (g_status_host) { atomicOr_system(g_status_host, CFB_STATUS_OVERFLOW); __threadfence_system(); }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, bool& aborted) {
+  if (aborted) return;                     // this thread has seen the abort: run the role loop to its end without blocking
   uint32_t done = 0;
-  const long long t0 = clock64();
+  long long t0 = 0;
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -262,9 +288,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity), "r"(0x989680u)
         : "memory");
     if (done) break;
-    if (clock64() - t0 > 4000000000LL) __trap();
+    if (*(volatile unsigned*)&g_abort) { aborted = true; break; }   // slow path only: a healthy wait succeeds on its first try_wait
+    if (t0 == 0) t0 = clock64();
+    else if (clock64() - t0 > *(volatile long long*)&g_wait_limit) { mbar_timeout(); aborted = true; break; }
   }
 }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { bool a = false; mbar_wait(bar, parity, a); }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -372,9 +401,10 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 // wait on a LOCAL barrier whose arrivals may come from the peer CTA (cluster-scope acquire)
-__device__ __forceinline__ void mbar_wait_cl(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_cl(uint32_t bar, uint32_t parity, bool& aborted) {
+  if (aborted) return;
   uint32_t done = 0;
-  const long long t0 = clock64();
+  long long t0 = 0;
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -384,7 +414,9 @@ __device__ __forceinline__ void mbar_wait_cl(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity), "r"(0x989680u)
         : "memory");
     if (done) break;
-    if (clock64() - t0 > 4000000000LL) __trap();
+    if (*(volatile unsigned*)&g_abort) { aborted = true; break; }
+    if (t0 == 0) t0 = clock64();
+    else if (clock64() - t0 > *(volatile long long*)&g_wait_limit) { mbar_timeout(); aborted = true; break; }
   }
 }
 // TMA loads of a CTA pair: data lands in the issuing CTA's shared memory, the byte count is signalled on `cluster_bar`,
@@ -403,6 +435,100 @@ __device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap
 }
 
 // ------------------------------------------------------------------------------------------------------
+// fused operand transform: per-patch worker of the transform warps (see conv_tc_kernel, XF)
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_ftz(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_ftz(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {      // {hi:16 | lo:16}, round to nearest even
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// float(h) - c as ONE mixed-precision instruction (FHADD); h = fp16 bits
+__device__ __forceinline__ float f16_minus_f32(uint32_t h, float c) {
+  float r;
+  asm("{\n\t.reg .b16 hh;\n\tcvt.u16.u32 hh, %1;\n\tsub.rn.f32.f16 %0, hh, %2;\n\t}" : "=f"(r) : "r"(h), "f"(c));
+  return r;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// 8 raw values -> y = act(x * sc + sh) -> fp16 hi / lo words.  MODE 2: affine + SiLU, 1: affine, 0: plain split.
+// SiLU = y / (1 + 2^(-y log2 e)) with ex2.approx / rcp.approx (~2^-21 relative: below the hi/lo operand error of 2^-22..2^-21).
+// lo = rn(y - hi) is formed as -(hi - y) with one mixed-precision subtract per element and a sign flip of the packed pair.
+template <int MODE>
+__device__ __forceinline__ void xf_chunk(const uint4& a, const uint4& b, const float (&sc)[8], const float (&sh)[8], uint4& hv,
+                                         uint4& lv, float& amax) {
+  const uint32_t raw[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  uint32_t hw[4], lw[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float y[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      float v = __uint_as_float(raw[2 * q + e]);
+      if (MODE >= 1) v = fmaf(v, sc[2 * q + e], sh[2 * q + e]);
+      if (MODE == 2) v = v * rcp_ftz(1.f + ex2_ftz(v * -1.4426950408889634f));
+      y[e] = v;
+    }
+    amax = fmaxf(amax, fmaxf(fabsf(y[0]), fabsf(y[1])));
+    hw[q] = pack_f16x2(y[0], y[1]);
+    const float d0 = f16_minus_f32(hw[q] & 0xffffu, y[0]);      // hi - y = -lo
+    const float d1 = f16_minus_f32(hw[q] >> 16, y[1]);
+    lw[q] = pack_f16x2(d0, d1) ^ 0x80008000u;
+  }
+  hv = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+  lv = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+}
+// One patch: RPP rows per pass (8 lanes per row), two passes in flight per iteration.
+template <int MODE, int RPP, int NPASS, int PW, int ROWS>
+__device__ __forceinline__ void xf_patch(uint32_t src_base, uint32_t hi_base, uint32_t lo_base, int c0, int j, int rsub,
+                                         const float (&sc)[8], const float (&sh)[8], bool border, int y0, int x0, int Hin,
+                                         int Win, float& amax) {
+#pragma unroll
+  for (int it = 0; it < NPASS; it += 2) {
+    uint4 a[2], b[2];
+    bool act[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int r = rsub + (it + u) * RPP;
+      act[u] = (it + u < NPASS) && (r < ROWS);                 // warp-uniform: a warp owns 4 consecutive rows and ROWS % 4 == 0
+      if (act[u]) {
+        const uint32_t row = src_base + (uint32_t)r * 128u;
+        const uint32_t sw = (row >> 7) & 7u;                    // swizzle phase = absolute address bits [7,10)
+        a[u] = lds128(row + (((uint32_t)c0 ^ sw) << 4));
+        b[u] = lds128(row + (((uint32_t)(c0 + 1) ^ sw) << 4));
+      }
+    }
+    __syncwarp();                                              // every lane of the row has loaded before any lane stores
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (act[u]) {
+        const int r = rsub + (it + u) * RPP;
+        uint4 hv, lv;
+        xf_chunk<MODE>(a[u], b[u], sc, sh, hv, lv, amax);
+        if (border) {
+          const int py = r / PW, px = r - py * PW;
+          if (!((unsigned)(y0 + py) < (unsigned)Hin && (unsigned)(x0 + px) < (unsigned)Win)) {
+            hv = make_uint4(0u, 0u, 0u, 0u);
+            lv = make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+        const uint32_t hrow = hi_base + (uint32_t)r * 128u, lrow = lo_base + (uint32_t)r * 128u;
+        sts128(hrow + ((((uint32_t)j) ^ ((hrow >> 7) & 7u)) << 4), hv);
+        sts128(lrow + ((((uint32_t)j) ^ ((lrow >> 7) & 7u)) << 4), lv);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------
 struct TcParams {
@@ -417,6 +543,9 @@ struct TcParams {
   int b_batched;          // B operand is a per-image activation plane: third TMA coordinate = image index, not the tap
   int up4;                // Upsample as four 2x2 convs: m-tile = (low-res tile, output parity), 4 taps, weights [16][Cout][Cin]
   int PW, PH;             // halo engine: input patch (BW+k-1) x (BH+k-1) pixels fetched once per 64-channel block
+  int fault;              // test hook (cfb_debug_inject_fault): CTA 0 drops the weight load of its first stage -> barrier time-out
+  int xform;              // XF kernel variant requested (in_scale may be null: raw split)
+  int a_split;            // XF: k-blocks [0, a_split) are read from fp32 source 0 (tmA_hi), the rest from source 1 (tmA_lo)
   const float* in_scale;    // XF: per-(n, cin) affine of the fused operand transform (GroupNorm folded), and its activation
   const float* in_shift;
   int in_act;
@@ -436,8 +565,9 @@ struct TcParams {
 
 constexpr int TC_EPI_WARPS = 8;                       // 4 TMEM lane quadrants x 2 column halves
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // warp0 TMA, warp1 MMA, warps 2..9 epilogue
-constexpr int TC_XF_WARPS = 4;                        // XF: warps 10..13 transform the A patches, warp 14 loads them
-constexpr int TC_THREADS_XF = TC_THREADS + 32 * TC_XF_WARPS + 32;
+// XF (fused operand transform): warps 10.. transform the A patches, the warp after them loads the raw patches.  The
+// 64-wide layers (one k-block per tile at Cin = 64: 4.1k cycles of MMA per patch) get 8 transform warps, the 128-wide 4.
+constexpr int XF_SKEW = 128;                          // byte skew of the second patch plane (see the transform warps)
 constexpr int TC_A_BYTES = 128 * 128;                 // 128 pixels x 64 fp16
 
 template <int BN>
@@ -478,7 +608,10 @@ struct TcCfg {
   // fused operand transform (XF, halo + pair only): the A patches arrive as RAW fp16 hi/lo planes of the producing conv's
   // output and four transform warps apply GroupNorm-affine + SiLU + the hi/lo re-split in place before the MMAs read them;
   // one more A slot for the short-K (Cin = 64) layers, whose MMA time per patch is below TMA + transform latency
+  static constexpr int XF_WARPS = (BN == 64) ? 8 : 4;
+  static constexpr int XF_THREADS = TC_THREADS + 32 * XF_WARPS + 32;
   static constexpr int X_A_SLOTS = (BN == 64) ? 3 : 2;
+  static constexpr int X_A_PLANE2 = H_A_PLANE + XF_SKEW;   // second plane of an XF slot (ends at 46720 <= H_A_SLOT)
   static constexpr int X_B_SLOTS = 4;
   static constexpr int X_SMEM_BYTES = X_A_SLOTS * H_A_SLOT + X_B_SLOTS * HP_B_SLOT + 1024 + 512 + STG_BYTES;
 };
@@ -495,7 +628,7 @@ struct TcCfg {
 // barriers collect the TMA bytes / epilogue arrivals of both CTAs; `empty` and `cfull` are signalled in both CTAs by
 // multicast commits.
 template <int BN, int CPG, bool HALO, bool PAIR, bool XF>
-__global__ void __launch_bounds__(XF ? TC_THREADS_XF : TC_THREADS, 1)
+__global__ void __launch_bounds__(XF ? TcCfg<BN>::XF_THREADS : TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                const __grid_constant__ CUtensorMap tmB_half, const TcParams p) {
@@ -527,10 +660,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
+  bool aborted = false;      // set when a barrier wait timed out anywhere on the device: finish without blocking (see mbar_wait)
 
   if (warp == 0 && lane == 0) {
     for (int a = 0; a < 3; ++a) {
-      mbar_init(smem_u32(afull + a), XF ? 2 * TC_XF_WARPS : 1);      // XF: the transform warps of both CTAs arrive on the leader
+      mbar_init(smem_u32(afull + a), XF ? 2 * TcCfg<BN>::XF_WARPS : 1);      // XF: the transform warps of both CTAs arrive on the leader
       mbar_init(smem_u32(aempty + a), 1);
       mbar_init(smem_u32(araw + a), 1);
     }
@@ -595,7 +729,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if constexpr (HALO) {
           for (int kb = 0; kb < p.kblocks; ++kb) {
             if constexpr (!XF) {
-            mbar_wait(smem_u32(aempty + aslot), aphase ^ 1);
+            mbar_wait(smem_u32(aempty + aslot), aphase ^ 1, aborted);
             if (elect_one()) {
               const uint32_t sa = smem_u32(smem + aslot * Cfg::H_A_SLOT);
               if constexpr (PAIR) {
@@ -615,13 +749,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
             for (int tap = 0; tap < p.taps; ++tap) {
               const int btap = p.up4 ? (mt & 3) * 4 + tap : tap;      // Upsample: weight slice of this output parity
-              mbar_wait(smem_u32(empty + stage), phase ^ 1);
+              mbar_wait(smem_u32(empty + stage), phase ^ 1, aborted);
               if (elect_one()) {
                 const uint32_t sb = smem_u32(ring_base + stage * RING_BYTES);
                 if constexpr (PAIR) {
                   if (rank == 0) mbar_expect_tx(smem_u32(full + stage), (uint32_t)(2 * Cfg::HP_B_SLOT));
                   const uint32_t fb = map_to_cta(smem_u32(full + stage), rank0);
-                  tma_load_3d_pair(sb, rank == 0 ? &tmB_hi : &tmB_lo, fb, kb * 64, nt * BN, btap);
+                  const bool drop = p.fault && blockIdx.x == 0 && tile == first_tile && kb == 0 && tap == 0;   // injected fault
+                  if (!drop) tma_load_3d_pair(sb, rank == 0 ? &tmB_hi : &tmB_lo, fb, kb * 64, nt * BN, btap);
                   tma_load_3d_pair(sb + Cfg::P_BX_BYTES, &tmB_half, fb, kb * 64, nt * BN + (int)rank * (BN / 2), btap);
                 } else {
                   const uint32_t fb = smem_u32(full + stage);
@@ -641,7 +776,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             if (p.up4) { r = (tap >> 1) + par_y; s = (tap & 1) + par_x; btap = (mt & 3) * 4 + tap; }
             else { r = (p.taps == 9) ? tap / 3 : 0; s = (p.taps == 9) ? tap - r * 3 : 0; }
             for (int kb = 0; kb < p.kblocks; ++kb) {
-              mbar_wait(smem_u32(empty + stage), phase ^ 1);
+              mbar_wait(smem_u32(empty + stage), phase ^ 1, aborted);
               if (elect_one()) {
                 const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
                 const int b3 = p.b_batched ? n : btap;
@@ -698,15 +833,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               const int par_y = par >> 1, par_x = par & 1;
               int it = 0;
               for (int kb = 0; kb < p.kblocks; ++kb) {
-                mbar_wait_cl(smem_u32(afull + aslot), aphase);
-                const uint32_t a_hi0 = smem_u32(smem + aslot * Cfg::H_A_SLOT), a_lo0 = a_hi0 + Cfg::H_A_PLANE;
+                mbar_wait_cl(smem_u32(afull + aslot), aphase, aborted);
+                const uint32_t a_hi0 = smem_u32(smem + aslot * Cfg::H_A_SLOT), a_lo0 = a_hi0 + (XF ? Cfg::X_A_PLANE2 : Cfg::H_A_PLANE);
                 for (int tap = 0; tap < p.taps; ++tap, ++it) {
                   int r = (p.taps == 9) ? tap / 3 : 0;
                   int sft = (p.taps == 9) ? tap - r * 3 : 0;
                   if (p.up4) { r = (tap >> 1) + par_y; sft = (tap & 1) + par_x; }
                   const bool first = (it % p.chunk) == 0;
-                  if (first) mbar_wait_cl(smem_u32(cempty + slot), slot_phase ^ 1);
-                  mbar_wait_cl(smem_u32(full + stage), phase);
+                  if (first) mbar_wait_cl(smem_u32(cempty + slot), slot_phase ^ 1, aborted);
+                  mbar_wait_cl(smem_u32(full + stage), phase, aborted);
                   tc_fence_after();
                   if (elect_one()) {
                     const uint32_t d_tmem = tmem_base + (uint32_t)(slot * Cfg::SLOT_COLS);
@@ -739,15 +874,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const int par_y = par >> 1, par_x = par & 1;
           int it = 0;
           for (int kb = 0; kb < p.kblocks; ++kb) {
-            mbar_wait(smem_u32(afull + aslot), aphase);
+            mbar_wait(smem_u32(afull + aslot), aphase, aborted);
             const uint32_t a_hi0 = smem_u32(smem + aslot * Cfg::H_A_SLOT), a_lo0 = a_hi0 + Cfg::H_A_PLANE;
             for (int tap = 0; tap < p.taps; ++tap, ++it) {
               int r = (p.taps == 9) ? tap / 3 : 0;
               int sft = (p.taps == 9) ? tap - r * 3 : 0;
               if (p.up4) { r = (tap >> 1) + par_y; sft = (tap & 1) + par_x; }
               const bool first = (it % p.chunk) == 0;
-              if (first) mbar_wait(smem_u32(cempty + slot), slot_phase ^ 1);
-              mbar_wait(smem_u32(full + stage), phase);
+              if (first) mbar_wait(smem_u32(cempty + slot), slot_phase ^ 1, aborted);
+              mbar_wait(smem_u32(full + stage), phase, aborted);
               tc_fence_after();
               if (elect_one()) {
                 const uint32_t d_tmem = tmem_base + (uint32_t)(slot * Cfg::SLOT_COLS);
@@ -781,10 +916,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (rank == 0) {
           for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
             for (int it0 = 0; it0 < nk; it0 += p.chunk) {
-              mbar_wait_cl(smem_u32(cempty + slot), slot_phase ^ 1);
+              mbar_wait_cl(smem_u32(cempty + slot), slot_phase ^ 1, aborted);
               const int it1 = (it0 + p.chunk < nk) ? it0 + p.chunk : nk;
               for (int it = it0; it < it1; ++it) {
-                mbar_wait_cl(smem_u32(full + stage), phase);
+                mbar_wait_cl(smem_u32(full + stage), phase, aborted);
                 tc_fence_after();
                 if (elect_one()) {
                   const uint32_t d_tmem = tmem_base + (uint32_t)(slot * Cfg::SLOT_COLS);
@@ -809,10 +944,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       } else {
         for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
           for (int it0 = 0; it0 < nk; it0 += p.chunk) {
-            mbar_wait(smem_u32(cempty + slot), slot_phase ^ 1);
+            mbar_wait(smem_u32(cempty + slot), slot_phase ^ 1, aborted);
             const int it1 = (it0 + p.chunk < nk) ? it0 + p.chunk : nk;
             for (int it = it0; it < it1; ++it) {
-              mbar_wait(smem_u32(full + stage), phase);
+              mbar_wait(smem_u32(full + stage), phase, aborted);
               tc_fence_after();
               if (elect_one()) {
                 const uint32_t d_tmem = tmem_base + (uint32_t)(slot * Cfg::SLOT_COLS);
@@ -834,8 +969,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
       }
     }
-  } else if (XF && warp == 2 + TC_EPI_WARPS + TC_XF_WARPS) {
+  } else if (XF && warp == 2 + TC_EPI_WARPS + TcCfg<BN>::XF_WARPS) {
     // ============================ XF: A-patch loader (own warp: patches must be requested a whole patch ahead) ==========
+    // The patch of one 64-channel block arrives as RAW fp32 NHWC values of the producing conv's output: two TMA boxes of
+    // 32 channels (128 B rows, 128B swizzle) into the two planes of the slot.  tmA_hi / tmA_lo are the fp32 tensor maps of
+    // source 0 / source 1: the k-blocks [0, a_split) come from source 0, the rest from source 1 -- torch.cat([enc, dec])
+    // of Fuse_sft_block (codeformer_arch.py:152) never exists in memory.
     if constexpr (XF) {
       int aslot = 0;
       uint32_t aphase = 0;
@@ -847,13 +986,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
         const int y0 = ty * p.BH, x0 = tx * p.BW;
         for (int kb = 0; kb < p.kblocks; ++kb) {
-          mbar_wait(smem_u32(aempty + aslot), aphase ^ 1);       // every MMA that read this slot has completed
+          mbar_wait(smem_u32(aempty + aslot), aphase ^ 1, aborted);       // every MMA that read this slot has completed
           if (elect_one()) {
             const uint32_t sa = smem_u32(smem + aslot * Cfg::H_A_SLOT);
             const uint32_t rb = smem_u32(araw + aslot);
+            const bool src0 = kb < p.a_split;
+            const CUtensorMap* src = src0 ? &tmA_hi : &tmA_lo;
+            const int c0 = (src0 ? kb : kb - p.a_split) * 64;
             mbar_expect_tx(rb, (uint32_t)(2 * p.PW * p.PH * 128));
-            tma_load_4d(sa, &tmA_hi, rb, kb * 64, x0 - p.pad, y0 - p.pad, n);
-            tma_load_4d(sa + Cfg::H_A_PLANE, &tmA_lo, rb, kb * 64, x0 - p.pad, y0 - p.pad, n);
+            tma_load_4d(sa, src, rb, c0, x0 - p.pad, y0 - p.pad, n);
+            tma_load_4d(sa + Cfg::X_A_PLANE2, src, rb, c0 + 32, x0 - p.pad, y0 - p.pad, n);
           }
           __syncwarp();
           if (++aslot == A_SLOTS) { aslot = 0; aphase ^= 1; }
@@ -861,19 +1003,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
     }
   } else if (XF && warp >= 2 + TC_EPI_WARPS) {
-    // ============================ XF: operand transform (warps 10..13) ============================
-    // raw patch (fp16 hi + lo of the producing conv's output, zero outside the image) -> y = act(x * scale[n,c] + shift[n,c])
-    // (GroupNorm folded into scale/shift, vqgan_arch.py:14-15,153-160) -> fp16 hi/lo of y, written back IN PLACE in the
-    // 128B-swizzled layout the MMA descriptors expect; pixels outside the image stay exactly zero (the conv pads the
-    // NORMALISED tensor).  fence.proxy.async publishes the generic-proxy writes to the tensor core.
+    // ============================ XF: operand transform (warps 10..) ============================
+    // raw fp32 patch (zero outside the image: TMA out-of-bounds fill) -> y = act(x * scale[n,c] + shift[n,c]) (GroupNorm folded
+    // into scale/shift, vqgan_arch.py:14-20,153-160) -> fp16 hi = rn(y), lo = rn(y - hi), written back IN PLACE in the
+    // 128B-swizzled K-major layout the MMA descriptors read: plane 0 (raw channels 0..31 of the block) becomes the hi plane
+    // (64 channels x fp16), plane 1 (raw channels 32..63) the lo plane.  A patch row (one pixel, 256 B raw) is handled by 8
+    // lanes of ONE warp -- lane j owns channels 8j..8j+7 -- and every lane loads before any lane stores (__syncwarp), which
+    // is what makes the in-place rewrite safe.  Plane 1 is skewed by 128 B so that, with the swizzle being a function of
+    // absolute shared-memory address bits, the 16-byte chunks {0,2,4,6} of plane-0 lanes and plane-1 lanes of the same row
+    // fall on different banks: each warp-wide LDS.128 / STS.128 is 4 conflict-free wavefronts.  Pixels outside the image
+    // stay exactly zero (the conv pads the NORMALISED tensor).  fence.proxy.async publishes the writes to the tensor core.
     if constexpr (XF) {
-      const int t = (int)threadIdx.x - 32 * (2 + TC_EPI_WARPS);      // 0..127
-      const int chunk = t & 7, r0 = t >> 3;                          // 16-byte chunk (8 channels) of a patch row; first row
+      constexpr int XFW = TcCfg<BN>::XF_WARPS;
+      constexpr int RPP = 4 * XFW;                                  // patch rows per pass (8 lanes per row)
+      constexpr int XF_PW = 10, XF_PH = 18, XF_ROWS = XF_PW * XF_PH;   // halo patch of an 8 x 16 tile and a 3 x 3 filter
+      constexpr int NPASS = (XF_ROWS + RPP - 1) / RPP;
+      const int t = (int)threadIdx.x - 32 * (2 + TC_EPI_WARPS);
+      const int j = t & 7, rsub = t >> 3;
+      const int pl = j >> 2, c0 = 2 * (j & 3);                      // source plane and first 16-byte chunk of this lane's 8 channels
       const uint32_t afull_leader = map_to_cta(smem_u32(afull), 0u);
-      constexpr int XF_PW = 10, XF_ROWS = 10 * 18;                   // halo patch of an 8 x 16 tile and a 3 x 3 filter
-      const bool silu = p.in_act == IN_SILU;
+      const int mode = p.in_scale ? (p.in_act == IN_SILU ? 2 : 1) : 0;   // 2: affine + SiLU, 1: affine, 0: raw split
       const int Hin = p.tiles_y * p.BH, Win = p.tiles_x * p.BW;
       const int Cin = p.kblocks * 64;
+      float amax = 0.f;
       int aslot = 0;
       uint32_t aphase = 0;
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
@@ -883,60 +1035,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int rem = mt - n * per_img;
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
         const int y0 = ty * p.BH - p.pad, x0 = tx * p.BW - p.pad;
+        const bool border = y0 < 0 || x0 < 0 || y0 + XF_PH > Hin || x0 + XF_PW > Win;
         for (int kb = 0; kb < p.kblocks; ++kb) {
           float sc[8], sh[8];
-          {
-            const float* sp = p.in_scale + (int64_t)n * Cin + kb * 64 + chunk * 8;
-            const float* hp = p.in_shift + (int64_t)n * Cin + kb * 64 + chunk * 8;
+          if (mode) {
+            const float* sp = p.in_scale + (int64_t)n * Cin + kb * 64 + j * 8;
+            const float* hp = p.in_shift + (int64_t)n * Cin + kb * 64 + j * 8;
             const float4 s0 = __ldg(reinterpret_cast<const float4*>(sp)), s1 = __ldg(reinterpret_cast<const float4*>(sp + 4));
             const float4 h0 = __ldg(reinterpret_cast<const float4*>(hp)), h1 = __ldg(reinterpret_cast<const float4*>(hp + 4));
             sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
             sh[0] = h0.x; sh[1] = h0.y; sh[2] = h0.z; sh[3] = h0.w; sh[4] = h1.x; sh[5] = h1.y; sh[6] = h1.z; sh[7] = h1.w;
-          }
-          mbar_wait(smem_u32(araw + aslot), aphase);
-          uint8_t* hi_base = smem + aslot * Cfg::H_A_SLOT;
-          uint8_t* lo_base = hi_base + Cfg::H_A_PLANE;
-          // 10 x 18 patch rows, 16 rows per pass: fully unrolled so the independent rows overlap their latencies
+          } else {
 #pragma unroll
-          for (int it = 0; it < (XF_ROWS + 15) / 16; ++it) {
-            const int r = r0 + it * 16;
-            if (r < XF_ROWS) {
-              const int py = r / XF_PW, px = r - py * XF_PW;
-              const bool inside = (unsigned)(y0 + py) < (unsigned)Hin && (unsigned)(x0 + px) < (unsigned)Win;
-              const uint32_t off = (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
-              uint4 hv = make_uint4(0u, 0u, 0u, 0u), lv = make_uint4(0u, 0u, 0u, 0u);
-              if (inside) {
-                const uint4 hr = *reinterpret_cast<const uint4*>(hi_base + off);
-                const uint4 lr = *reinterpret_cast<const uint4*>(lo_base + off);
-                const __half2* h2 = reinterpret_cast<const __half2*>(&hr);
-                const __half2* l2 = reinterpret_cast<const __half2*>(&lr);
-                __half2* oh = reinterpret_cast<__half2*>(&hv);
-                __half2* ol = reinterpret_cast<__half2*>(&lv);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 a = __half22float2(h2[j]), b = __half22float2(l2[j]);
-                  float v0 = fmaf(a.x + b.x, sc[2 * j], sh[2 * j]);
-                  float v1 = fmaf(a.y + b.y, sc[2 * j + 1], sh[2 * j + 1]);
-                  if (silu) {      // x * sigmoid(x) with the fast exp / reciprocal: ~2^-21 relative, below the hi/lo operand error
-                    v0 = __fdividef(v0, 1.f + __expf(-v0));
-                    v1 = __fdividef(v1, 1.f + __expf(-v1));
-                  }
-                  const __half2 hh = __floats2half2_rn(v0, v1);
-                  const float2 hf = __half22float2(hh);
-                  oh[j] = hh;
-                  ol[j] = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
-                }
-              }
-              *reinterpret_cast<uint4*>(hi_base + off) = hv;
-              *reinterpret_cast<uint4*>(lo_base + off) = lv;
-            }
+            for (int k = 0; k < 8; ++k) { sc[k] = 1.f; sh[k] = 0.f; }
           }
+          mbar_wait(smem_u32(araw + aslot), aphase, aborted);
+          const uint32_t base0 = smem_u32(smem + aslot * Cfg::H_A_SLOT);
+          const uint32_t src_base = base0 + (pl ? (uint32_t)Cfg::X_A_PLANE2 : 0u);
+          const uint32_t lo_base = base0 + (uint32_t)Cfg::X_A_PLANE2;
+          if (mode == 2) xf_patch<2, RPP, NPASS, XF_PW, XF_ROWS>(src_base, base0, lo_base, c0, j, rsub, sc, sh, border, y0, x0, Hin, Win, amax);
+          else if (mode == 1) xf_patch<1, RPP, NPASS, XF_PW, XF_ROWS>(src_base, base0, lo_base, c0, j, rsub, sc, sh, border, y0, x0, Hin, Win, amax);
+          else xf_patch<0, RPP, NPASS, XF_PW, XF_ROWS>(src_base, base0, lo_base, c0, j, rsub, sc, sh, border, y0, x0, Hin, Win, amax);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(afull_leader + (uint32_t)(aslot * 8));
           if (++aslot == A_SLOTS) { aslot = 0; aphase ^= 1; }
         }
       }
+      if (amax > 65504.f) report_overflow();      // an operand left the fp16 range: the host turns the status word into an error
     }
   } else {
     // ============================ epilogue (warps 2..9) ============================
@@ -948,6 +1074,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const float wsi = __ldg(p.wscale_inv);
     int slot = 0;
     uint32_t slot_phase = 0;
+    float omax = 0.f;                        // largest magnitude emitted into fp16 operand planes (range guard)
     const uint32_t cempty_leader = PAIR ? map_to_cta(smem_u32(cempty), 0u) : 0u;
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
       const int pm = tile / p.n_tiles, nt = tile - pm * p.n_tiles;
@@ -979,7 +1106,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
       for (int j = 0; j < HC; ++j) acc[j] = 0.f;
       for (int it0 = 0; it0 < nk; it0 += p.chunk) {
-        mbar_wait(smem_u32(cfull + slot), slot_phase);
+        mbar_wait(smem_u32(cfull + slot), slot_phase, aborted);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(slot * Cfg::SLOT_COLS + cbase);
 #pragma unroll
@@ -1054,6 +1181,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           }
           if (p.out) *reinterpret_cast<float4*>(p.out + off) = v;      // null: only the operand planes are consumed
           if (p.pl_hi) {
+            omax = fmaxf(omax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
             const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
             const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
             const __half2 l01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
@@ -1095,8 +1223,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         __syncwarp();
       }
     }
+    if (omax > 65504.f) report_overflow();   // a value left the fp16 range of the operand planes: reported, never silent
   }
 
+  if (aborted) {             // error path only: let bulk copies that were issued without back-pressure land before the CTA's
+    const long long t0 = clock64();          // shared memory is handed to another CTA
+    while (clock64() - t0 < 400000) {}
+  }
   tc_fence_before();
   __syncthreads();
   if constexpr (PAIR) cluster_sync_all();      // the peer may still read this CTA's operands / signal its barriers
@@ -1109,6 +1242,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
                    : "memory");
   }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// asynchronous status word: binding of this device's symbols (called once per device by runtime.cu)
+// ------------------------------------------------------------------------------------------------------
+int tc_bind_status_word(unsigned* host_mapped_dev_ptr, long long wait_limit_cycles) {
+  const unsigned zero = 0;
+  CFB_CUDA(cudaMemcpyToSymbol(g_status_host, &host_mapped_dev_ptr, sizeof(host_mapped_dev_ptr)));
+  CFB_CUDA(cudaMemcpyToSymbol(g_wait_limit, &wait_limit_cycles, sizeof(wait_limit_cycles)));
+  CFB_CUDA(cudaMemcpyToSymbol(g_abort, &zero, sizeof(zero)));
+  return 0;
+}
+static std::atomic<int> g_inject_fault{0};
+int tc_inject_fault(int kind) { g_inject_fault.store(kind); return 0; }
+int tc_clear_abort() {
+  const unsigned zero = 0;
+  CFB_CUDA(cudaMemcpyToSymbol(g_abort, &zero, sizeof(zero)));
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1132,12 +1283,12 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box, int spatial_stride = 1) {
+                    const uint32_t* box, int spatial_stride = 1, bool f32 = false) {
   EncodeTiledFn fn = get_encode_fn();
   CFB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   // traversal stride 2 along W and H turns the box into the stride-2 sampling pattern of Downsample
   cuuint32_t estr[5] = {1, (cuuint32_t)spatial_stride, (cuuint32_t)spatial_stride, 1, 1};
-  const CUresult rc = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+  const CUresult rc = fn(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
                          reinterpret_cast<const cuuint64_t*>(dims), reinterpret_cast<const cuuint64_t*>(strides_bytes),
                          reinterpret_cast<const cuuint32_t*>(box), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1203,14 +1354,14 @@ bool tc_supported(const ConvArgs& a) {
   return true;
 }
 
-// fused operand transform: available for 3x3 stride-1 convs on the halo + pair engine, USED where it measured faster than
-// prep pass + conv (profiles/round1_xform_launch_summary_b8.md): 128-wide output tiles with >= 2 k-blocks at >= 64x64 --
-// there the MMAs of one patch (6.9k cycles) cover TMA + transform.  The Cin = 64 layers (4.1k cycles of MMA per patch)
-// and the 16x16 / 32x32 layers (one or two tiles per SM: latency exposed) lose.  CFB_TC_XFORM=0 disables, =2 forces all.
+// fused operand transform: available for 3x3 stride-1 convs on the halo + pair engine.  Round 1 read fp16 hi/lo planes and
+// only paid on the 128-wide layers at >= 64x64; the round-2 transform reads the fp32 activation itself (no planes written by
+// the producer, no prep pass), needs ~3x fewer instructions per element and has 8 transform warps + 3 patch slots on the
+// 64-wide layers, so it is used wherever the engine exists.  CFB_TC_XFORM=0 disables it, =3 restores the round-1 rule.
 bool tc_can_xform(const ConvArgs& a) {
   static const int mode = [] { const char* e = getenv("CFB_TC_XFORM"); return e ? atoi(e) : 1; }();
   if (mode == 0 || !tc_supported(a) || a.mode != CONV_SAME || a.ksize != 3) return false;
-  if (mode == 1 && !(a.Cout % 128 == 0 && a.Cin >= 128 && (int64_t)a.Ho * a.Wo >= 4096)) return false;
+  if (mode == 3 && !(a.Cout % 128 == 0 && a.Cin >= 128 && (int64_t)a.Ho * a.Wo >= 4096)) return false;
   const TcGeom g = tc_geometry(a);
   if (!g.halo) return false;
   const int64_t m_tiles = (int64_t)a.N * (a.Wo / g.BW) * (a.Ho / g.BH);
@@ -1238,12 +1389,17 @@ static int launch_tc2(const TcMaps& m, const TcParams& p, int sm_count, cudaStre
   using Cfg = TcCfg<BN>;
   constexpr int SMEM = XF ? Cfg::X_SMEM_BYTES
                           : (HALO ? (PAIR ? Cfg::HP_SMEM_BYTES : Cfg::H_SMEM_BYTES) : (PAIR ? Cfg::P_SMEM_BYTES : Cfg::SMEM_BYTES));
-  constexpr int THREADS = XF ? TC_THREADS_XF : TC_THREADS;
+  constexpr int THREADS = XF ? TcCfg<BN>::XF_THREADS : TC_THREADS;
   static_assert(SMEM <= 232448, "shared memory budget");
-  static bool attr_done = false;
-  if (!attr_done) {
+  // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE property of the function: remember it per device
+  // (one process may drive several GPUs from several threads)
+  static std::atomic<uint64_t> attr_done{0};
+  int dev = 0;
+  CFB_CUDA(cudaGetDevice(&dev));
+  const uint64_t bit = 1ull << (dev & 63);
+  if (!(attr_done.load(std::memory_order_acquire) & bit)) {
     CFB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, CPG, HALO, PAIR, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_done = true;
+    attr_done.fetch_or(bit, std::memory_order_release);
   }
   if constexpr (PAIR) {
     const int pairs = (p.m_tiles / 2) * p.n_tiles;
@@ -1269,7 +1425,7 @@ static int launch_tc2(const TcMaps& m, const TcParams& p, int sm_count, cudaStre
 }
 template <int BN, int CPG>
 static int launch_tc(const TcMaps& m, const TcParams& p, int sm_count, cudaStream_t st) {
-  if (p.in_scale) {      // fused operand transform: conv_tc() only asks for it when tc_can_xform() holds
+  if (p.xform) {         // fused operand transform: conv_tc() only asks for it when tc_can_xform() holds
     CFB_REQUIRE(p.PW == 10 && p.PH == 18 && pair_ok(p), "conv_tc: fused operand transform needs the halo + pair engine");
     return launch_tc2<BN, CPG, true, true, true>(m, p, sm_count, st);
   }
@@ -1319,7 +1475,24 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
   const int BN = (a.Cout % 128 == 0) ? 128 : 64;
   TcMaps mp;
   CUtensorMap &mA_hi = mp.a_hi, &mA_lo = mp.a_lo, &mB_hi = mp.b_hi, &mB_lo = mp.b_lo;
-  {
+  if (a.xform) {
+    // fused operand transform: the A operand is read straight from the fp32 NHWC activation(s); boxes of 32 channels
+    // (128 B rows) x the halo patch.  Source 1 is the second half of a channel concatenation (or source 0 again).
+    CFB_REQUIRE(a.in != nullptr && geo.halo, "conv_tc: fused operand transform needs the fp32 input and the halo engine");
+    const int C0 = a.in2 ? a.Cin1 : a.Cin, C1 = a.in2 ? a.Cin - a.Cin1 : a.Cin;
+    CFB_REQUIRE(C0 % 64 == 0 && C1 % 64 == 0 && C0 > 0 && C1 > 0, "conv_tc: concatenated sources must be multiples of 64 channels");
+    const uint32_t box[4] = {32, (uint32_t)PW, (uint32_t)PH, 1};
+    {
+      const uint64_t dims[4] = {(uint64_t)C0, (uint64_t)Wp, (uint64_t)Hp, (uint64_t)a.N};
+      const uint64_t str[3] = {(uint64_t)C0 * 4, (uint64_t)Wp * C0 * 4, (uint64_t)Hp * Wp * C0 * 4};
+      CFB_CHECK(make_map(&mA_hi, a.in, 4, dims, str, box, 1, true));
+    }
+    {
+      const uint64_t dims[4] = {(uint64_t)C1, (uint64_t)Wp, (uint64_t)Hp, (uint64_t)a.N};
+      const uint64_t str[3] = {(uint64_t)C1 * 4, (uint64_t)Wp * C1 * 4, (uint64_t)Hp * Wp * C1 * 4};
+      CFB_CHECK(make_map(&mA_lo, a.in2 ? a.in2 : a.in, 4, dims, str, box, 1, true));
+    }
+  } else {
     const int sp = a.mode == CONV_DOWN ? 2 : 1;
     const uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)Wp, (uint64_t)Hp, (uint64_t)a.N};
     const uint64_t str[3] = {(uint64_t)a.Cin * 2, (uint64_t)Wp * a.Cin * 2, (uint64_t)Hp * Wp * a.Cin * 2};
@@ -1350,10 +1523,16 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
   p.tiles_x = (p.up4 ? a.W : a.Wo) / BW; p.tiles_y = (p.up4 ? a.H : a.Ho) / BH;
   p.m_tiles = a.N * p.tiles_x * p.tiles_y * (p.up4 ? 4 : 1); p.n_tiles = a.Cout / BN; p.kblocks = a.Cin / 64;
   if (p.taps * p.kblocks <= 12) p.chunk = p.taps * p.kblocks;   // short K (Cin = 64): one partial sum, no 8+1 split
-  p.in_scale = nullptr; p.in_shift = nullptr; p.in_act = IN_NONE;
+  p.in_scale = nullptr; p.in_shift = nullptr; p.in_act = IN_NONE; p.xform = a.xform ? 1 : 0;
+  p.fault = g_inject_fault.exchange(0);
+  p.a_split = a.in2 ? a.Cin1 / 64 : a.Cin / 64;
   if (a.xform) {
-    CFB_REQUIRE(a.skip_prep && a.in_scale && a.in_shift && tc_can_xform(a), "conv_tc: fused operand transform not available for this conv");
+    CFB_REQUIRE(a.skip_prep && tc_can_xform(a), "conv_tc: fused operand transform not available for this conv");
+    CFB_REQUIRE((a.in_scale != nullptr) == (a.in_shift != nullptr) && (a.in_scale || a.in_act == IN_NONE),
+                "conv_tc: fused operand transform takes scale and shift together");
     p.in_scale = a.in_scale; p.in_shift = a.in_shift; p.in_act = a.in_act;
+  } else {
+    CFB_REQUIRE(a.in2 == nullptr, "conv_tc: a two-source input needs the fused operand transform");
   }
   p.bias = a.bias; p.residual = a.residual; p.out_act = a.out_act;
   p.sft_dec = a.sft_dec; p.sft_scale = a.sft_scale; p.sft_w = a.sft_w; p.wscale_inv = a.wscale_inv; p.out = a.out;
@@ -1417,7 +1596,7 @@ int bmm_tc(const BmmArgs& g, int sm_count, cudaStream_t st) {
   p.PW = 0; p.PH = 0;
   p.BW = 16; p.BH = 8; p.tiles_x = 1; p.tiles_y = 2;
   p.m_tiles = g.N * 2; p.n_tiles = g.Cout / 128; p.kblocks = g.K / 64;
-  p.in_scale = nullptr; p.in_shift = nullptr; p.in_act = IN_NONE;
+  p.in_scale = nullptr; p.in_shift = nullptr; p.in_act = IN_NONE; p.xform = 0; p.a_split = 0; p.fault = 0;
   p.bias = nullptr; p.residual = nullptr; p.out_act = OUT_NONE; p.sft_dec = nullptr; p.sft_scale = nullptr; p.sft_w = 0.f;
   p.wscale_inv = g.scale_dev; p.out = g.out;
   p.gn_part = nullptr; p.gn_cpg = 0;
@@ -1626,8 +1805,7 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int N, int nacc, int 
 int umma_rate(int N, int nacc, int reps, long long* out_dev, int ctas, cudaStream_t st) {
   CFB_REQUIRE((N == 64 || N == 128 || N == 256) && nacc >= 1 && nacc * N <= 512, "umma_rate: bad configuration");
   const int smem = 4 * 16384 + 4 * 32768 + 64 + 1024;
-  static bool done = false;
-  if (!done) { CFB_CUDA(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); done = true; }
+  CFB_CUDA(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   umma_rate_kernel<<<ctas, 128, smem, st>>>(N, nacc, reps, out_dev);
   CFB_LAUNCH_CHECK();
   return 0;
@@ -1708,8 +1886,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
 int umma_pair(int N, int reps, float* vals_dev, long long* info_dev, int ctas, cudaStream_t st) {
   CFB_REQUIRE((N == 64 || N == 128 || N == 256) && reps >= 1 && ctas >= 2 && ctas % 2 == 0, "umma_pair: bad configuration");
   const int smem = 2 * 16384 + 1024 + 64;
-  static bool done = false;
-  if (!done) { CFB_CUDA(cudaFuncSetAttribute(umma_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); done = true; }
+  CFB_CUDA(cudaFuncSetAttribute(umma_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   umma_pair_kernel<<<ctas, 128, smem, st>>>(N, reps, vals_dev, info_dev);
   CFB_LAUNCH_CHECK();
   return 0;

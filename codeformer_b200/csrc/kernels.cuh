@@ -40,6 +40,16 @@ void set_error(const std::string& msg);
     }                                                                                             \
   } while (0)
 
+// asynchronous device status word (host-mapped): kernels report a barrier time-out or an fp16 operand overflow here instead
+// of trapping; the host turns it into an error without poisoning the context (runtime.cu)
+#define CFB_STATUS_TIMEOUT 1u
+#define CFB_STATUS_OVERFLOW 2u
+int async_status_init(cudaStream_t st);      // per-device one-time setup (idempotent)
+int async_status_check(const char* where);   // non-zero + set_error() when a kernel reported a failure since the last check
+int tc_bind_status_word(unsigned* host_mapped_dev_ptr, long long wait_limit_cycles);   // conv_tc.cu: device symbols of this device
+int tc_clear_abort();
+int tc_inject_fault(int kind);               // test hook: the next tcgen05 conv launch drops one TMA load (-> barrier time-out)
+
 void count_launch();
 int64_t launch_count();
 void reset_launch_count();
@@ -76,7 +86,10 @@ struct ConvArgs {
   // tensor-core engine only: also emit `out` as fp16 hi/lo operand planes for a following conv that consumes it raw
   void* out_planes = nullptr;       // [hi plane | lo plane], each align1024(N*Ho*Wo*Cout*2) bytes
   bool skip_prep = false;           // operand planes in `scratch` are already valid (kernel-only timing)
-  bool xform = false;      // tensor engine: `in` planes are RAW; apply in_scale/in_shift/in_act inside the conv kernel (tc_can_xform)
+  bool xform = false;      // tensor engine: read the fp32 activation `in` directly and apply in_scale/in_shift/in_act + the fp16 hi/lo
+                           // split inside the conv kernel (tc_can_xform); in_scale == null: plain split of the raw values
+  const float* in2 = nullptr;   // xform only: channels [Cin1, Cin) come from this second NHWC tensor (torch.cat of Fuse_sft_block)
+  int Cin1 = 0;
 };
 
 int conv_f32(const ConvArgs& a, cudaStream_t st);                       // CUDA-core fp32 implicit GEMM

@@ -34,6 +34,53 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 int64_t launch_count() { return g_launches.load(); }
 void reset_launch_count() { g_launches.store(0); }
 
+// ---- asynchronous device status (barrier time-out / fp16 operand overflow) ---------------------------------
+// One host-mapped word per device.  Kernels never trap: they set bits here (conv_tc.cu) and the host reports them as an
+// ordinary error at the next check point -- the CUDA context stays usable, the caller's per-face fallback keeps working
+// (SURVEY.md section 8(b) "Errors"; /root/reference/inference_codeformer.py:209-211).
+static std::mutex g_status_mu;
+static unsigned* g_status_words = nullptr;            // host pointer of a mapped, portable allocation: [64] words
+static uint64_t g_status_bound = 0;                   // devices whose symbols are bound
+static long long g_wait_limit_cycles = 4000000000LL;
+
+int async_status_init(cudaStream_t) {
+  int dev = 0;
+  CFB_CUDA(cudaGetDevice(&dev));
+  CFB_REQUIRE(dev >= 0 && dev < 64, "more than 64 CUDA devices are not supported");
+  std::lock_guard<std::mutex> lk(g_status_mu);
+  if (g_status_bound & (1ull << dev)) return 0;
+  if (!g_status_words) {
+    CFB_CUDA(cudaHostAlloc((void**)&g_status_words, 64 * sizeof(unsigned), cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(g_status_words, 0, 64 * sizeof(unsigned));
+  }
+  unsigned* dptr = nullptr;
+  CFB_CUDA(cudaHostGetDevicePointer((void**)&dptr, g_status_words, 0));
+  CFB_CHECK(tc_bind_status_word(dptr + dev, g_wait_limit_cycles));
+  g_status_bound |= 1ull << dev;
+  return 0;
+}
+
+int async_status_check(const char* where) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return 0; }
+  unsigned bits = 0;
+  {
+    std::lock_guard<std::mutex> lk(g_status_mu);
+    if (!g_status_words || !(g_status_bound & (1ull << dev))) return 0;
+    bits = __atomic_exchange_n(g_status_words + dev, 0u, __ATOMIC_ACQ_REL);
+  }
+  if (!bits) return 0;
+  std::string msg = std::string(where) + ": a kernel of an earlier launch on this device reported";
+  if (bits & CFB_STATUS_TIMEOUT) msg += " [barrier time-out: the tensor-core pipeline was aborted, results of that launch are invalid]";
+  if (bits & CFB_STATUS_OVERFLOW) msg += " [fp16 operand overflow: an activation exceeded 65504 on the split-fp16 tensor-core path]";
+  if (bits & CFB_STATUS_TIMEOUT) {
+    if (cudaDeviceSynchronize() != cudaSuccess) cudaGetLastError();   // the aborted launch has drained; the context is healthy
+    tc_clear_abort();
+  }
+  set_error(msg);
+  return 1;
+}
+
 // ---- stream-ordered arena over the caller's workspace ---------------------------------------------
 // All work of one forward is enqueued on one stream, so a block can be handed out again as soon as the
 // host has *enqueued* its last reader.  First-fit with coalescing; `dry` mode only tracks the high-water mark.
@@ -91,6 +138,8 @@ struct Tensor {
   float* gn_part = nullptr;   // GroupNorm partial sums emitted by the producing tensor-core conv (or null)
   int gn_slots = 0;           // partial slots per image
   void* planes = nullptr;     // fp16 hi/lo operand planes of this tensor emitted by the producing conv (raw values)
+  const float* p2 = nullptr;  // channel concatenation held as two tensors: channels [0,C1) live in p, [C1,C) in p2 (Fuse_sft_block)
+  int C1 = 0;
   int64_t numel() const { return (int64_t)N * H * W * C; }
 };
 
@@ -145,6 +194,8 @@ struct cfb_net {
   // small owned copies of norm params etc. live in the slab too
   std::vector<std::pair<const float**, std::pair<std::string, int64_t>>> vec_params;  // (dst, (name, numel))
   std::vector<ConvW*> convs;
+  int device = -1;                    // CUDA device the slab / prepared weights live on
+  std::map<int, int64_t> ws_memo;     // batch -> cfb_workspace_bytes (16 host-side dry runs per miss)
   int engine = 0;                     // 0 auto (tcgen05 where the shape allows), 1 fp32 CUDA cores, 2 tcgen05 only
   std::map<std::string, std::pair<float*, int64_t>> captures;   // stage name -> (device dst, capacity in floats)
 };
@@ -341,12 +392,31 @@ static int prepare(cfb_net* n, cudaStream_t st) {
   const size_t scratch = align256((size_t)3 * 512 * 512 * 4) + align256(3 * 512 * 4);
   total += scratch;
   total += 256 * (n->enc.size() + n->gen.size());      // per-AttnBlock device constants
-  if (n->slab_bytes < total) {
-    if (n->slab) cudaFree(n->slab);
+  // the net lives on the device that is current at prepare time (net.to(other_gpu) -> a new prepare): slab, SM count and
+  // engine availability all follow it
+  int dev = 0, major = 0, sms = 148;
+  CFB_CUDA(cudaGetDevice(&dev));
+  CFB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  CFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (n->slab && (n->device != dev || n->slab_bytes < total)) {
+    if (n->device != dev && n->device >= 0) {
+      cudaSetDevice(n->device);
+      cudaFree(n->slab);
+      cudaSetDevice(dev);
+    } else {
+      cudaFree(n->slab);
+    }
     n->slab = nullptr; n->slab_bytes = 0;
+  }
+  if (!n->slab) {
     CFB_CUDA(cudaMalloc((void**)&n->slab, total));
     n->slab_bytes = total;
   }
+  n->device = dev;
+  n->sm_count = sms > 0 ? sms : 148;
+  n->tc_ok = (major == 10);
+  n->ws_memo.clear();
+  CFB_CHECK(async_status_init(st));
   char* p = (char*)n->slab;
   auto take = [&](size_t bytes) { char* r = p; p += align256(bytes); return r; };
   float* qkv_w = (float*)take((size_t)3 * 512 * 512 * 4);
@@ -421,6 +491,7 @@ struct Fwd {
 
   int alloc(Tensor& t, int N, int H, int W, int C) {
     t.N = N; t.H = H; t.W = W; t.C = C; t.owned = true; t.gn_part = nullptr; t.gn_slots = 0; t.planes = nullptr;
+    t.p2 = nullptr; t.C1 = 0;
     t.p = (float*)ar.alloc((size_t)t.numel() * 4);
     CFB_REQUIRE(t.p != nullptr, "workspace too small (use cfb_workspace_bytes)");
     return 0;
@@ -458,7 +529,6 @@ struct Fwd {
     float* out_ptr = nullptr;   // write into caller memory instead of the arena
     bool want_stats = false;    // consumer is a GroupNorm: let the tensor-core epilogue emit the partial sums
     bool want_planes = false;   // a following conv reads this output raw: emit its fp16 hi/lo operand planes too
-    bool planes_only = false;   // the fp32 tensor itself is never read (ResBlock h: statistics + planes suffice): skip its store
   };
 
   int conv(const ConvW& w, const Tensor& in, Tensor& out, const ConvOpt& o) {
@@ -472,14 +542,9 @@ struct Fwd {
     a.in_scale = o.in_scale; a.in_shift = o.in_shift; a.in_act = o.in_act; a.residual = o.residual;
     a.out_act = o.out_act; a.sft_dec = o.sft_dec; a.sft_scale = o.sft_scale; a.sft_w = o.sft_w;
     bool use_tc = engine == 2 || (engine == 0 && n->tc_ok && tc_supported(a));
-    // planes-only output: legal when this conv emits both the GroupNorm partial sums and the operand planes
-    const bool no_f32 = o.planes_only && use_tc && !o.out_ptr && o.want_stats && o.want_planes && tc_supported(a) && tc_can_emit_stats(a);
     if (o.out_ptr) {
       out.p = o.out_ptr; out.N = in.N; out.H = Ho; out.W = Wo; out.C = w.cout; out.owned = false;
-      out.gn_part = nullptr; out.gn_slots = 0; out.planes = nullptr;
-    } else if (no_f32) {
-      out.p = nullptr; out.N = in.N; out.H = Ho; out.W = Wo; out.C = w.cout; out.owned = true;
-      out.gn_part = nullptr; out.gn_slots = 0; out.planes = nullptr;
+      out.gn_part = nullptr; out.gn_slots = 0; out.planes = nullptr; out.p2 = nullptr; out.C1 = 0;
     } else {
       CFB_CHECK(alloc(out, in.N, Ho, Wo, w.cout));
     }
@@ -497,20 +562,25 @@ struct Fwd {
         CFB_CHECK(alloc_raw(&out.planes, pb));
         a.out_planes = out.planes;
       }
-      // the producer already emitted this input's RAW operand planes: a conv that takes it raw needs no prep pass, and a
-      // GroupNorm + SiLU conv on the halo + pair engine applies the affine / activation inside the kernel (tc_can_xform)
-      const bool raw = in.planes && !o.in_scale && o.in_act == IN_NONE;
-      const bool xf = in.planes && o.in_scale && o.in_shift && tc_can_xform(a);
+      // Three ways the A operand reaches the tensor core:
+      //  xf   GroupNorm-affine (+ SiLU) consumers on the halo + pair engine read the fp32 activation itself -- or the two
+      //       halves of a channel concatenation -- and transform + split it inside the conv kernel (tc_can_xform);
+      //  raw  the producer already emitted this tensor's fp16 hi/lo planes and the consumer takes it untransformed;
+      //  prep everything else: a separate operand-preparation pass over the fp32 tensor.
+      const bool xf = in.p && o.in_scale && o.in_shift && tc_can_xform(a);
+      const bool raw = !xf && in.planes && !o.in_scale && o.in_act == IN_NONE;
       const bool reuse = raw || xf;
-      void* scratch = in.planes;
+      void* scratch = raw ? in.planes : nullptr;
       if (!reuse) CFB_CHECK(alloc_raw(&scratch, tc_scratch_bytes(a)));
-      CFB_REQUIRE(in.p != nullptr || reuse, "conv: planes-only input without a planes consumer: " + w.name);
+      CFB_REQUIRE(in.p != nullptr || raw, "conv: planes-only input without a planes consumer: " + w.name);
+      CFB_REQUIRE(in.p2 == nullptr || reuse, "conv: a two-source tensor needs the fused operand transform or its planes: " + w.name);
+      if (xf) { a.in2 = in.p2; a.Cin1 = in.C1; }
       a.skip_prep = reuse;
       a.xform = xf;
       if (!dry) CFB_CHECK(conv_tc(a, scratch, n->sm_count, st));
       if (!reuse) release_raw(scratch);
     } else {
-      CFB_REQUIRE(in.p != nullptr && out.p != nullptr, "conv: planes-only tensor reached the fp32 engine: " + w.name);
+      CFB_REQUIRE(in.p != nullptr && out.p != nullptr && in.p2 == nullptr, "conv: planes-only / two-source tensor reached the fp32 engine: " + w.name);
       if (!dry) CFB_CHECK(conv_f32(a, st));
     }
     return 0;
@@ -540,10 +610,7 @@ struct Fwd {
     CFB_CHECK(gn(r.n1, x, &s1, &h1));
     Tensor h;
     ConvOpt o1; o1.in_scale = s1; o1.in_shift = h1; o1.in_act = IN_SILU; o1.want_stats = true;
-    // if conv2 runs the fused operand transform, h is only ever read through its raw planes (+ the epilogue's statistics)
-    o1.want_planes = xf_ok(x.N, x.H, x.W, r.c2);
-    o1.planes_only = o1.want_planes && n->captures.empty();
-    CFB_CHECK(conv(r.c1, x, h, o1));
+    CFB_CHECK(conv(r.c1, x, h, o1));      // conv2 reads h as fp32 (fused operand transform or prep pass): no planes of h
     release_raw(s1); release_raw(h1);
     CFB_CHECK(gn(r.n2, h, &s2, &h2));
     Tensor skip = x; skip.owned = false;
@@ -610,32 +677,40 @@ struct Fwd {
   int fuse(const FuseW& f, const Tensor& enc_feat, const Tensor& dec, float wgt, Tensor& y) {
     Tensor cat;
     const bool stats_from_parts = enc_feat.gn_part && dec.gn_part && enc_feat.gn_slots == dec.gn_slots && enc_feat.C == dec.C;
-    bool planes_cat = false;
-    if (stats_from_parts && n->captures.empty() && (engine == 2 || (engine == 0 && n->tc_ok))) {
+    bool two_src = false;
+    if (stats_from_parts && (engine == 2 || (engine == 0 && n->tc_ok))) {
       ConvArgs a1;      // conv1 of the fused ResBlock: does it run the in-kernel operand transform?
       a1.N = dec.N; a1.H = dec.H; a1.W = dec.W; a1.Cin = f.enc.c1.cin; a1.Ho = dec.H; a1.Wo = dec.W; a1.Cout = f.enc.c1.cout;
       a1.ksize = f.enc.c1.k; a1.mode = CONV_SAME;
-      planes_cat = f.enc.has_out && tc_can_xform(a1);
+      two_src = f.enc.has_out && tc_can_xform(a1) && enc_feat.C % 64 == 0 && dec.C % 64 == 0;
     }
-    if (planes_cat) {
-      // the concatenation exists only as raw operand planes (no fp32 copy, no prep pass)
-      cat.p = nullptr; cat.N = dec.N; cat.H = dec.H; cat.W = dec.W; cat.C = enc_feat.C + dec.C; cat.owned = true;
+    void* cat_planes = nullptr;
+    if (two_src) {
+      // torch.cat([enc_feat, dec]) (codeformer_arch.py:152) is never materialised in fp32: conv1 of the fused ResBlock reads the
+      // two tensors through two tensor maps (fused operand transform), GroupNorm statistics come from the sources' partial
+      // sums, and only the raw 1x1 conv_out needs the concatenation -- as fp16 hi/lo operand planes
+      cat.p = enc_feat.p; cat.p2 = dec.p; cat.C1 = enc_feat.C;
+      cat.N = dec.N; cat.H = dec.H; cat.W = dec.W; cat.C = enc_feat.C + dec.C; cat.owned = false;
       cat.gn_part = nullptr; cat.gn_slots = 0; cat.planes = nullptr;
-      CFB_CHECK(alloc_raw(&cat.planes, 2 * (((size_t)cat.numel() * 2 + 1023) / 1024 * 1024)));
+      CFB_CHECK(alloc_raw(&cat_planes, 2 * (((size_t)cat.numel() * 2 + 1023) / 1024 * 1024)));
+      cat.planes = cat_planes;
       if (!dry) CFB_CHECK(concat_planes(enc_feat.p, dec.p, cat.planes, (int64_t)dec.N * dec.H * dec.W, enc_feat.C, dec.C, st));
     } else {
       CFB_CHECK(alloc(cat, dec.N, dec.H, dec.W, enc_feat.C + dec.C));
       if (!dry) CFB_CHECK(concat_channels(enc_feat.p, dec.p, cat.p, (int64_t)dec.N * dec.H * dec.W, enc_feat.C, dec.C, st));
     }
+    float* cat_part = nullptr;
     if (stats_from_parts) {
       // GroupNorm statistics of the concatenation follow from the two sources' partial sums (no extra pass)
       cat.gn_slots = dec.gn_slots;
-      CFB_CHECK(alloc_raw((void**)&cat.gn_part, (size_t)dec.N * cat.gn_slots * 64 * sizeof(float)));
+      CFB_CHECK(alloc_raw((void**)&cat_part, (size_t)dec.N * cat.gn_slots * 64 * sizeof(float)));
+      cat.gn_part = cat_part;
       if (!dry) CFB_CHECK(gn_cat_partials(enc_feat.gn_part, dec.gn_part, cat.gn_part, (int64_t)dec.N * cat.gn_slots, st));
     }
     Tensor e;
     CFB_CHECK(resblock(f.enc, cat, e, true));      // scale.0 / shift.0 both read `e` raw: one set of planes, no prep
-    release(cat);
+    if (two_src) { release_raw(cat_planes); if (cat_part) release_raw(cat_part); cat.planes = nullptr; cat.gn_part = nullptr; }
+    else release(cat);
     Tensor s0, sc, h0;
     ConvOpt ol; ol.out_act = OUT_LRELU; ol.want_planes = true;      // s0 / h0 feed scale.2 / shift.2 raw
     CFB_CHECK(conv(f.s0, e, s0, ol));
@@ -650,24 +725,22 @@ struct Fwd {
     return 0;
   }
 
-  // Does the consumer of block i's output read it through the tensor engine's operand planes?  Down/Upsample convs and a
-  // ResBlock's 1x1 conv_out take them raw; a ResBlock's conv1 and a norm -> conv pair apply GroupNorm + SiLU to the raw
-  // planes inside the conv kernel (fused operand transform).  `last_is_simt`: the final conv of the Generator is the
-  // CUDA-core conv_last.
+  // conv1 of a fused ResBlock at this shape: fused operand transform available?
   bool xf_ok(int N, int H, int W, const ConvW& w) const {
     if (!(engine == 2 || (engine == 0 && n->tc_ok))) return false;
     ConvArgs a;
     a.N = N; a.H = H; a.W = W; a.Ho = H; a.Wo = W; a.Cin = w.cin; a.Cout = w.cout; a.ksize = w.k; a.mode = CONV_SAME;
     return tc_can_xform(a);
   }
-  // (N, H, W): shape of block i's output
-  bool next_takes_planes(const std::vector<Block>& bl, size_t i, bool last_is_simt, int N, int H, int W) const {
+  // Does a consumer of block i's output read it RAW through the tensor engine (then the producer also emits its fp16 hi/lo
+  // operand planes)?  Down/Upsample convs and a ResBlock's 1x1 conv_out do.  GroupNorm (+SiLU) consumers -- a ResBlock's
+  // conv1, a norm -> conv pair -- read the fp32 tensor itself (fused operand transform or prep pass).
+  bool next_takes_planes(const std::vector<Block>& bl, size_t i) const {
+    if (!(engine == 2 || (engine == 0 && n->tc_ok))) return false;
     if (i + 1 >= bl.size()) return false;
     const Block& nb = bl[i + 1];
     if (nb.kind == B_DOWN || nb.kind == B_UP) return true;
-    if (nb.kind == B_RES) return nb.res_w.has_out || xf_ok(N, H, W, nb.res_w.c1);
-    if (nb.kind == B_NORM && i + 2 < bl.size() && bl[i + 2].kind == B_CONV)
-      return !(last_is_simt && i + 3 == bl.size()) && xf_ok(N, H, W, bl[i + 2].conv);
+    if (nb.kind == B_RES) return nb.res_w.has_out;
     return false;
   }
 
@@ -684,8 +757,7 @@ struct Fwd {
     float *ps = nullptr, *ph = nullptr;   // pending GroupNorm of a 'norm' block
     for (size_t i = 1; i < n->enc.size(); ++i) {
       const Block& b = n->enc[i];
-      const int oh = b.kind == B_DOWN ? x.H / 2 : x.H, ow = b.kind == B_DOWN ? x.W / 2 : x.W;
-      const bool pl = next_takes_planes(n->enc, i, false, x.N, oh, ow);
+      const bool pl = next_takes_planes(n->enc, i);
       Tensor y;
       switch (b.kind) {
         case B_RES: CFB_CHECK(resblock(b.res_w, x, y, pl)); break;
@@ -716,8 +788,7 @@ struct Fwd {
     float *ps = nullptr, *ph = nullptr;
     for (size_t i = 0; i < n->gen.size(); ++i) {
       const Block& b = n->gen[i];
-      const int oh = b.kind == B_UP ? x.H * 2 : x.H, ow = b.kind == B_UP ? x.W * 2 : x.W;
-      bool pl = next_takes_planes(n->gen, i, true, x.N, oh, ow);
+      bool pl = next_takes_planes(n->gen, i);
       if (taps && w > 0.f)
         for (int fb : fuse_blocks)
           if ((int)i == fb) pl = false;      // consumed by the fusion (concat + SFT read fp32); the fused output emits its own
@@ -808,6 +879,16 @@ struct Fwd {
   }
 };
 
+// The prepared weights live on ONE device; a forward issued while another device is current would launch kernels there
+// on foreign memory.  Also the place where an asynchronous failure of an earlier launch is reported (never silently lost).
+static int check_device(cfb_net* n) {
+  int dev = -1;
+  CFB_CUDA(cudaGetDevice(&dev));
+  CFB_REQUIRE(dev == n->device, "the net was prepared on CUDA device " + std::to_string(n->device) + " but device " +
+                                    std::to_string(dev) + " is current (call net.to(device) / cfb_net_prepare again)");
+  return async_status_check("forward");
+}
+
 static std::vector<int> tap_blocks_of(const cfb_config& c, bool encoder) {
   // fuse_encoder_block / fuse_generator_block  codeformer_arch.py:204-206
   static const int enc_of[6][2] = {{512, 2}, {256, 5}, {128, 8}, {64, 11}, {32, 14}, {16, 18}};
@@ -825,6 +906,7 @@ static int codeformer_forward_impl(cfb_net* n, const float* x, float* out, float
                                    unsigned char* out_u8 = nullptr) {
   CFB_REQUIRE(n->cfg.kind == 1, "net was created as VQAutoEncoder");
   CFB_REQUIRE(dry || n->prepared, "cfb_net_prepare has not been called");
+  if (!dry) CFB_CHECK(check_device(n));
   CFB_REQUIRE(B >= 0, "negative batch");
   if (B == 0) return 0;
   n->arena.reset(ws, (size_t)ws_bytes, dry);
@@ -866,6 +948,7 @@ static int vqae_forward_impl(cfb_net* n, const float* x, float* out, int64_t* id
                              void* ws, int64_t ws_bytes, cudaStream_t st, bool dry) {
   CFB_REQUIRE(dry || n->prepared, "cfb_net_prepare has not been called");
   if (B == 0) return 0;
+  if (!dry) CFB_CHECK(check_device(n));
   n->arena.reset(ws, (size_t)ws_bytes, dry);
   Fwd f{n, st, n->arena, dry, n->engine};
   const cfb_config& c = n->cfg;
@@ -949,14 +1032,49 @@ cfb_net* cfb_net_create(const cfb_config* cfg) {
   }
   n->sm_count = sms > 0 ? sms : 148;
   n->tc_ok = (major == 10);
+  n->device = dev;
   return n;
   API_END(nullptr)
 }
 
 void cfb_net_destroy(cfb_net* n) {
   if (!n) return;
-  if (n->slab) cudaFree(n->slab);
+  if (n->slab) {
+    int cur = -1;
+    const bool sw = cudaGetDevice(&cur) == cudaSuccess && n->device >= 0 && cur != n->device;
+    if (sw) cudaSetDevice(n->device);
+    cudaFree(n->slab);
+    if (sw) cudaSetDevice(cur);
+  }
   delete n;
+}
+
+int cfb_check_async_status(void) {
+  API_BEGIN
+  return cfb::async_status_check("cfb_check_async_status");
+  API_END(1)
+}
+
+int cfb_debug_set_wait_limit(int64_t cycles) {
+  API_BEGIN
+  CFB_REQUIRE(cycles > 0, "cfb_debug_set_wait_limit: cycles must be positive");
+  CFB_CHECK(cfb::async_status_init(nullptr));
+  {
+    std::lock_guard<std::mutex> lk(cfb::g_status_mu);
+    cfb::g_wait_limit_cycles = cycles;
+  }
+  int dev = 0;
+  CFB_CUDA(cudaGetDevice(&dev));
+  unsigned* dptr = nullptr;
+  CFB_CUDA(cudaHostGetDevicePointer((void**)&dptr, cfb::g_status_words, 0));
+  return cfb::tc_bind_status_word(dptr + dev, cycles);
+  API_END(1)
+}
+
+int cfb_debug_inject_fault(int32_t kind) {
+  API_BEGIN
+  return cfb::tc_inject_fault(kind);
+  API_END(1)
 }
 
 int cfb_net_set_param(cfb_net* n, const char* name, const float* dev_ptr, int64_t numel) {
@@ -981,6 +1099,10 @@ int64_t cfb_workspace_bytes(cfb_net* n, int32_t batch) {
   API_BEGIN
   if (!n) { cfb::set_error("cfb_workspace_bytes: NULL net"); return -1; }
   std::lock_guard<std::mutex> lk(n->mu);
+  {
+    auto it = n->ws_memo.find(batch);      // 16 host-side dry-run plans per miss: remember the answer per batch size
+    if (it != n->ws_memo.end()) return it->second;
+  }
   // The arena is first-fit, so the peak depends on the exact allocation sequence, which the call flags change (fusion on
   // or off, AdaIN, code_only, caller-provided logits or not): size for the worst of all of them (host-only dry runs).
   size_t high = 0;
@@ -1001,6 +1123,7 @@ int64_t cfb_workspace_bytes(cfb_net* n, int32_t batch) {
       if (n->arena.high() > high) high = n->arena.high();
     }
   }
+  n->ws_memo[batch] = (int64_t)high + 4096;
   return (int64_t)high + 4096;
   API_END(-1)
 }
@@ -1012,6 +1135,7 @@ int cfb_net_set_engine(cfb_net* n, int32_t engine) {
   CFB_REQUIRE(n && engine >= 0 && engine <= 2, "cfb_net_set_engine: engine must be 0 (auto), 1 (fp32) or 2 (tcgen05)");
   std::lock_guard<std::mutex> lk(n->mu);
   n->engine = engine;
+  n->ws_memo.clear();
   return 0;
   API_END(1)
 }
@@ -1022,6 +1146,7 @@ int cfb_net_capture(cfb_net* n, const char* stage, float* dst, int64_t capacity)
   std::lock_guard<std::mutex> lk(n->mu);
   if (dst) n->captures[stage] = {dst, capacity};
   else n->captures.erase(stage);
+  n->ws_memo.clear();
   return 0;
   API_END(1)
 }
@@ -1072,7 +1197,7 @@ int cfb_codeformer_restore_host(cfb_net* n, const uint8_t* faces_host, uint8_t* 
   CFB_CHECK(cfb_codeformer_forward_u8(n, din, dout, nullptr, nullptr, nullptr, batch, w, adain, workspace, workspace_bytes, stream));
   CFB_CUDA(cudaMemcpyAsync(restored_host, dout, img, cudaMemcpyDeviceToHost, st));
   CFB_CUDA(cudaStreamSynchronize(st));
-  return 0;
+  return cfb::async_status_check("cfb_codeformer_restore_host");
   API_END(1)
 }
 
@@ -1118,7 +1243,7 @@ int cfb_codeformer_forward_host(cfb_net* n, const float* x_host, float* out_host
   if (logits_host) CFB_CUDA(cudaMemcpyAsync(logits_host, dlog, lat * c.codebook_size * 4, cudaMemcpyDeviceToHost, st));
   if (lq_host) CFB_CUDA(cudaMemcpyAsync(lq_host, dlq, lat * c.emb_dim * 4, cudaMemcpyDeviceToHost, st));
   CFB_CUDA(cudaStreamSynchronize(st));
-  return 0;
+  return cfb::async_status_check("cfb_codeformer_forward_host");
   API_END(1)
 }
 
@@ -1231,6 +1356,7 @@ int cfb_conv2d_nhwc(const float* in, const float* weight_oihw, const float* bias
                     void* workspace, int64_t workspace_bytes, void* stream) {
   API_BEGIN
   CFB_REQUIRE(in && weight_oihw && out && workspace, "cfb_conv2d_nhwc: NULL argument");
+  CFB_CHECK(cfb::async_status_init(nullptr));
   CFB_REQUIRE(workspace_bytes >= cfb_conv2d_workspace_bytes(n, h, w, cin, cout, ksize, mode), "cfb_conv2d_nhwc: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   cfb::ConvArgs a;
@@ -1262,6 +1388,9 @@ int cfb_conv2d_nhwc(const float* in, const float* weight_oihw, const float* bias
     CFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (mode == cfb::CONV_UP) CFB_CHECK(cfb::tc_split_weights_up4(weight_oihw, whi, wlo, cout, cin, wsc, st));
     else CFB_CHECK(cfb::tc_split_weights(weight_oihw, whi, wlo, cout, cin, ksize, wsc, st));
+    // same choice as the network runtime (Fwd::conv): a GroupNorm-affine (+SiLU) input goes through the in-kernel operand
+    // transform wherever the engine has it, so the kernel tests exercise the path the forward ships
+    if (in_scale && in_shift && cfb::tc_can_xform(a)) { a.xform = true; a.skip_prep = true; }
     CFB_CHECK(cfb::conv_tc(a, p, sms, st));
   } else {
     CFB_CHECK(cfb::relayout_oihw_to_tck(weight_oihw, wf, cout, cin, ksize, st));

@@ -14,6 +14,8 @@
 //   Fuse_sft combine                      codeformer_arch.py:155-156                       conv epilogue (sft_*)
 //   VectorQuantizer.forward               vqgan_arch.py:33-70                              vq_nearest
 #include <cuda_runtime.h>
+
+#include <atomic>
 #include <math.h>
 #include <stdint.h>
 
@@ -794,11 +796,15 @@ int attention(const float* q, const float* k, const float* v, float* out, int B,
   CFB_REQUIRE(d == 64 || d == 512, "attention: head width must be 64 or 512");
   if (B == 0) return 0;
   const size_t smem = (size_t)(32 * AT_QB + 32 * AT_S + AT_QB * AT_S) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
+  // the opt-in is a per-device property of the function (several GPUs may be driven from one process)
+  static std::atomic<uint64_t> attr_done{0};
+  int dev = 0;
+  CFB_CUDA(cudaGetDevice(&dev));
+  const uint64_t bit = 1ull << (dev & 63);
+  if (!(attr_done.load(std::memory_order_acquire) & bit)) {
     CFB_CUDA(cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CFB_CUDA(cudaFuncSetAttribute(attention_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
+    attr_done.fetch_or(bit, std::memory_order_release);
   }
   dim3 grid(S / AT_QB, heads, B);
   if (d == 64)
@@ -875,8 +881,10 @@ __global__ void __launch_bounds__(256) argmax_gather_kernel(const float* __restr
   const int l = threadIdx.x & 31;
   if (tok >= T) return;
   const float* lr = logits + (int64_t)tok * K;
+  // A row of NaN / -inf logits never satisfies `v > best`: the index then stays at a VALID position (this lane's first
+  // column), like torch.topk, instead of indexing the codebook out of bounds (a NaN in must not become a sticky fault).
   float best = -INFINITY;
-  int bi = 0x7fffffff;
+  int bi = l < K ? l : 0;
   for (int i = l; i < K; i += 32) {
     const float v = __ldg(lr + i);
     if (v > best) { best = v; bi = i; }
@@ -887,6 +895,7 @@ __global__ void __launch_bounds__(256) argmax_gather_kernel(const float* __restr
     const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
     if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
   }
+  bi = min(max(bi, 0), K - 1);
   if (l == 0 && idx) idx[tok] = (int64_t)bi;
   if (quant) {
     const float* e = codebook + (int64_t)bi * D;
@@ -1096,7 +1105,7 @@ __global__ void __launch_bounds__(256) vq_nearest_kernel(const float* __restrict
   int besti[4];
   double dsum = 0.0;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { bestd[i] = INFINITY; besti[i] = 0x7fffffff; }
+  for (int i = 0; i < 4; ++i) { bestd[i] = INFINITY; besti[i] = K - 1; }
 
   for (int k0 = 0; k0 < K; k0 += 256) {
     float s[4][8];
@@ -1168,7 +1177,7 @@ __global__ void __launch_bounds__(256) vq_nearest_kernel(const float* __restrict
       const int oi = __shfl_xor_sync(0xffffffffu, besti[i], o);
       if (od < bestd[i] || (od == bestd[i] && oi < besti[i])) { bestd[i] = od; besti[i] = oi; }
     }
-    if (kg == 0) best_idx[qg * 4 + i] = besti[i];
+    if (kg == 0) best_idx[qg * 4 + i] = min(max(besti[i], 0), K - 1);   // all-NaN rows: a valid index, never out of bounds
   }
   __syncthreads();
   // outputs: idx, straight-through z_q, squared error, histogram
@@ -1270,7 +1279,7 @@ __global__ void __launch_bounds__(256) vq_select_kernel(const float* __restrict_
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) z2 += __shfl_xor_sync(0xffffffffu, z2, o);
     float best = INFINITY;
-    int bi = 0x7fffffff;
+    int bi = l < K ? l : 0;                 // NaN / +inf distances keep a valid index (no out-of-bounds gather or histogram write)
     const float* dr = dots + (int64_t)tok * K;
     for (int k = l; k < K; k += 32) {
       const float d = (z2 + __ldg(e2 + k)) - 2.f * __ldg(dr + k);
@@ -1283,6 +1292,7 @@ __global__ void __launch_bounds__(256) vq_select_kernel(const float* __restrict_
       const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
       if (od < best || (od == best && oi < bi)) { best = od; bi = oi; }
     }
+    bi = min(max(bi, 0), K - 1);
     if (l == 0) { idx[tok] = (int64_t)bi; atomicAdd(hist + bi, 1u); }
     for (int c = l; c < D; c += 32) {
       const float zz = z[(int64_t)tok * D + c];

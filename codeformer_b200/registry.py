@@ -1,58 +1,68 @@
-"""Registry with the interface of /root/reference/basicsr/utils/registry.py:4-82.
+"""Name -> class lookup behind the reference's plugin API.
 
-The reference looks its networks up with ``ARCH_REGISTRY.get('CodeFormer')`` /
-``.get('VQAutoEncoder')`` (inference_codeformer.py:135, scripts/inference_vqgan.py:31); registering a
-second class under an existing name asserts (registry.py:39).  ``install()`` therefore either
-*replaces* the entries in the reference's own ARCH_REGISTRY (when ``basicsr`` is importable) or the
-caller uses this module's ARCH_REGISTRY, which has the same methods.
+The reference finds its networks with ``ARCH_REGISTRY.get('CodeFormer')`` / ``.get('VQAutoEncoder')``
+(/root/reference/inference_codeformer.py:135, scripts/inference_vqgan.py:31; the registry itself is
+basicsr/utils/registry.py:4-82, whose ``register`` refuses a second class under an existing name, :39).
+Two ways to drop the B200 modules in:
+
+* ``install()`` swaps the two entries inside the reference's OWN ``ARCH_REGISTRY`` (when ``basicsr`` is
+  importable) -- the caller's ``ARCH_REGISTRY.get(...)`` line stays as it is;
+* without ``basicsr``, ``codeformer_b200.ARCH_REGISTRY`` below answers the same three calls the callers make
+  (``register()`` as a decorator, ``get(name)``, ``name in registry``).
 """
+from collections import OrderedDict
 
 
-class Registry:
-    def __init__(self, name):
-        self._name = name
-        self._obj_map = {}
+class ArchTable:
+    """Insertion-ordered name -> class table with the reference registry's call surface."""
 
-    def _do_register(self, name, obj):
-        assert name not in self._obj_map, (f"An object named '{name}' was already registered "
-                                           f"in '{self._name}' registry!")
-        self._obj_map[name] = obj
+    def __init__(self, label):
+        self.label = label
+        self.table = OrderedDict()
 
-    def register(self, obj=None):
-        if obj is None:
-            def deco(func_or_class):
-                self._do_register(func_or_class.__name__, func_or_class)
-                return func_or_class
-            return deco
-        self._do_register(obj.__name__, obj)
+    def add(self, cls, name=None):
+        key = name or cls.__name__
+        if key in self.table:
+            raise AssertionError(f'{self.label}: {key!r} is already taken by {self.table[key]!r}')
+        self.table[key] = cls
+        return cls
+
+    def register(self, cls=None):
+        """``@REG.register()`` (decorator factory, the form the reference uses) or ``REG.register(cls)``."""
+        return self.add if cls is None else self.add(cls)
 
     def get(self, name):
-        ret = self._obj_map.get(name)
-        if ret is None:
-            raise KeyError(f"No object named '{name}' found in '{self._name}' registry!")
-        return ret
+        try:
+            return self.table[name]
+        except KeyError:
+            raise KeyError(f'{self.label}: nothing registered under {name!r} (have: {", ".join(self.table)})') from None
 
     def __contains__(self, name):
-        return name in self._obj_map
+        return name in self.table
 
     def __iter__(self):
-        return iter(self._obj_map.items())
+        return iter(self.table.items())
 
     def keys(self):
-        return self._obj_map.keys()
+        return self.table.keys()
 
 
-ARCH_REGISTRY = Registry('arch')
+ARCH_REGISTRY = ArchTable('codeformer_b200 arch table')
 
 
 def install(registry=None):
     """Make ``registry.get('CodeFormer' | 'VQAutoEncoder')`` return the B200 modules.
 
-    With ``registry=None`` the reference's own ``basicsr.utils.registry.ARCH_REGISTRY`` is patched if
-    ``basicsr`` is importable; the existing entries are replaced (not added beside: registry.py:39)."""
+    ``registry=None`` patches the reference's ``basicsr.utils.registry.ARCH_REGISTRY`` (``basicsr`` must be importable).
+    Existing entries are REPLACED -- adding beside them is impossible (registry.py:39 asserts on duplicates) -- by writing
+    the mapping the reference registry keeps (its ``_obj_map`` dict) or, for any other mapping-like object, by item
+    assignment."""
     from .arch import CodeFormer, VQAutoEncoder
     if registry is None:
         from basicsr.utils.registry import ARCH_REGISTRY as registry  # type: ignore
+    store = getattr(registry, '_obj_map', None)
+    if store is None:
+        store = getattr(registry, 'table', registry)
     for cls in (CodeFormer, VQAutoEncoder):
-        registry._obj_map[cls.__name__] = cls
+        store[cls.__name__] = cls
     return registry

@@ -175,6 +175,17 @@ int cfb_debug_umma_rate(int32_t n, int32_t nacc, int32_t reps, int64_t* out_dev,
 int cfb_debug_time_conv(const float* in, const float* weight_oihw, float* out, int32_t n, int32_t h, int32_t w, int32_t cin,
                         int32_t cout, int32_t ksize, int32_t mode, int32_t reps, void* workspace, int64_t workspace_bytes,
                         void* stream, float* ms_per_launch);
+/* Asynchronous failures.  Kernels never trap and never leave a sticky CUDA error behind (the reference's callers catch
+ * RuntimeError and fall back to the input face, inference_codeformer.py:209-211; web-demos/hugging_face/app.py:176): a
+ * barrier time-out of the tensor-core pipeline or an activation outside the fp16 operand range (|x| > 65504) sets a bit
+ * in a host-mapped status word.  It is reported (status 1 + cfb_last_error) by the NEXT forward on that device, by the
+ * *_host entry points right after their stream synchronisation, and by this call -- use it after synchronising the stream
+ * of an asynchronous forward.  The context stays usable; the reporting call clears the condition. */
+int cfb_check_async_status(void);
+/* test hooks: barrier time-out in SM cycles (default 4e9, about 2 s); kind != 0 makes the next tcgen05 conv launch drop one
+ * TMA load so that its pipeline times out (tests/test_gpu_faults.py) */
+int cfb_debug_set_wait_limit(int64_t cycles);
+int cfb_debug_inject_fault(int32_t kind);
 /* layout plumbing */
 int cfb_nchw_to_nhwc(const float* in, float* out, int32_t n, int32_t c, int32_t hw, void* stream);
 int cfb_nhwc_to_nchw(const float* in, float* out, int32_t n, int32_t c, int32_t hw, void* stream);

@@ -60,10 +60,21 @@ def test_registry_interface():
         cb.ARCH_REGISTRY.get('nope')
     with pytest.raises(AssertionError):                      # duplicate names assert, registry.py:39
         cb.ARCH_REGISTRY.register(cb.CodeFormer)
-    r = cb.registry.Registry('x')
-    r._obj_map['CodeFormer'] = object
-    cb.install(r)
-    assert r.get('CodeFormer') is cb.CodeFormer
+    r = cb.registry.ArchTable('x')
+    r.add(object, 'CodeFormer')
+
+    @r.register()
+    class Other:        # decorator form, as the reference's arch files use it (codeformer_arch.py:160)
+        pass
+    assert r.get('Other') is Other
+    cb.install(r)                                            # existing entries are replaced, not added beside
+    assert r.get('CodeFormer') is cb.CodeFormer and r.get('VQAutoEncoder') is cb.VQAutoEncoder
+
+    class RefLike:      # an object shaped like the reference's registry (a private name -> class dict)
+        def __init__(self):
+            self._obj_map = {'CodeFormer': int}
+    rl = cb.install(RefLike())
+    assert rl._obj_map['CodeFormer'] is cb.CodeFormer
 
 
 def test_c_abi_exports_every_declared_symbol():

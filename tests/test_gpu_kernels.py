@@ -79,6 +79,36 @@ def test_conv_fused_groupnorm_silu_residual_epilogues(engine):
         raise
 
 
+# (N, Cin, Cout, H, act): the in-kernel operand transform (fp32 activation -> GroupNorm affine (+SiLU) -> fp16 hi/lo inside the
+# conv kernel) on both tile widths, with border tiles, several k-blocks and one-tile-high images
+XF_CASES = [(2, 64, 64, 64, 1), (1, 128, 64, 32, 1), (2, 256, 128, 32, 1), (1, 64, 128, 32, 0), (2, 512, 512, 16, 1),
+            (4, 128, 128, 16, 0)]
+
+
+@pytest.mark.parametrize('case', XF_CASES)
+def test_conv_in_kernel_operand_transform(case):
+    """vqgan_arch.py:14-20,153-160: conv(swish(GroupNorm(x))) with the normalisation applied inside the tcgen05 conv kernel
+    (engine 2) against torch CPU fp32 and against the fp32 CUDA-core engine.  x has a large per-channel offset so that a
+    wrong affine or a missing zero-padding of the NORMALISED tensor is visible at the image border."""
+    N, Cin, Cout, H, act = case
+    x = _rand(N, Cin, H, H, seed=11) * 1.5 + _rand(1, Cin, 1, 1, seed=12) * 3
+    gamma, beta = 1 + 0.2 * _rand(Cin, seed=13), 0.5 * _rand(Cin, seed=14)
+    w = _rand(Cout, Cin, 3, 3, seed=15, scale=1 / math.sqrt(9 * Cin))
+    b = _rand(Cout, seed=16, scale=0.1)
+    res = _rand(N, Cout, H, H, seed=17)
+    h = F.group_norm(x, 32, gamma, beta, eps=1e-6)
+    ref = F.conv2d(h * torch.sigmoid(h) if act else h, w, b, padding=1) + res
+    _, scale, shift = G.gn_coef(x, gamma, beta)
+    out_tc = G.conv2d(x, w, b, in_scale=scale, in_shift=shift, in_act=act, residual=res, engine=2).cpu()
+    out_f32 = G.conv2d(x, w, b, in_scale=scale, in_shift=shift, in_act=act, residual=res, engine=1).cpu()
+    bound = 6e-5 * float(ref.abs().max())
+    assert maxabs(out_tc, ref) < bound, 'tensor-core engine with the fused operand transform'
+    assert maxabs(out_f32, ref) < bound
+    from codeformer_b200 import _lib as L
+    _lib_status = L.load().cfb_check_async_status()
+    assert _lib_status == 0, L.load().cfb_last_error()
+
+
 @pytest.mark.parametrize('C,H', [(64, 64), (128, 32), (256, 16), (512, 16), (512, 64)])
 def test_group_norm_coef(C, H):
     x = _rand(2, C, H, H, seed=C + H) * 3 + 1
