@@ -161,7 +161,11 @@ def run_reference(args):
     value = batch * len(timed) / total
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(timed), 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config_dict(args.gpus, 32),
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': dict(config_dict(args.gpus, 32), sample_batch=batch,
+                           sample_note=f'the CPU arm times {batch} face(s) per step, not 32: a bounded sample of the batch-32 '
+                                       'workload (its per-face time is best at small batch, BASELINE.md section 2, so the '
+                                       'GPU/CPU ratio is conservative); it runs on ONE host whatever --gpus is'),
             'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                              'sample': f'{batch} face(s) per step (bounded sample of the batch-32 workload), '
                                        f'{len(timed)} timed steps, torch CPU fp32 oneDNN, best of 16/32 threads '
@@ -171,36 +175,119 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def dominant_kernel_roofline(torch, cb, batch, peaks, peak_kind):
-    """The dominant kernel = conv_tc_kernel on the most frequent shape (ResBlock 128->128 3x3 at 256^2: 13 launches of
-    19.33 GFLOP/face).  Timed alone -- operand planes and split weights prepared outside the timed
-    region -- with CUDA events on the launching stream (cfb_debug_time_conv), B=8 like the committed ncu capture."""
+def committed_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/): never a
+    constant in this file.  -> (bytes or None, source)."""
+    for name in ('round2_dominant_kernel.json', 'round1_dominant_kernel.json'):
+        path = os.path.join(ROOT, 'profiles', name)
+        if os.path.exists(path):
+            try:
+                d = json.load(open(path))
+                return float(d['dram_bytes_read']) + float(d['dram_bytes_write']), f'profiles/{name}: {d.get("source", "")}'
+            except Exception:
+                continue
+    return None, 'no committed capture found under profiles/'
+
+
+def time_conv_kernel(torch, N, H, Cin, Cout, xf, reps=20):
+    """CUDA-event time of ONE tcgen05 conv kernel (cfb_debug_time_conv): 3x3, stride 1.  xf=True: the kernel the forward
+    launches for a GroupNorm+SiLU consumer (fused operand transform on the fp32 activation, all-in)."""
     import ctypes
     from codeformer_b200 import _lib
     lib = _lib.load()
-    N, H, C = 8, 256, 128
     g = torch.Generator().manual_seed(3)
-    x = torch.randn(N, H, H, C, generator=g).cuda()
-    w = (torch.randn(C, C, 3, 3, generator=g) / (9 * C) ** 0.5).cuda()
-    out = torch.empty(N, H, H, C, device='cuda')
-    wsb = lib.cfb_conv2d_workspace_bytes(N, H, H, C, C, 3, 0)
+    x = torch.randn(N, H, H, Cin, generator=g).cuda()
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (9 * Cin) ** 0.5).cuda()
+    out = torch.empty(N, H, H, Cout, device='cuda')
+    sc = (1 + 0.1 * torch.randn(N, Cin, generator=g)).cuda() if xf else None
+    sh = (0.1 * torch.randn(N, Cin, generator=g)).cuda() if xf else None
+    wsb = lib.cfb_conv2d_workspace_bytes(N, H, H, Cin, Cout, 3, 0)
     ws = torch.empty(int(wsb), dtype=torch.uint8, device='cuda')
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     ms = ctypes.c_float(0)
-    _lib.check(lib.cfb_debug_time_conv(_lib.ptr(x), _lib.ptr(w), _lib.ptr(out), N, H, H, C, C, 3, 0, 20, _lib.ptr(ws), wsb, st,
-                                       ctypes.byref(ms)), 'cfb_debug_time_conv')
-    ms = float(ms.value)
+    _lib.check(lib.cfb_debug_time_conv(_lib.ptr(x), _lib.ptr(w), _lib.ptr(out), N, H, H, Cin, Cout, 3, 0, reps, _lib.ptr(ws), wsb, st,
+                                       _lib.ptr(sc), _lib.ptr(sh), 1 if xf else 0, ctypes.byref(ms)), 'cfb_debug_time_conv')
+    return float(ms.value)
+
+
+def dominant_kernel_roofline(torch, cb, batch, peaks, peak_kind):
+    """The dominant kernel = conv_tc_kernel on the most frequent shape (ResBlock conv 128->128 3x3 at 256^2: 13 launches of
+    19.33 GFLOP/face), in the variant the forward launches there: GroupNorm+SiLU applied to the fp32
+    activation inside the kernel (fused operand transform), split weights prepared at load time.  Timed alone with CUDA
+    events on the launching stream, B=8 like the committed ncu capture.  Also reported: the same shape on raw operand planes
+    and the 64->64 @512^2 layer (the worst conv family of round 1)."""
+    N, H, C = 8, 256, 128
+    ms = time_conv_kernel(torch, N, H, C, C, True)
+    ms_raw = time_conv_kernel(torch, N, H, C, C, False)
+    ms64 = time_conv_kernel(torch, N, 512, 64, 64, True)
     flops = 2.0 * N * H * H * C * C * 9
     achieved = flops / (ms * 1e-3) / 1e12
-    return {'bound': 'tensor', 'kernel': 'conv_tc_kernel<128,0,halo,pair>: conv 3x3 128->128 @256^2, B=8 (kernel only)',
+    traffic, tsrc = committed_traffic()
+    return {'bound': 'tensor', 'kernel': 'conv_tc_kernel<128,halo,pair,xform>: GroupNorm+SiLU+conv 3x3 128->128 @256^2, B=8 (kernel only, all-in)',
             'achieved': achieved, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s', 'frac': achieved / peaks['bf16_tflops'],
             'peak_kind': f'{peak_kind} bf16 burst (MEASURED_PEAKS.json)', 'ms_per_launch': ms,
             'algorithmic_gflop_per_launch': flops / 1e9,
             'executed_mma_passes': '2 tcgen05.mma.cta_group::2 (M=256) per k-step (N=256 + N=128) = 3x the nominal MACs (split-fp16 '
-                                   'operands); tensor pipe 83.6 % active in the ncu capture',
-            'traffic': 492.1e6, 'traffic_unit': 'bytes/launch',
-            'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum, profiles/round1_conv128_256_pair_full.raw.csv '
-                              '(ncu --set full, same shape and batch); algorithmic = 268 MB operand planes + 268 MB output'}
+                                   'operands): the 3-pass ceiling of this frac is 1/3',
+            'traffic': traffic, 'traffic_unit': 'bytes/launch',
+            'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum of ' + tsrc +
+                              ' (ncu --set full, same shape and batch); algorithmic = 268 MB fp32 input + 268 MB fp32 output',
+            'other_kernels': {
+                'conv 3x3 128->128 @256^2 B=8 on raw fp16 operand planes (no transform)': {
+                    'ms_per_launch': ms_raw, 'frac': flops / (ms_raw * 1e-3) / 1e12 / peaks['bf16_tflops']},
+                'GroupNorm+SiLU+conv 3x3 64->64 @512^2 B=8 (fused transform, all-in; same FLOPs)': {
+                    'ms_per_launch': ms64, 'frac': flops / (ms64 * 1e-3) / 1e12 / peaks['bf16_tflops']}}}
+
+
+def _median_ms(torch, fn, iters, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def extra_configs(torch, cb, S, net, peaks, dev):
+    """The other single-GPU configurations of BASELINE.json, measured AFTER the headline so they cannot perturb it:
+    configs[0] single-face latency on the GPU, configs[2] VectorQuantizer microbench (HBM roofline on 17.9 MB),
+    configs[3] VQAutoEncoder.forward at batch 64."""
+    out = {}
+    x1 = synthetic_batch(1, 5).to(dev)
+    out['latency_b1_ms'] = {'value': _median_ms(torch, lambda: net(x1, w=0.5, adain=True), 30), 'unit': 'ms',
+                            'what': 'BASELINE configs[0] on the GPU: one 512x512 face, CodeFormer.forward(w=0.5, adain=True) through '
+                                    'the public module API (CUDA-graph replay), median of 30, input resident on the device'}
+    g = torch.Generator().manual_seed(0)
+    E = torch.randn(1024, 256, generator=g)
+    z = torch.randn(32, 256, 16, 16, generator=g).to(dev)
+    vq = cb.VectorQuantizer(1024, 256, 0.25)
+    vq.embedding.weight.data.copy_(E)
+    vq = vq.to(dev)
+    ms = _median_ms(torch, lambda: vq(z, return_min_encodings=False), 50)
+    nbytes = 17.9e6            # SURVEY section 8(d) config 3: z 8.39 + E 1.05 + z_q 8.39 + idx 0.07 MB
+    out['vq_micro'] = {'ms': ms, 'vectors_per_s': 8192 / (ms * 1e-3), 'algorithmic_bytes': nbytes,
+                       'roofline': {'bound': 'hbm', 'achieved': nbytes / (ms * 1e-3) / 1e9, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                                    'frac': nbytes / (ms * 1e-3) / 1e9 / peaks['hbm_gbs']},
+                       'what': 'BASELINE configs[2]: VectorQuantizer.forward, z [32,256,16,16] vs 1024 codes, NCHW in / NCHW out, '
+                               'median of 50 (indices bit-exact vs the reference golden in tests/test_gpu_kernels.py)'}
+    del vq, z
+    vqae = cb.VQAutoEncoder(512, 64, [1, 2, 2, 4, 4, 8], 'nearest', 2, [16], 1024).to(dev).eval()
+    vqae.load_state_dict(S.random_state_dict(S.vqae_spec(), 2), strict=True)
+    x64 = synthetic_batch(64, 9).to(dev)
+    ms = _median_ms(torch, lambda: vqae(x64, return_min_encodings=False), 3, warm=2)
+    out['vqae_b64'] = {'faces_per_s': 64 / (ms * 1e-3), 'ms_per_step': ms, 'gflop_per_face': 580.59,
+                       'step_algorithmic_tflops': 64 / (ms * 1e-3) * 580.59 / 1e3,
+                       'what': 'BASELINE configs[3]: VQAutoEncoder(512,64,[1,2,2,4,4,8]).forward at batch 64, median of 3'}
+    del vqae, x64
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_b200(args):
@@ -227,12 +314,14 @@ def run_b200(args):
     xs_host = [synthetic_batch(batch, 100 + rank * 2 + i).pin_memory() for i in range(2)]
     xs = [x.to(dev) for x in xs_host]
     gathered = torch.empty((world * batch, 3, 512, 512), device=dev) if world > 1 else None
+    from codeformer_b200.parallel import pipelined_forward_gather
 
     def step(i):
-        out = net(xs[i % 2], w=0.5, adain=True)[0]
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, out)          # the one collective of the path (§8e)
-        return out
+        if world == 1:
+            return net(xs[i % 2], w=0.5, adain=True)[0]
+        # the one collective of the path (section 8e), off the critical path: the all-gather of the first half-batch runs on
+        # NCCL's stream while the second half computes (parallel.py)
+        return pipelined_forward_gather(net, xs[i % 2], gathered, chunks=args.gather_chunks, w=0.5, adain=True)[1]
 
     def barrier():
         if world > 1:
@@ -260,14 +349,56 @@ def run_b200(args):
     ms_total = float(ms.item())
     value = world * batch * args.steps / (ms_total * 1e-3)
 
+    # ---- multi-GPU evidence (section 8d config 5): the gathered tensor holds every rank's shard bit for bit, and where the
+    # step time goes on each rank (forward alone, gather alone; CUDA events)
+    multi = None
+    if world > 1:
+        local = step(0)
+        torch.cuda.synchronize()
+        same = torch.tensor([1 if torch.equal(gathered[rank * batch:(rank + 1) * batch], local) else 0], device=dev)
+        # every rank also checks the shard of its right neighbour against that rank's own result (sent as a checksum)
+        chk = torch.stack([gathered[r * batch:(r + 1) * batch].double().sum() for r in range(world)])
+        mine = local.double().sum().reshape(1)
+        allsum = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allsum, mine)
+        same2 = torch.tensor([1 if all(float(chk[r]) == float(allsum[r]) for r in range(world)) else 0], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        dist.all_reduce(same2, op=dist.ReduceOp.MIN)
+        fe0, fe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        fe0.record()
+        for i in range(3):
+            o_loc = net(xs[i % 2], w=0.5, adain=True)[0]
+        fe1.record()
+        torch.cuda.synchronize()
+        fwd_ms = fe0.elapsed_time(fe1) / 3
+        barrier()
+        fe0.record()
+        for i in range(3):
+            dist.all_gather_into_tensor(gathered, o_loc)
+        fe1.record()
+        torch.cuda.synchronize()
+        gat_ms = fe0.elapsed_time(fe1) / 3
+        t = torch.tensor([fwd_ms, gat_ms], device=dev)
+        tmax, tmin = t.clone(), t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        multi = {'gather_bit_identical': bool(int(same.item()) == 1 and int(same2.item()) == 1),
+                 'forward_only_ms_per_rank_min_max': [float(tmin[0]), float(tmax[0])],
+                 'blocking_gather_only_ms_min_max': [float(tmin[1]), float(tmax[1])],
+                 'gather_bytes_per_rank': batch * 3 * 512 * 512 * 4, 'gather_chunks': args.gather_chunks,
+                 'note': 'the timed step overlaps the gather of half-batch 1 with the compute of half-batch 2; the step is '
+                         'max over ranks, each GPU under its own power-capped clock'}
+
     # ---- e2e: public API with host buffers, H2D + D2H inside the timed region
     out_host = torch.empty((batch, 3, 512, 512), dtype=torch.float32, pin_memory=True)
 
     def step_e2e(i):
         x = xs_host[i % 2].to(dev, non_blocking=True)
-        out = net(x, w=0.5, adain=True)[0]
         if world > 1:
-            dist.all_gather_into_tensor(gathered, out)
+            out = pipelined_forward_gather(net, x, gathered, chunks=args.gather_chunks, w=0.5, adain=True)[1]
+        else:
+            out = net(x, w=0.5, adain=True)[0]
         out_host.copy_(out, non_blocking=True)
         torch.cuda.current_stream().synchronize()               # the caller reads the result (tensor2img .cpu())
     e_steps = max(2, min(args.steps, 5))
@@ -314,6 +445,11 @@ def run_b200(args):
                 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof}
         if e2e_u8:
             line['e2e_u8'] = e2e_u8
+        if multi:
+            line['multi_gpu'] = multi
+            line['gather_bit_identical'] = multi['gather_bit_identical']
+        if world == 1 and not args.no_extras:
+            line.update(extra_configs(torch, cb, S, net, peaks, dev))
         if world == 1 and not args.no_cpu_baseline:
             times, cores = time_oracle(2, 3)
             best = min(times[1:])
@@ -334,6 +470,8 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=32, help='faces per GPU (the metric is quoted at 32)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip BASELINE configs 1/3/4 (latency, VQ microbench, VQAE B=64)')
+    ap.add_argument('--gather-chunks', type=int, default=2, help='N>1: sub-batches whose all-gather overlaps the next one\'s compute')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -8,4 +8,13 @@ Public surface = the reference's plugin API for this path:
 from .registry import ARCH_REGISTRY, install          # noqa: F401
 from .arch import CodeFormer, VQAutoEncoder, VectorQuantizer   # noqa: F401
 
-__all__ = ['ARCH_REGISTRY', 'install', 'CodeFormer', 'VQAutoEncoder', 'VectorQuantizer']
+
+def check_async_status():
+    """Raise ``RuntimeError`` if a kernel of an earlier (asynchronous) forward on the current device reported a failure --
+    a tensor-core pipeline time-out or an activation outside the fp16 operand range.  Call after synchronising the stream;
+    the next forward and the ``restore_faces`` / ``forward_host`` front-ends check by themselves (include/cfb200.h)."""
+    from . import _lib
+    _lib.check(_lib.load().cfb_check_async_status(), 'check_async_status')
+
+
+__all__ = ['ARCH_REGISTRY', 'install', 'CodeFormer', 'VQAutoEncoder', 'VectorQuantizer', 'check_async_status']

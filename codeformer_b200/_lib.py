@@ -59,7 +59,7 @@ SIGNATURES = {
     'cfb_debug_umma_pair': (c_int, [c_int32, c_int32, _P, _P, c_int32, _P]),
     'cfb_debug_umma_rate': (c_int, [c_int32, c_int32, c_int32, _P, c_int32, _P]),
     'cfb_debug_time_conv': (c_int, [_P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P, c_int64,
-                                   _P, POINTER(c_float)]),
+                                   _P, _P, _P, c_int32, POINTER(c_float)]),
     'cfb_check_async_status': (c_int, []),
     'cfb_debug_set_wait_limit': (c_int, [c_int64]),
     'cfb_debug_inject_fault': (c_int, [c_int32]),

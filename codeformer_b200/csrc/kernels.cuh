@@ -116,8 +116,10 @@ size_t gn_workspace_bytes(int N, int HW, int C);
 int gn_coef(const float* x, const float* gamma, const float* beta, float* scale, float* shift, int N, int HW, int C,
             int groups, float eps, void* ws, cudaStream_t st);
 // finalize from the tensor-core epilogue's partial sums (slots per image = tiles_per_image*4)
+// scratch: gn_final_scratch_bytes(N, slots) bytes; counters: N zero-initialised unsigned (left zero again by the kernel)
+size_t gn_final_scratch_bytes(int N, int slots);
 int gn_coef_from_partials(const float* part, int slots, const float* gamma, const float* beta, float* scale, float* shift,
-                          int N, int HW, int C, int groups, float eps, cudaStream_t st);
+                          int N, int HW, int C, int groups, float eps, void* scratch, unsigned* counters, cudaStream_t st);
 // partial sums of cat([a,b]) (2C channels, 32 groups) from the partial sums of a and b (C channels each)
 int gn_cat_partials(const float* a_part, const float* b_part, float* out_part, int64_t total_slots, cudaStream_t st);
 int affine_act(const float* x, const float* scale, const float* shift, float* y, int N, int HW, int C, int act,

@@ -171,6 +171,8 @@ enum { B_CONV = 0, B_RES, B_ATTN, B_DOWN, B_UP, B_NORM };
 
 using namespace cfb;
 
+constexpr int GN_COUNTERS = 1 << 16;
+
 struct cfb_net {
   cfb_config cfg;
   std::mutex mu;
@@ -194,6 +196,8 @@ struct cfb_net {
   // small owned copies of norm params etc. live in the slab too
   std::vector<std::pair<const float**, std::pair<std::string, int64_t>>> vec_params;  // (dst, (name, numel))
   std::vector<ConvW*> convs;
+  unsigned* gn_counters = nullptr;    // ticket-counter ring of the split GroupNorm finalize (in the slab, zero between uses)
+  int gn_ctr_pos = 0;
   int device = -1;                    // CUDA device the slab / prepared weights live on
   std::map<int, int64_t> ws_memo;     // batch -> cfb_workspace_bytes (16 host-side dry runs per miss)
   int engine = 0;                     // 0 auto (tcgen05 where the shape allows), 1 fp32 CUDA cores, 2 tcgen05 only
@@ -392,6 +396,7 @@ static int prepare(cfb_net* n, cudaStream_t st) {
   const size_t scratch = align256((size_t)3 * 512 * 512 * 4) + align256(3 * 512 * 4);
   total += scratch;
   total += 256 * (n->enc.size() + n->gen.size());      // per-AttnBlock device constants
+  total += align256((size_t)GN_COUNTERS * sizeof(unsigned));
   // the net lives on the device that is current at prepare time (net.to(other_gpu) -> a new prepare): slab, SM count and
   // engine availability all follow it
   int dev = 0, major = 0, sms = 148;
@@ -419,6 +424,9 @@ static int prepare(cfb_net* n, cudaStream_t st) {
   CFB_CHECK(async_status_init(st));
   char* p = (char*)n->slab;
   auto take = [&](size_t bytes) { char* r = p; p += align256(bytes); return r; };
+  n->gn_counters = (unsigned*)take((size_t)GN_COUNTERS * sizeof(unsigned));
+  n->gn_ctr_pos = 0;
+  CFB_CUDA(cudaMemsetAsync(n->gn_counters, 0, (size_t)GN_COUNTERS * sizeof(unsigned), st));
   float* qkv_w = (float*)take((size_t)3 * 512 * 512 * 4);
   float* qkv_b = (float*)take(3 * 512 * 4);
   for (ConvW* c : n->convs) {
@@ -593,8 +601,19 @@ struct Fwd {
     CFB_CHECK(alloc_raw((void**)scale, (size_t)x.N * x.C * 4));
     CFB_CHECK(alloc_raw((void**)shift, (size_t)x.N * x.C * 4));
     if (x.gn_part) {   // statistics already reduced per tile by the producing conv's epilogue
-      if (!dry)
-        CFB_CHECK(gn_coef_from_partials(x.gn_part, x.gn_slots, w.gamma, w.beta, *scale, *shift, x.N, x.H * x.W, x.C, 32, 1e-6f, st));
+      void* scr = nullptr;
+      const size_t sb = gn_final_scratch_bytes(x.N, x.gn_slots);
+      if (sb) CFB_CHECK(alloc_raw(&scr, sb));
+      if (!dry) {
+        CFB_REQUIRE(x.N <= GN_COUNTERS / 2, "GroupNorm finalize: batch larger than the ticket-counter ring");
+        // ticket counters: a ring in the net's slab, zero between uses (the kernel resets them); every call takes the next N
+        // so that forwards in flight on other streams never share a counter
+        if (n->gn_ctr_pos + x.N > GN_COUNTERS) n->gn_ctr_pos = 0;
+        unsigned* ctr = n->gn_counters + n->gn_ctr_pos;
+        n->gn_ctr_pos += x.N;
+        CFB_CHECK(gn_coef_from_partials(x.gn_part, x.gn_slots, w.gamma, w.beta, *scale, *shift, x.N, x.H * x.W, x.C, 32, 1e-6f, scr, ctr, st));
+      }
+      if (scr) release_raw(scr);
       return 0;
     }
     void* ws = nullptr;
@@ -1421,7 +1440,7 @@ int cfb_debug_umma_pair(int32_t n, int32_t reps, float* vals_dev, int64_t* info_
 
 int cfb_debug_time_conv(const float* in, const float* weight_oihw, float* out, int32_t n, int32_t h, int32_t w, int32_t cin,
                         int32_t cout, int32_t ksize, int32_t mode, int32_t reps, void* workspace, int64_t workspace_bytes,
-                        void* stream, float* ms_per_launch) {
+                        void* stream, const float* in_scale, const float* in_shift, int32_t in_act, float* ms_per_launch) {
   API_BEGIN
   CFB_REQUIRE(in && weight_oihw && out && workspace && ms_per_launch && reps > 0, "cfb_debug_time_conv: bad argument");
   CFB_REQUIRE(workspace_bytes >= cfb_conv2d_workspace_bytes(n, h, w, cin, cout, ksize, mode), "cfb_debug_time_conv: workspace too small");
@@ -1445,6 +1464,11 @@ int cfb_debug_time_conv(const float* in, const float* weight_oihw, float* out, i
   CFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   if (mode == cfb::CONV_UP) CFB_CHECK(cfb::tc_split_weights_up4(weight_oihw, whi, wlo, cout, cin, wsc, st));
   else CFB_CHECK(cfb::tc_split_weights(weight_oihw, whi, wlo, cout, cin, ksize, wsc, st));
+  CFB_CHECK(cfb::async_status_init(nullptr));
+  a.in_scale = in_scale; a.in_shift = in_shift; a.in_act = in_act;
+  // a GroupNorm-affine (+SiLU) input: the kernel timed is the one the forward ships -- fused operand transform where the
+  // engine has it (all-in: no separate prep pass exists), otherwise prep once outside the timed region
+  if (in_scale && in_shift && cfb::tc_can_xform(a)) { a.xform = true; a.skip_prep = true; }
   CFB_CHECK(cfb::conv_tc(a, p, sms, st));          // operand prep + one warm-up launch
   a.skip_prep = true;
   for (int i = 0; i < 2; ++i) CFB_CHECK(cfb::conv_tc(a, p, sms, st));

@@ -573,33 +573,66 @@ int gn_coef(const float* x, const float* gamma, const float* beta, float* scale,
   return 0;
 }
 
-__global__ void __launch_bounds__(1024) gn_final_f32_kernel(const float* __restrict__ part, const float* __restrict__ gamma,
-                                                            const float* __restrict__ beta, float* __restrict__ scale,
-                                                            float* __restrict__ shift, int HW, int C, int slots, float eps) {
-  // 32 groups; thread t -> group t%32, slot stripe t/32 (32 stripes, fixed order => deterministic)
-  __shared__ double ps[32][33], pq[32][33];
+// GroupNorm finalize from the conv epilogue's per-tile partial sums.  A 512x512 image has 8192 partial slots (2 MB): one CTA
+// per image was latency-bound (11 us per call, 72 calls per forward = 10 % of a single-face forward), so the slots of an
+// image are split over G CTAs; each reduces its contiguous range in a fixed order into fp64, publishes 64 doubles, and the
+// LAST CTA of the image to finish (ticket counter) adds the G partials in index order and writes scale / shift.  The
+// summation tree depends only on (slots, G(slots)) -- not on the batch, not on which CTA happens to be last -- so the result
+// is deterministic and batch-invariant.  Counters are zero on entry and reset by the last CTA.
+__host__ __device__ inline int gn_final_split(int slots) {
+  int g = slots / 256;
+  return g < 1 ? 1 : (g > 16 ? 16 : g);
+}
+__global__ void __launch_bounds__(256) gn_final_f32_kernel(const float* __restrict__ part, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float* __restrict__ scale,
+                                                           float* __restrict__ shift, int HW, int C, int slots, float eps,
+                                                           double* __restrict__ part2, unsigned* __restrict__ counters) {
+  __shared__ double ps[8][33], pq[8][33];
   __shared__ double gmean[32], grstd[32];
-  const int n = blockIdx.x, t = threadIdx.x;
+  __shared__ int is_last;
+  const int n = blockIdx.y, G = gridDim.x, blk = blockIdx.x, t = threadIdx.x;
   const int g = t & 31, stripe = t >> 5;
+  const int per = (slots + G - 1) / G;
+  const int lo = blk * per, hi = min(slots, lo + per);
   double a = 0.0, b = 0.0;
   const float2* base = reinterpret_cast<const float2*>(part) + (int64_t)n * slots * 32 + g;
-  int k = stripe;
-  for (; k + 96 < slots; k += 128) {     // 4 independent loads in flight
-    const float2 v0 = __ldg(base + (int64_t)k * 32), v1 = __ldg(base + (int64_t)(k + 32) * 32);
-    const float2 v2 = __ldg(base + (int64_t)(k + 64) * 32), v3 = __ldg(base + (int64_t)(k + 96) * 32);
+  int k = lo + stripe;
+  for (; k + 24 < hi; k += 32) {     // 4 independent loads in flight
+    const float2 v0 = __ldg(base + (int64_t)k * 32), v1 = __ldg(base + (int64_t)(k + 8) * 32);
+    const float2 v2 = __ldg(base + (int64_t)(k + 16) * 32), v3 = __ldg(base + (int64_t)(k + 24) * 32);
     a += ((double)v0.x + (double)v1.x) + ((double)v2.x + (double)v3.x);
     b += ((double)v0.y + (double)v1.y) + ((double)v2.y + (double)v3.y);
   }
-  for (; k < slots; k += 32) {
+  for (; k < hi; k += 8) {
     const float2 v = __ldg(base + (int64_t)k * 32);
     a += (double)v.x; b += (double)v.y;
   }
   ps[stripe][g] = a; pq[stripe][g] = b;
   __syncthreads();
+  double sa = 0.0, sb = 0.0;
+  if (t < 32) {
+    for (int s = 0; s < 8; ++s) { sa += ps[s][t]; sb += pq[s][t]; }
+  }
+  if (G > 1) {
+    if (t < 32) {
+      double* dst = part2 + ((int64_t)n * G + blk) * 64;
+      dst[2 * t] = sa; dst[2 * t + 1] = sb;
+      __threadfence();
+    }
+    __syncthreads();
+    if (t == 0) is_last = (atomicAdd(counters + n, 1u) == (unsigned)(G - 1));
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (t < 32) {
+      sa = 0.0; sb = 0.0;
+      const double* src = part2 + (int64_t)n * G * 64;
+      for (int q = 0; q < G; ++q) { sa += __ldcg(src + q * 64 + 2 * t); sb += __ldcg(src + q * 64 + 2 * t + 1); }
+    }
+    if (t == 0) counters[n] = 0u;
+  }
   const int cpg = C / 32;
   if (t < 32) {
-    double sa = 0.0, sb = 0.0;
-    for (int s = 0; s < 32; ++s) { sa += ps[s][t]; sb += pq[s][t]; }
     const double cnt = (double)HW * cpg;
     const double mean = sa / cnt;
     double var = sb / cnt - mean * mean;
@@ -608,18 +641,25 @@ __global__ void __launch_bounds__(1024) gn_final_f32_kernel(const float* __restr
     grstd[t] = 1.0 / sqrt(var + (double)eps);
   }
   __syncthreads();
-  for (int c = t; c < C; c += 1024) {
+  for (int c = t; c < C; c += 256) {
     const int gg = c / cpg;
     const double sc = grstd[gg] * (double)gamma[c];
     scale[(int64_t)n * C + c] = (float)sc;
     shift[(int64_t)n * C + c] = (float)((double)beta[c] - gmean[gg] * sc);
   }
 }
+size_t gn_final_scratch_bytes(int N, int slots) {
+  const int G = gn_final_split(slots);
+  return G > 1 ? (size_t)N * G * 64 * sizeof(double) : 0;
+}
 int gn_coef_from_partials(const float* part, int slots, const float* gamma, const float* beta, float* scale, float* shift,
-                          int N, int HW, int C, int groups, float eps, cudaStream_t st) {
+                          int N, int HW, int C, int groups, float eps, void* scratch, unsigned* counters, cudaStream_t st) {
   CFB_REQUIRE(groups == 32 && C % 32 == 0, "gn_coef_from_partials: 32 groups only");
   if (N == 0) return 0;
-  gn_final_f32_kernel<<<N, 1024, 0, st>>>(part, gamma, beta, scale, shift, HW, C, slots, eps);
+  const int G = gn_final_split(slots);
+  CFB_REQUIRE(G == 1 || (scratch && counters), "gn_coef_from_partials: scratch / counters missing");
+  CFB_REQUIRE(N <= 65535, "gn_coef_from_partials: batch too large");
+  gn_final_f32_kernel<<<dim3(G, N), 256, 0, st>>>(part, gamma, beta, scale, shift, HW, C, slots, eps, (double*)scratch, counters);
   CFB_LAUNCH_CHECK();
   return 0;
 }

@@ -170,11 +170,13 @@ int cfb_debug_umma_probe(const void* a_f16, int32_t rows_a, const void* b_f16, c
 /* CTA-pair probe (tcgen05.mma.cta_group::2): vals [ctas][2][4] accumulator samples, info [ctas][2] = cycles, tmem base */
 int cfb_debug_umma_pair(int32_t n, int32_t reps, float* vals_dev, int64_t* info_dev, int32_t ctas, void* stream);
 int cfb_debug_umma_rate(int32_t n, int32_t nacc, int32_t reps, int64_t* out_dev, int32_t ctas, void* stream);
-/* diagnostics / bench: average device time (CUDA events on `stream`) of the tcgen05 conv KERNEL alone -- weights split
- * and operand planes prepared once outside the timed region -- over `reps` launches (bench.py roofline). */
+/* diagnostics / bench: average device time (CUDA events on `stream`) of the tcgen05 conv KERNEL alone over `reps` launches
+ * (bench.py roofline).  With in_scale/in_shift (per-(n,cin) GroupNorm affine) and in_act the kernel is the one the forward
+ * launches for a GroupNorm+SiLU consumer: the fused-operand-transform variant reading the fp32 activation (all-in, no prep
+ * pass exists); without them the weights are split and the raw operand planes prepared once outside the timed region. */
 int cfb_debug_time_conv(const float* in, const float* weight_oihw, float* out, int32_t n, int32_t h, int32_t w, int32_t cin,
                         int32_t cout, int32_t ksize, int32_t mode, int32_t reps, void* workspace, int64_t workspace_bytes,
-                        void* stream, float* ms_per_launch);
+                        void* stream, const float* in_scale, const float* in_shift, int32_t in_act, float* ms_per_launch);
 /* Asynchronous failures.  Kernels never trap and never leave a sticky CUDA error behind (the reference's callers catch
  * RuntimeError and fall back to the input face, inference_codeformer.py:209-211; web-demos/hugging_face/app.py:176): a
  * barrier time-out of the tensor-core pipeline or an activation outside the fp16 operand range (|x| > 65504) sets a bit

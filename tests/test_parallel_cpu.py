@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from codeformer_b200.parallel import gather_faces, shard_bounds, sharded_forward
+from codeformer_b200.parallel import gather_faces, pipelined_forward_gather, shard_bounds, sharded_forward
 
 
 def test_shard_bounds_cover_and_balance():
@@ -41,6 +41,13 @@ def _worker(rank, world, port, batch, ret):
         ok = torch.equal(out, full)                       # gathered result is bit-identical to the unsharded run
         lo, hi = shard_bounds(batch, rank, world)
         ok = ok and torch.equal(gather_faces(full[lo:hi], batch), full)
+        # pipelined variant (equal shards per rank): sub-batch k's gather overlaps sub-batch k+1's compute; same bits
+        per = 3
+        xg = torch.randn(world * per, 3, 8, 8, generator=g)
+        fullg = _FakeNet()(xg, w=0.5)[0]
+        for chunks in (1, 2, 3):
+            got, mine = pipelined_forward_gather(_FakeNet(), xg[rank * per:(rank + 1) * per], chunks=chunks, w=0.5)
+            ok = ok and torch.equal(got, fullg) and torch.equal(mine, fullg[rank * per:(rank + 1) * per])
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()

@@ -38,7 +38,7 @@ for (C, H) in [(128, 256), (64, 512), (256, 128)]:
         torch.cuda.synchronize()
         full = e0.elapsed_time(e1) / (2 * reps)
         ms = ctypes.c_float(0)
-        _lib.check(lib.cfb_debug_time_conv(_lib.ptr(x), _lib.ptr(w), _lib.ptr(y), N, H, H, C, C, 3, 0, 2 * reps, _lib.ptr(ws), wsb, st,
+        _lib.check(lib.cfb_debug_time_conv(_lib.ptr(x), _lib.ptr(w), _lib.ptr(y), N, H, H, C, C, 3, 0, 2 * reps, _lib.ptr(ws), wsb, st, None, None, 0,
                                            ctypes.byref(ms)))
         print(json.dumps({'shape': f'{C}->{C}@{H}^2', 'batch': N, 'prep+conv_us_per_face': round(full / N * 1e3, 1),
                           'conv_only_us_per_face': round(ms.value / N * 1e3, 1),
