@@ -262,8 +262,9 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // GPU and never as a sticky context error (SURVEY.md section 8(b) "Errors": the reference's callers catch RuntimeError and
 // fall back to the input face, inference_codeformer.py:209-211).  On time-out the waiting thread raises the device-wide
 // abort flag and reports through the host-mapped status word; every other wait loop sees the flag after its next failed
-// try_wait and falls through, the roles run their loops to the end without blocking, the kernel exits normally and the host
-// turns the status word into an error (runtime.cu: async_status_check).  The results of that launch are garbage by contract.
+// try_wait; a warp that has seen it leaves its role loop at once (no further TMA / MMA / barrier traffic), all warps meet at
+// the kernel's tear-down, the kernel exits normally and the host turns the status word into an error (runtime.cu:
+// async_status_check).  The results of that launch are garbage by contract.
 __device__ unsigned g_abort = 0;                 // per device: set on a barrier time-out, cleared by the host when it reports it
 __device__ unsigned* g_status_host = nullptr;    // host-mapped status word (bit 0: barrier time-out, bit 1: fp16 operand overflow)
 __device__ long long g_wait_limit = 4000000000LL;   // cycles (~2 s); the fault-injection test lowers it
@@ -275,25 +276,48 @@ __device__ __noinline__ void mbar_timeout() {
 __device__ __noinline__ void report_overflow() {
   if (g_status_host) { atomicOr_system(g_status_host, CFB_STATUS_OVERFLOW); __threadfence_system(); }
 }
+// RELAX_NS > 0: a producer / helper role whose wake-up latency is not critical sleeps between polls, leaving the issue slots
+// to the working warps of its scheduler (a failed try_wait comes back after a few hundred cycles, whatever the hint says:
+// in the round-2 profile the poll loops of 19 warps were 40 % of all executed instructions).  The abort flag and the
+// time-out clock are only looked at every 128 failed polls.
+template <int RELAX_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, bool& aborted) {
-  if (aborted) return;                     // this thread has seen the abort: run the role loop to its end without blocking
   uint32_t done = 0;
+  uint32_t polls = 0;
   long long t0 = 0;
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"      // suspend-time hint: the warp sleeps instead of
-        "selp.u32 %0, 1, 0, p;\n\t}"                                          // competing for issue slots while it polls
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
         : "r"(bar), "r"(parity), "r"(0x989680u)
         : "memory");
     if (done) break;
-    if (*(volatile unsigned*)&g_abort) { aborted = true; break; }   // slow path only: a healthy wait succeeds on its first try_wait
-    if (t0 == 0) t0 = clock64();
-    else if (clock64() - t0 > *(volatile long long*)&g_wait_limit) { mbar_timeout(); aborted = true; break; }
+    if (RELAX_NS > 0) __nanosleep(RELAX_NS);
+    if ((++polls & 127u) == 0u) {
+      if (*(volatile unsigned*)&g_abort) { aborted = true; break; }
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > *(volatile long long*)&g_wait_limit) { mbar_timeout(); aborted = true; break; }
+    }
+  }
+  aborted = __any_sync(0xffffffffu, aborted);      // the whole (converged) warp takes the same decision
+}
+// diagnostics kernels: plain bounded wait
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity), "r"(0x989680u)
+        : "memory");
+    if (!done && clock64() - t0 > *(volatile long long*)&g_wait_limit) { mbar_timeout(); break; }
   }
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { bool a = false; mbar_wait(bar, parity, a); }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -402,8 +426,8 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
 }
 // wait on a LOCAL barrier whose arrivals may come from the peer CTA (cluster-scope acquire)
 __device__ __forceinline__ void mbar_wait_cl(uint32_t bar, uint32_t parity, bool& aborted) {
-  if (aborted) return;
   uint32_t done = 0;
+  uint32_t polls = 0;
   long long t0 = 0;
   while (true) {
     asm volatile(
@@ -414,10 +438,13 @@ __device__ __forceinline__ void mbar_wait_cl(uint32_t bar, uint32_t parity, bool
         : "r"(bar), "r"(parity), "r"(0x989680u)
         : "memory");
     if (done) break;
-    if (*(volatile unsigned*)&g_abort) { aborted = true; break; }
-    if (t0 == 0) t0 = clock64();
-    else if (clock64() - t0 > *(volatile long long*)&g_wait_limit) { mbar_timeout(); aborted = true; break; }
+    if ((++polls & 127u) == 0u) {
+      if (*(volatile unsigned*)&g_abort) { aborted = true; break; }
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > *(volatile long long*)&g_wait_limit) { mbar_timeout(); aborted = true; break; }
+    }
   }
+  aborted = __any_sync(0xffffffffu, aborted);
 }
 // TMA loads of a CTA pair: data lands in the issuing CTA's shared memory, the byte count is signalled on `cluster_bar`,
 // which may live in the peer (leader) CTA
@@ -660,7 +687,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
-  bool aborted = false;      // set when a barrier wait timed out anywhere on the device: finish without blocking (see mbar_wait)
+  bool aborted = false;      // set when a barrier wait timed out anywhere on the device: leave the role loop (see mbar_wait)
 
   if (warp == 0 && lane == 0) {
     for (int a = 0; a < 3; ++a) {
@@ -729,7 +756,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if constexpr (HALO) {
           for (int kb = 0; kb < p.kblocks; ++kb) {
             if constexpr (!XF) {
-            mbar_wait(smem_u32(aempty + aslot), aphase ^ 1, aborted);
+            mbar_wait<40>(smem_u32(aempty + aslot), aphase ^ 1, aborted); if (aborted) goto teardown;
             if (elect_one()) {
               const uint32_t sa = smem_u32(smem + aslot * Cfg::H_A_SLOT);
               if constexpr (PAIR) {
@@ -749,7 +776,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
             for (int tap = 0; tap < p.taps; ++tap) {
               const int btap = p.up4 ? (mt & 3) * 4 + tap : tap;      // Upsample: weight slice of this output parity
-              mbar_wait(smem_u32(empty + stage), phase ^ 1, aborted);
+              mbar_wait<40>(smem_u32(empty + stage), phase ^ 1, aborted); if (aborted) goto teardown;
               if (elect_one()) {
                 const uint32_t sb = smem_u32(ring_base + stage * RING_BYTES);
                 if constexpr (PAIR) {
@@ -776,7 +803,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             if (p.up4) { r = (tap >> 1) + par_y; s = (tap & 1) + par_x; btap = (mt & 3) * 4 + tap; }
             else { r = (p.taps == 9) ? tap / 3 : 0; s = (p.taps == 9) ? tap - r * 3 : 0; }
             for (int kb = 0; kb < p.kblocks; ++kb) {
-              mbar_wait(smem_u32(empty + stage), phase ^ 1, aborted);
+              mbar_wait<40>(smem_u32(empty + stage), phase ^ 1, aborted); if (aborted) goto teardown;
               if (elect_one()) {
                 const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
                 const int b3 = p.b_batched ? n : btap;
@@ -833,15 +860,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               const int par_y = par >> 1, par_x = par & 1;
               int it = 0;
               for (int kb = 0; kb < p.kblocks; ++kb) {
-                mbar_wait_cl(smem_u32(afull + aslot), aphase, aborted);
+                mbar_wait_cl(smem_u32(afull + aslot), aphase, aborted); if (aborted) goto teardown;
                 const uint32_t a_hi0 = smem_u32(smem + aslot * Cfg::H_A_SLOT), a_lo0 = a_hi0 + (XF ? Cfg::X_A_PLANE2 : Cfg::H_A_PLANE);
                 for (int tap = 0; tap < p.taps; ++tap, ++it) {
                   int r = (p.taps == 9) ? tap / 3 : 0;
                   int sft = (p.taps == 9) ? tap - r * 3 : 0;
                   if (p.up4) { r = (tap >> 1) + par_y; sft = (tap & 1) + par_x; }
                   const bool first = (it % p.chunk) == 0;
-                  if (first) mbar_wait_cl(smem_u32(cempty + slot), slot_phase ^ 1, aborted);
-                  mbar_wait_cl(smem_u32(full + stage), phase, aborted);
+                  if (first) mbar_wait_cl(smem_u32(cempty + slot), slot_phase ^ 1, aborted); if (aborted) goto teardown;
+                  mbar_wait_cl(smem_u32(full + stage), phase, aborted); if (aborted) goto teardown;
                   tc_fence_after();
                   if (elect_one()) {
                     const uint32_t d_tmem = tmem_base + (uint32_t)(slot * Cfg::SLOT_COLS);
@@ -874,15 +901,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const int par_y = par >> 1, par_x = par & 1;
           int it = 0;
           for (int kb = 0; kb < p.kblocks; ++kb) {
-            mbar_wait(smem_u32(afull + aslot), aphase, aborted);
+            mbar_wait(smem_u32(afull + aslot), aphase, aborted); if (aborted) goto teardown;
             const uint32_t a_hi0 = smem_u32(smem + aslot * Cfg::H_A_SLOT), a_lo0 = a_hi0 + Cfg::H_A_PLANE;
             for (int tap = 0; tap < p.taps; ++tap, ++it) {
               int r = (p.taps == 9) ? tap / 3 : 0;
               int sft = (p.taps == 9) ? tap - r * 3 : 0;
               if (p.up4) { r = (tap >> 1) + par_y; sft = (tap & 1) + par_x; }
               const bool first = (it % p.chunk) == 0;
-              if (first) mbar_wait(smem_u32(cempty + slot), slot_phase ^ 1, aborted);
-              mbar_wait(smem_u32(full + stage), phase, aborted);
+              if (first) mbar_wait(smem_u32(cempty + slot), slot_phase ^ 1, aborted); if (aborted) goto teardown;
+              mbar_wait(smem_u32(full + stage), phase, aborted); if (aborted) goto teardown;
               tc_fence_after();
               if (elect_one()) {
                 const uint32_t d_tmem = tmem_base + (uint32_t)(slot * Cfg::SLOT_COLS);
@@ -916,10 +943,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (rank == 0) {
           for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
             for (int it0 = 0; it0 < nk; it0 += p.chunk) {
-              mbar_wait_cl(smem_u32(cempty + slot), slot_phase ^ 1, aborted);
+              mbar_wait_cl(smem_u32(cempty + slot), slot_phase ^ 1, aborted); if (aborted) goto teardown;
               const int it1 = (it0 + p.chunk < nk) ? it0 + p.chunk : nk;
               for (int it = it0; it < it1; ++it) {
-                mbar_wait_cl(smem_u32(full + stage), phase, aborted);
+                mbar_wait_cl(smem_u32(full + stage), phase, aborted); if (aborted) goto teardown;
                 tc_fence_after();
                 if (elect_one()) {
                   const uint32_t d_tmem = tmem_base + (uint32_t)(slot * Cfg::SLOT_COLS);
@@ -944,10 +971,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       } else {
         for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
           for (int it0 = 0; it0 < nk; it0 += p.chunk) {
-            mbar_wait(smem_u32(cempty + slot), slot_phase ^ 1, aborted);
+            mbar_wait(smem_u32(cempty + slot), slot_phase ^ 1, aborted); if (aborted) goto teardown;
             const int it1 = (it0 + p.chunk < nk) ? it0 + p.chunk : nk;
             for (int it = it0; it < it1; ++it) {
-              mbar_wait(smem_u32(full + stage), phase, aborted);
+              mbar_wait(smem_u32(full + stage), phase, aborted); if (aborted) goto teardown;
               tc_fence_after();
               if (elect_one()) {
                 const uint32_t d_tmem = tmem_base + (uint32_t)(slot * Cfg::SLOT_COLS);
@@ -986,7 +1013,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
         const int y0 = ty * p.BH, x0 = tx * p.BW;
         for (int kb = 0; kb < p.kblocks; ++kb) {
-          mbar_wait(smem_u32(aempty + aslot), aphase ^ 1, aborted);       // every MMA that read this slot has completed
+          mbar_wait<40>(smem_u32(aempty + aslot), aphase ^ 1, aborted); if (aborted) goto teardown;       // every MMA that read this slot has completed
           if (elect_one()) {
             const uint32_t sa = smem_u32(smem + aslot * Cfg::H_A_SLOT);
             const uint32_t rb = smem_u32(araw + aslot);
@@ -1049,7 +1076,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
             for (int k = 0; k < 8; ++k) { sc[k] = 1.f; sh[k] = 0.f; }
           }
-          mbar_wait(smem_u32(araw + aslot), aphase, aborted);
+          mbar_wait<20>(smem_u32(araw + aslot), aphase, aborted); if (aborted) goto teardown;
           const uint32_t base0 = smem_u32(smem + aslot * Cfg::H_A_SLOT);
           const uint32_t src_base = base0 + (pl ? (uint32_t)Cfg::X_A_PLANE2 : 0u);
           const uint32_t lo_base = base0 + (uint32_t)Cfg::X_A_PLANE2;
@@ -1106,7 +1133,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
       for (int j = 0; j < HC; ++j) acc[j] = 0.f;
       for (int it0 = 0; it0 < nk; it0 += p.chunk) {
-        mbar_wait(smem_u32(cfull + slot), slot_phase, aborted);
+        mbar_wait<20>(smem_u32(cfull + slot), slot_phase, aborted); if (aborted) goto teardown;
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(slot * Cfg::SLOT_COLS + cbase);
 #pragma unroll
@@ -1226,8 +1253,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (omax > 65504.f) report_overflow();   // a value left the fp16 range of the operand planes: reported, never silent
   }
 
-  if (aborted) {             // error path only: let bulk copies that were issued without back-pressure land before the CTA's
-    const long long t0 = clock64();          // shared memory is handed to another CTA
+teardown:
+  if (aborted) {             // error path only: let the bulk copies / MMAs that are still in flight finish before the CTA's
+    const long long t0 = clock64();          // shared and tensor memory are handed back
     while (clock64() - t0 < 400000) {}
   }
   tc_fence_before();

@@ -125,10 +125,13 @@ int gn_cat_partials(const float* a_part, const float* b_part, float* out_part, i
 int affine_act(const float* x, const float* scale, const float* shift, float* y, int N, int HW, int C, int act,
                cudaStream_t st);
 
+// out (fp32) and/or out_planes (fp16 hi | lo operand planes of the same [B*S, o_pitch] matrix) receive the result
 int attention(const float* q, const float* k, const float* v, float* out, int B, int S, int heads, int d, int q_pitch,
-              int k_pitch, int v_pitch, int o_pitch, float scale, cudaStream_t st);
+              int k_pitch, int v_pitch, int o_pitch, float scale, cudaStream_t st, void* out_planes = nullptr);
 int layer_norm(const float* x, const float* gamma, const float* beta, float* y, float* y2, const float* pos,
                int pos_rows, int rows, int C, cudaStream_t st);
+int layer_norm_planes(const float* x, const float* gamma, const float* beta, void* y_planes, void* y2_planes, const float* pos,
+                      int pos_rows, int rows, int C, cudaStream_t st);
 int add_pos(const float* x, const float* pos, float* y, int rows, int pos_rows, int C, cudaStream_t st);
 // logits [T,K] -> idx [T] (first max), quant [T,D] = E[idx]
 int argmax_gather(const float* logits, const float* codebook, int64_t* idx, float* quant, int T, int K, int D,

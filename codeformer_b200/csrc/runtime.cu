@@ -537,6 +537,7 @@ struct Fwd {
     float* out_ptr = nullptr;   // write into caller memory instead of the arena
     bool want_stats = false;    // consumer is a GroupNorm: let the tensor-core epilogue emit the partial sums
     bool want_planes = false;   // a following conv reads this output raw: emit its fp16 hi/lo operand planes too
+    bool planes_only = false;   // ... and nothing reads the fp32 tensor: skip its store (tensor engine only)
   };
 
   int conv(const ConvW& w, const Tensor& in, Tensor& out, const ConvOpt& o) {
@@ -550,8 +551,12 @@ struct Fwd {
     a.in_scale = o.in_scale; a.in_shift = o.in_shift; a.in_act = o.in_act; a.residual = o.residual;
     a.out_act = o.out_act; a.sft_dec = o.sft_dec; a.sft_scale = o.sft_scale; a.sft_w = o.sft_w;
     bool use_tc = engine == 2 || (engine == 0 && n->tc_ok && tc_supported(a));
+    const bool no_f32 = o.planes_only && o.want_planes && use_tc && !o.out_ptr;
     if (o.out_ptr) {
       out.p = o.out_ptr; out.N = in.N; out.H = Ho; out.W = Wo; out.C = w.cout; out.owned = false;
+      out.gn_part = nullptr; out.gn_slots = 0; out.planes = nullptr; out.p2 = nullptr; out.C1 = 0;
+    } else if (no_f32) {
+      out.p = nullptr; out.N = in.N; out.H = Ho; out.W = Wo; out.C = w.cout; out.owned = true;
       out.gn_part = nullptr; out.gn_slots = 0; out.planes = nullptr; out.p2 = nullptr; out.C1 = 0;
     } else {
       CFB_CHECK(alloc(out, in.N, Ho, Wo, w.cout));
@@ -575,8 +580,9 @@ struct Fwd {
       //       halves of a channel concatenation -- and transform + split it inside the conv kernel (tc_can_xform);
       //  raw  the producer already emitted this tensor's fp16 hi/lo planes and the consumer takes it untransformed;
       //  prep everything else: a separate operand-preparation pass over the fp32 tensor.
-      const bool xf = in.p && o.in_scale && o.in_shift && tc_can_xform(a);
-      const bool raw = !xf && in.planes && !o.in_scale && o.in_act == IN_NONE;
+      const bool plain = !o.in_scale && !o.in_shift && o.in_act == IN_NONE;
+      const bool xf = in.p && tc_can_xform(a) && ((o.in_scale && o.in_shift) || (plain && !in.planes));   // plain: in-kernel split only
+      const bool raw = !xf && in.planes && plain;
       const bool reuse = raw || xf;
       void* scratch = raw ? in.planes : nullptr;
       if (!reuse) CFB_CHECK(alloc_raw(&scratch, tc_scratch_bytes(a)));
@@ -864,24 +870,45 @@ struct Fwd {
     Tensor tok = lq; tok.owned = false;   // [B,16,16,256] == tokens [T,256]
     Tensor x;
     { ConvOpt o; CFB_CHECK(conv(n->feat_emb, tok, x, o)); }
+    // On the tensor engine every LayerNorm / attention / GELU output of a layer is only ever a GEMM operand: the producing
+    // kernel writes it straight as fp16 hi/lo operand planes (no fp32 copy, no operand-preparation pass).
+    const bool tcp = engine != 1 && n->tc_ok;
+    const size_t plE = 2 * (((size_t)T * E * 2 + 1023) / 1024 * 1024);
+    auto planes_tensor = [&](Tensor& t, int C, size_t bytes) -> int {
+      t.p = nullptr; t.N = B; t.H = lq.H; t.W = lq.W; t.C = C; t.owned = true; t.gn_part = nullptr; t.gn_slots = 0;
+      t.p2 = nullptr; t.C1 = 0; t.planes = nullptr;
+      return alloc_raw(&t.planes, bytes);
+    };
     for (const LayerW& L : n->layers) {
       Tensor t2, qkin, qk, v, a, x2, hdn, x3;
-      CFB_CHECK(alloc(t2, B, lq.H, lq.W, E));
-      CFB_CHECK(alloc(qkin, B, lq.H, lq.W, E));
-      if (!dry) CFB_CHECK(layer_norm(x.p, L.n1.gamma, L.n1.beta, t2.p, qkin.p, n->position_emb, S, T, E, st));
+      if (tcp) {
+        CFB_CHECK(planes_tensor(t2, E, plE));
+        CFB_CHECK(planes_tensor(qkin, E, plE));
+        if (!dry) CFB_CHECK(layer_norm_planes(x.p, L.n1.gamma, L.n1.beta, t2.planes, qkin.planes, n->position_emb, S, T, E, st));
+      } else {
+        CFB_CHECK(alloc(t2, B, lq.H, lq.W, E));
+        CFB_CHECK(alloc(qkin, B, lq.H, lq.W, E));
+        if (!dry) CFB_CHECK(layer_norm(x.p, L.n1.gamma, L.n1.beta, t2.p, qkin.p, n->position_emb, S, T, E, st));
+      }
       { ConvOpt o; CFB_CHECK(conv(L.qk, qkin, qk, o)); }
       { ConvOpt o; CFB_CHECK(conv(L.v, t2, v, o)); }
       release(qkin); release(t2);
-      CFB_CHECK(alloc(a, B, lq.H, lq.W, E));
+      if (tcp) CFB_CHECK(planes_tensor(a, E, plE));
+      else CFB_CHECK(alloc(a, B, lq.H, lq.W, E));
       if (!dry)
         CFB_CHECK(attention(qk.p, qk.p + E, v.p, a.p, B, S, c.n_head, E / c.n_head, 2 * E, 2 * E, E, E,
-                            sqrtf(1.0f / (float)(E / c.n_head)), st));
+                            sqrtf(1.0f / (float)(E / c.n_head)), st, a.planes));
       release(qk); release(v);
       { ConvOpt o; o.residual = x.p; CFB_CHECK(conv(L.o, a, x2, o)); }
       release(a); release(x);
-      CFB_CHECK(alloc(t2, B, lq.H, lq.W, E));
-      if (!dry) CFB_CHECK(layer_norm(x2.p, L.n2.gamma, L.n2.beta, t2.p, nullptr, nullptr, 0, T, E, st));
-      { ConvOpt o; o.out_act = OUT_GELU; CFB_CHECK(conv(L.l1, t2, hdn, o)); }
+      if (tcp) {
+        CFB_CHECK(planes_tensor(t2, E, plE));
+        if (!dry) CFB_CHECK(layer_norm_planes(x2.p, L.n2.gamma, L.n2.beta, t2.planes, nullptr, nullptr, 0, T, E, st));
+      } else {
+        CFB_CHECK(alloc(t2, B, lq.H, lq.W, E));
+        if (!dry) CFB_CHECK(layer_norm(x2.p, L.n2.gamma, L.n2.beta, t2.p, nullptr, nullptr, 0, T, E, st));
+      }
+      { ConvOpt o; o.out_act = OUT_GELU; o.want_planes = tcp; o.planes_only = tcp; CFB_CHECK(conv(L.l1, t2, hdn, o)); }
       release(t2);
       { ConvOpt o; o.residual = x2.p; CFB_CHECK(conv(L.l2, hdn, x3, o)); }
       release(hdn); release(x2);
@@ -889,8 +916,13 @@ struct Fwd {
       CFB_CHECK(capture("ft." + std::to_string((int)(&L - &n->layers[0])), x));
     }
     Tensor t2, lg;
-    CFB_CHECK(alloc(t2, B, lq.H, lq.W, E));
-    if (!dry) CFB_CHECK(layer_norm(x.p, n->idx_norm.gamma, n->idx_norm.beta, t2.p, nullptr, nullptr, 0, T, E, st));
+    if (tcp) {
+      CFB_CHECK(planes_tensor(t2, E, plE));
+      if (!dry) CFB_CHECK(layer_norm_planes(x.p, n->idx_norm.gamma, n->idx_norm.beta, t2.planes, nullptr, nullptr, 0, T, E, st));
+    } else {
+      CFB_CHECK(alloc(t2, B, lq.H, lq.W, E));
+      if (!dry) CFB_CHECK(layer_norm(x.p, n->idx_norm.gamma, n->idx_norm.beta, t2.p, nullptr, nullptr, 0, T, E, st));
+    }
     release(x);
     { ConvOpt o; o.out_ptr = logits_out; CFB_CHECK(conv(n->idx_lin, t2, lg, o)); }
     release(t2);

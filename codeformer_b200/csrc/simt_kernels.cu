@@ -13,6 +13,7 @@
 //   AdaIN                                 codeformer_arch.py:12-43                         adain_nhwc
 //   Fuse_sft combine                      codeformer_arch.py:155-156                       conv epilogue (sft_*)
 //   VectorQuantizer.forward               vqgan_arch.py:33-70                              vq_nearest
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -713,6 +714,8 @@ int affine_act(const float* x, const float* scale, const float* shift, float* y,
   return 0;
 }
 
+__device__ __forceinline__ void split_store4(__half* __restrict__ hi, __half* __restrict__ lo, int64_t off, const float4& o);
+
 // =====================================================================================================
 // Attention core: out = softmax(q k^T * scale) v, S = 256 keys, one CTA per (32 queries, head, batch).
 // =====================================================================================================
@@ -722,7 +725,8 @@ constexpr int AT_QB = 32;
 template <int D>
 __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                         const float* __restrict__ v, float* __restrict__ out, int q_pitch,
-                                                        int k_pitch, int v_pitch, int o_pitch, float scale) {
+                                                        int k_pitch, int v_pitch, int o_pitch, float scale,
+                                                        __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
   extern __shared__ __align__(16) float sm[];
   float* Qs = sm;                       // [32 dd][32 q]
   float* Ks = Qs + 32 * AT_QB;          // [32 dd][256 keys]
@@ -824,14 +828,18 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
       }
     }
   }
-  float* ob = out + ((int64_t)b * AT_S + q0) * o_pitch + h * D + c4 * 4;
+  const int64_t obase = ((int64_t)b * AT_S + q0) * o_pitch + h * D + c4 * 4;
 #pragma unroll
-  for (int i = 0; i < QPT; ++i)
-    *reinterpret_cast<float4*>(ob + (int64_t)(qs + i) * o_pitch) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  for (int i = 0; i < QPT; ++i) {
+    const float4 o = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    const int64_t off = obase + (int64_t)(qs + i) * o_pitch;
+    if (out) *reinterpret_cast<float4*>(out + off) = o;
+    if (out_hi) split_store4(out_hi, out_lo, off, o);      // operand planes of the out_proj linear (values are convex
+  }                                                         // combinations of v: inside the fp16 range whenever v is)
 }
 
 int attention(const float* q, const float* k, const float* v, float* out, int B, int S, int heads, int d, int q_pitch,
-              int k_pitch, int v_pitch, int o_pitch, float scale, cudaStream_t st) {
+              int k_pitch, int v_pitch, int o_pitch, float scale, cudaStream_t st, void* out_planes) {
   CFB_REQUIRE(S == AT_S, "attention: token count must be 256 (16x16 latent)");
   CFB_REQUIRE(d == 64 || d == 512, "attention: head width must be 64 or 512");
   if (B == 0) return 0;
@@ -847,10 +855,13 @@ int attention(const float* q, const float* k, const float* v, float* out, int B,
     attr_done.fetch_or(bit, std::memory_order_release);
   }
   dim3 grid(S / AT_QB, heads, B);
+  __half* ohi = (__half*)out_planes;
+  __half* olo = out_planes ? (__half*)((char*)out_planes + (((size_t)B * S * o_pitch * 2 + 1023) / 1024 * 1024)) : nullptr;
+  CFB_REQUIRE(out || out_planes, "attention: no output");
   if (d == 64)
-    attention_kernel<64><<<grid, 256, smem, st>>>(q, k, v, out, q_pitch, k_pitch, v_pitch, o_pitch, scale);
+    attention_kernel<64><<<grid, 256, smem, st>>>(q, k, v, out, q_pitch, k_pitch, v_pitch, o_pitch, scale, ohi, olo);
   else
-    attention_kernel<512><<<grid, 256, smem, st>>>(q, k, v, out, q_pitch, k_pitch, v_pitch, o_pitch, scale);
+    attention_kernel<512><<<grid, 256, smem, st>>>(q, k, v, out, q_pitch, k_pitch, v_pitch, o_pitch, scale, ohi, olo);
   CFB_LAUNCH_CHECK();
   return 0;
 }
@@ -858,11 +869,25 @@ int attention(const float* q, const float* k, const float* v, float* out, int B,
 // =====================================================================================================
 // LayerNorm (eps 1e-5), warp per row; optional second output y2 = y + pos[row % pos_rows]
 // =====================================================================================================
-template <int C>
+__device__ __forceinline__ void split_store4(__half* __restrict__ hi, __half* __restrict__ lo, int64_t off, const float4& o) {
+  const __half2 h01 = __floats2half2_rn(o.x, o.y), h23 = __floats2half2_rn(o.z, o.w);
+  const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+  const __half2 l01 = __floats2half2_rn(o.x - f01.x, o.y - f01.y), l23 = __floats2half2_rn(o.z - f23.x, o.w - f23.y);
+  uint2 ph, pl;
+  ph.x = *reinterpret_cast<const uint32_t*>(&h01); ph.y = *reinterpret_cast<const uint32_t*>(&h23);
+  pl.x = *reinterpret_cast<const uint32_t*>(&l01); pl.y = *reinterpret_cast<const uint32_t*>(&l23);
+  *reinterpret_cast<uint2*>(hi + off) = ph;
+  *reinterpret_cast<uint2*>(lo + off) = pl;
+}
+
+// PLANES: y / y2 are written as fp16 hi/lo operand planes (hi = rn(v), lo = rn(v - hi)) for the tensor-core linears that
+// consume them -- the LayerNorm output of a TransformerSALayer is only ever a GEMM operand (codeformer_arch.py:124-131),
+// so no fp32 copy and no separate operand-preparation pass exist on that path.  |LN output| is O(10): inside the fp16 range.
+template <int C, bool PLANES>
 __global__ void __launch_bounds__(256) layer_norm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, float* __restrict__ y,
                                                          float* __restrict__ y2, const float* __restrict__ pos,
-                                                         int pos_rows, int rows) {
+                                                         int pos_rows, int rows, int64_t plane_elems) {
   constexpr int V = C / 128;  // float4 per lane
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int l = threadIdx.x & 31;
@@ -895,10 +920,17 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const float* __restrict
     float4 o;
     o.x = (v[i].x - mean) * rstd * g.x + bb.x; o.y = (v[i].y - mean) * rstd * g.y + bb.y;
     o.z = (v[i].z - mean) * rstd * g.z + bb.z; o.w = (v[i].w - mean) * rstd * g.w + bb.w;
-    *reinterpret_cast<float4*>(y + (int64_t)row * C + c) = o;
+    const int64_t off = (int64_t)row * C + c;
+    if (PLANES) {
+      if (y) split_store4(reinterpret_cast<__half*>(y), reinterpret_cast<__half*>(y) + plane_elems, off, o);
+    } else {
+      *reinterpret_cast<float4*>(y + off) = o;
+    }
     if (y2) {
       const float4 p = __ldg(reinterpret_cast<const float4*>(pos + (int64_t)(row % pos_rows) * C + c));
-      *reinterpret_cast<float4*>(y2 + (int64_t)row * C + c) = make_float4(o.x + p.x, o.y + p.y, o.z + p.z, o.w + p.w);
+      const float4 o2 = make_float4(o.x + p.x, o.y + p.y, o.z + p.z, o.w + p.w);
+      if (PLANES) split_store4(reinterpret_cast<__half*>(y2), reinterpret_cast<__half*>(y2) + plane_elems, off, o2);
+      else *reinterpret_cast<float4*>(y2 + off) = o2;
     }
   }
 }
@@ -906,7 +938,18 @@ int layer_norm(const float* x, const float* gamma, const float* beta, float* y, 
                int pos_rows, int rows, int C, cudaStream_t st) {
   CFB_REQUIRE(C == 512, "layer_norm: only dim_embd=512 is built");
   if (rows == 0) return 0;
-  layer_norm_kernel<512><<<(rows + 7) / 8, 256, 0, st>>>(x, gamma, beta, y, y2, pos, pos_rows > 0 ? pos_rows : 1, rows);
+  layer_norm_kernel<512, false><<<(rows + 7) / 8, 256, 0, st>>>(x, gamma, beta, y, y2, pos, pos_rows > 0 ? pos_rows : 1, rows, 0);
+  CFB_LAUNCH_CHECK();
+  return 0;
+}
+// outputs as fp16 hi/lo operand planes: [hi plane | lo plane], each align1024(rows*C*2) bytes (the conv engine's layout)
+int layer_norm_planes(const float* x, const float* gamma, const float* beta, void* y_planes, void* y2_planes, const float* pos,
+                      int pos_rows, int rows, int C, cudaStream_t st) {
+  CFB_REQUIRE(C == 512, "layer_norm: only dim_embd=512 is built");
+  if (rows == 0) return 0;
+  const int64_t plane_elems = (int64_t)((((size_t)rows * C * 2 + 1023) / 1024 * 1024) / 2);
+  layer_norm_kernel<512, true><<<(rows + 7) / 8, 256, 0, st>>>(x, gamma, beta, (float*)y_planes, (float*)y2_planes, pos,
+                                                              pos_rows > 0 ? pos_rows : 1, rows, plane_elems);
   CFB_LAUNCH_CHECK();
   return 0;
 }
