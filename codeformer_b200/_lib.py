@@ -60,6 +60,12 @@ SIGNATURES = {
     'cfb_debug_umma_rate': (c_int, [c_int32, c_int32, c_int32, _P, c_int32, _P]),
     'cfb_debug_time_conv': (c_int, [_P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P, c_int64,
                                    _P, _P, _P, c_int32, POINTER(c_float)]),
+    'cfb_rrdb_create': (c_void_p, [c_int32, c_int32, c_int32, c_int32, c_int32, c_int32]),
+    'cfb_rrdb_destroy': (None, [_P]),
+    'cfb_rrdb_set_param': (c_int, [_P, c_char_p, _P, c_int64]),
+    'cfb_rrdb_prepare': (c_int, [_P, _P]),
+    'cfb_rrdb_workspace_bytes': (c_int64, [_P, c_int32, c_int32, c_int32]),
+    'cfb_rrdb_forward': (c_int, [_P, _P, _P, c_int32, c_int32, c_int32, _P, c_int64, _P]),
     'cfb_check_async_status': (c_int, []),
     'cfb_debug_set_wait_limit': (c_int, [c_int64]),
     'cfb_debug_inject_fault': (c_int, [c_int32]),

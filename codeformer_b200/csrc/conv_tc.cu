@@ -570,6 +570,16 @@ struct TcParams {
   int b_batched;          // B operand is a per-image activation plane: third TMA coordinate = image index, not the tap
   int up4;                // Upsample as four 2x2 convs: m-tile = (low-res tile, output parity), 4 taps, weights [16][Cout][Cin]
   int PW, PH;             // halo engine: input patch (BW+k-1) x (BH+k-1) pixels fetched once per 64-channel block
+  // GEN variant (XF only; ParseNet / RRDBNet): true image sizes with ragged tiles, padding mode of the halo patch, output
+  // placement into a wider buffer, a second (scaled) residual, stride-2 by subsampling
+  int Hin, Win;           // true input height / width (tiles are ceil-divided; out-of-image patch pixels follow pad_mode)
+  int pad_mode;           // 0 zero, 1 reflect (ReflectionPad2d), 2 replicate (reflection padding of a nearest-x2 upsampled tensor)
+  int sub;                // 1: keep only the even output positions (3x3 stride-2 pad-1 conv == its stride-1 result subsampled)
+  int out_pitch, out_c0, cout_valid;   // destination: channels per pixel, channel offset, number of real output channels
+  int res_pitch;          // channels per pixel of `residual`
+  const float* residual2; // out = (conv + bias + residual) * post_scale + residual2
+  int res2_pitch;
+  float post_scale;
   int fault;              // test hook (cfb_debug_inject_fault): CTA 0 drops the weight load of its first stage -> barrier time-out
   int xform;              // XF kernel variant requested (in_scale may be null: raw split)
   int a_split;            // XF: k-blocks [0, a_split) are read from fp32 source 0 (tmA_hi), the rest from source 1 (tmA_lo)
@@ -654,12 +664,13 @@ struct TcCfg {
 // 60 %) and each SM stages / reads only half of every B operand.  Rank 0 (leader) issues all MMAs; its `full` and `cempty`
 // barriers collect the TMA bytes / epilogue arrivals of both CTAs; `empty` and `cfull` are signalled in both CTAs by
 // multicast commits.
-template <int BN, int CPG, bool HALO, bool PAIR, bool XF>
+template <int BN, int CPG, bool HALO, bool PAIR, bool XF, bool GEN = false>
 __global__ void __launch_bounds__(XF ? TcCfg<BN>::XF_THREADS : TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                const __grid_constant__ CUtensorMap tmB_half, const TcParams p) {
   static_assert(!XF || (HALO && PAIR), "the fused operand transform exists for the halo + pair engine only");
+  static_assert(!GEN || (XF && CPG == 0), "the generalised addressing exists for the fused-transform engine only");
   using Cfg = TcCfg<BN>;
   constexpr int A_SLOTS = XF ? Cfg::X_A_SLOTS : Cfg::H_A_SLOTS;
   constexpr int STAGES = PAIR ? Cfg::P_STAGES : Cfg::STAGES;
@@ -685,7 +696,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(araw + 3);
   uint8_t* stage_buf = reinterpret_cast<uint8_t*>(bars) + 512;      // epilogue transpose patches (16-byte aligned)
 
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
+  // Roles are numbered logically (0 TMA, 1 MMA, 2..9 epilogue, 10.. transform, then the patch loader) but sit on the warp
+  // ids in REVERSE order: the sub-partition arbiter favours the highest warp id among its eligible warps, and the role that
+  // must never wait for an issue slot is the MMA issuer, then the TMA producer, then the epilogue; the instruction-heavy
+  // transform warps come last.  (TMEM lane quadrants follow the PHYSICAL warp id: lg below.)
+  constexpr int NWARPS = (XF ? TcCfg<BN>::XF_THREADS : TC_THREADS) / 32;
+  const int pwarp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
+  const int warp = NWARPS - 1 - pwarp;
   const int lane = threadIdx.x & 31;
   bool aborted = false;      // set when a barrier wait timed out anywhere on the device: leave the role loop (see mbar_wait)
 
@@ -756,7 +773,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if constexpr (HALO) {
           for (int kb = 0; kb < p.kblocks; ++kb) {
             if constexpr (!XF) {
-            mbar_wait<40>(smem_u32(aempty + aslot), aphase ^ 1, aborted); if (aborted) goto teardown;
+            mbar_wait<500>(smem_u32(aempty + aslot), aphase ^ 1, aborted); if (aborted) goto teardown;
             if (elect_one()) {
               const uint32_t sa = smem_u32(smem + aslot * Cfg::H_A_SLOT);
               if constexpr (PAIR) {
@@ -776,7 +793,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
             for (int tap = 0; tap < p.taps; ++tap) {
               const int btap = p.up4 ? (mt & 3) * 4 + tap : tap;      // Upsample: weight slice of this output parity
-              mbar_wait<40>(smem_u32(empty + stage), phase ^ 1, aborted); if (aborted) goto teardown;
+              mbar_wait<500>(smem_u32(empty + stage), phase ^ 1, aborted); if (aborted) goto teardown;
               if (elect_one()) {
                 const uint32_t sb = smem_u32(ring_base + stage * RING_BYTES);
                 if constexpr (PAIR) {
@@ -803,7 +820,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             if (p.up4) { r = (tap >> 1) + par_y; s = (tap & 1) + par_x; btap = (mt & 3) * 4 + tap; }
             else { r = (p.taps == 9) ? tap / 3 : 0; s = (p.taps == 9) ? tap - r * 3 : 0; }
             for (int kb = 0; kb < p.kblocks; ++kb) {
-              mbar_wait<40>(smem_u32(empty + stage), phase ^ 1, aborted); if (aborted) goto teardown;
+              mbar_wait<500>(smem_u32(empty + stage), phase ^ 1, aborted); if (aborted) goto teardown;
               if (elect_one()) {
                 const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
                 const int b3 = p.b_batched ? n : btap;
@@ -1006,14 +1023,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       int aslot = 0;
       uint32_t aphase = 0;
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
-        const int mt = mtile_of(tile / p.n_tiles);
+        const int mt0 = mtile_of(tile / p.n_tiles);
+        const int mt = p.up4 ? (mt0 >> 2) : mt0;           // Upsample: the four output parities read the same low-res patch
         const int per_img = p.tiles_x * p.tiles_y;
         const int n = mt / per_img;
         const int rem = mt - n * per_img;
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
         const int y0 = ty * p.BH, x0 = tx * p.BW;
         for (int kb = 0; kb < p.kblocks; ++kb) {
-          mbar_wait<40>(smem_u32(aempty + aslot), aphase ^ 1, aborted); if (aborted) goto teardown;       // every MMA that read this slot has completed
+          mbar_wait<500>(smem_u32(aempty + aslot), aphase ^ 1, aborted); if (aborted) goto teardown;       // every MMA that read this slot has completed
           if (elect_one()) {
             const uint32_t sa = smem_u32(smem + aslot * Cfg::H_A_SLOT);
             const uint32_t rb = smem_u32(araw + aslot);
@@ -1045,18 +1063,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       constexpr int RPP = 4 * XFW;                                  // patch rows per pass (8 lanes per row)
       constexpr int XF_PW = 10, XF_PH = 18, XF_ROWS = XF_PW * XF_PH;   // halo patch of an 8 x 16 tile and a 3 x 3 filter
       constexpr int NPASS = (XF_ROWS + RPP - 1) / RPP;
-      const int t = (int)threadIdx.x - 32 * (2 + TC_EPI_WARPS);
+      const int t = (warp - (2 + TC_EPI_WARPS)) * 32 + lane;
       const int j = t & 7, rsub = t >> 3;
       const int pl = j >> 2, c0 = 2 * (j & 3);                      // source plane and first 16-byte chunk of this lane's 8 channels
       const uint32_t afull_leader = map_to_cta(smem_u32(afull), 0u);
       const int mode = p.in_scale ? (p.in_act == IN_SILU ? 2 : 1) : 0;   // 2: affine + SiLU, 1: affine, 0: raw split
-      const int Hin = p.tiles_y * p.BH, Win = p.tiles_x * p.BW;
+      const int Hin = GEN ? p.Hin : p.tiles_y * p.BH, Win = GEN ? p.Win : p.tiles_x * p.BW;
       const int Cin = p.kblocks * 64;
       float amax = 0.f;
       int aslot = 0;
       uint32_t aphase = 0;
       for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
-        const int mt = mtile_of(tile / p.n_tiles);
+        const int mt0 = mtile_of(tile / p.n_tiles);
+        const int mt = p.up4 ? (mt0 >> 2) : mt0;
         const int per_img = p.tiles_x * p.tiles_y;
         const int n = mt / per_img;
         const int rem = mt - n * per_img;
@@ -1066,8 +1085,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         for (int kb = 0; kb < p.kblocks; ++kb) {
           float sc[8], sh[8];
           if (mode) {
-            const float* sp = p.in_scale + (int64_t)n * Cin + kb * 64 + j * 8;
-            const float* hp = p.in_shift + (int64_t)n * Cin + kb * 64 + j * 8;
+            const int nn = GEN ? min(n, p.N - 1) : n;       // GEN: the tile count is padded to an even number (dummy tile)
+            const float* sp = p.in_scale + (int64_t)nn * Cin + kb * 64 + j * 8;
+            const float* hp = p.in_shift + (int64_t)nn * Cin + kb * 64 + j * 8;
             const float4 s0 = __ldg(reinterpret_cast<const float4*>(sp)), s1 = __ldg(reinterpret_cast<const float4*>(sp + 4));
             const float4 h0 = __ldg(reinterpret_cast<const float4*>(hp)), h1 = __ldg(reinterpret_cast<const float4*>(hp + 4));
             sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
@@ -1076,13 +1096,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
             for (int k = 0; k < 8; ++k) { sc[k] = 1.f; sh[k] = 0.f; }
           }
-          mbar_wait<20>(smem_u32(araw + aslot), aphase, aborted); if (aborted) goto teardown;
+          mbar_wait<250>(smem_u32(araw + aslot), aphase, aborted); if (aborted) goto teardown;
           const uint32_t base0 = smem_u32(smem + aslot * Cfg::H_A_SLOT);
           const uint32_t src_base = base0 + (pl ? (uint32_t)Cfg::X_A_PLANE2 : 0u);
           const uint32_t lo_base = base0 + (uint32_t)Cfg::X_A_PLANE2;
           if (mode == 2) xf_patch<2, RPP, NPASS, XF_PW, XF_ROWS>(src_base, base0, lo_base, c0, j, rsub, sc, sh, border, y0, x0, Hin, Win, amax);
           else if (mode == 1) xf_patch<1, RPP, NPASS, XF_PW, XF_ROWS>(src_base, base0, lo_base, c0, j, rsub, sc, sh, border, y0, x0, Hin, Win, amax);
           else xf_patch<0, RPP, NPASS, XF_PW, XF_ROWS>(src_base, base0, lo_base, c0, j, rsub, sc, sh, border, y0, x0, Hin, Win, amax);
+          if constexpr (GEN) {
+            if (p.pad_mode && border) {
+              // ReflectionPad2d / replicate padding: an out-of-image pixel of the patch equals an in-image pixel of the SAME
+              // patch (index -1 -> 1 or 0, index H -> H-2 or H-1), so after every warp has written its rows the outside rows
+              // are copied from their source rows (transformed values: the per-channel affine is position independent)
+              asm volatile("bar.sync 1, %0;" ::"r"(32 * XFW) : "memory");
+#pragma unroll 1
+              for (int r = rsub; r < XF_ROWS; r += RPP) {
+                const int py = r / XF_PW, px = r - py * XF_PW;
+                const int gy = y0 + py, gx = x0 + px;
+                if ((unsigned)gy < (unsigned)Hin && (unsigned)gx < (unsigned)Win) continue;
+                int sy = gy, sx = gx;
+                if (p.pad_mode == 1) {
+                  sy = sy < 0 ? -sy : (sy >= Hin ? 2 * Hin - 2 - sy : sy);
+                  sx = sx < 0 ? -sx : (sx >= Win ? 2 * Win - 2 - sx : sx);
+                }
+                sy = min(max(sy, max(y0, 0)), min(Hin, y0 + XF_PH) - 1);      // inside the image AND inside this patch
+                sx = min(max(sx, max(x0, 0)), min(Win, x0 + XF_PW) - 1);
+                const int rs = (sy - y0) * XF_PW + (sx - x0);
+                const uint32_t hs = base0 + (uint32_t)rs * 128u, hd = base0 + (uint32_t)r * 128u;
+                const uint32_t ls = lo_base + (uint32_t)rs * 128u, ld = lo_base + (uint32_t)r * 128u;
+                const uint4 hv = lds128(hs + ((((uint32_t)j) ^ ((hs >> 7) & 7u)) << 4));
+                const uint4 lv = lds128(ls + ((((uint32_t)j) ^ ((ls >> 7) & 7u)) << 4));
+                sts128(hd + ((((uint32_t)j) ^ ((hd >> 7) & 7u)) << 4), hv);
+                sts128(ld + ((((uint32_t)j) ^ ((ld >> 7) & 7u)) << 4), lv);
+              }
+            }
+          }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(afull_leader + (uint32_t)(aslot * 8));
@@ -1094,8 +1142,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   } else {
     // ============================ epilogue (warps 2..9) ============================
     constexpr int HC = BN / 2;               // columns owned by this thread
-    const int lg = warp & 3;                 // TMEM lane quadrant this warp may access: lanes [32*lg, 32*lg+32)
-    const int half = (warp - 2) >> 2;        // which half of the tile's columns
+    const int lg = pwarp & 3;                // TMEM lane quadrant this warp may access: lanes [32*lg, 32*lg+32) (physical warp id)
+    const int half = (warp - 2) >> 2;        // which half of the tile's columns (logical warps e and e+4 share a quadrant)
     const int row = lg * 32 + lane;          // pixel row of the tile
     const int cbase = half * HC;
     const float wsi = __ldg(p.wscale_inv);
@@ -1118,7 +1166,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const int col0 = nt * BN + cbase;
       const int64_t off0 = pix * p.Cout + col0;
       // pull this thread's residual / SFT row slices towards L2 now: they are consumed only after the whole K loop
-      if (p.residual) {
+      if (!GEN && p.residual) {
 #pragma unroll
         for (int j = 0; j < HC; j += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + off0 + j));
       }
@@ -1133,7 +1181,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
       for (int j = 0; j < HC; ++j) acc[j] = 0.f;
       for (int it0 = 0; it0 < nk; it0 += p.chunk) {
-        mbar_wait<20>(smem_u32(cfull + slot), slot_phase, aborted); if (aborted) goto teardown;
+        mbar_wait<250>(smem_u32(cfull + slot), slot_phase, aborted); if (aborted) goto teardown;
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(slot * Cfg::SLOT_COLS + cbase);
 #pragma unroll
@@ -1160,6 +1208,59 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       // line and every global access (residual / SFT loads, the store) is a fully used line.
       float4* stg = reinterpret_cast<float4*>(stage_buf) + (warp - 2) * 256;     // 32 rows x 8 chunks
       const int cch = lane & 7, rsub = lane >> 3;
+      if constexpr (GEN) {
+        // generalised placement (ParseNet / RRDBNet): ragged tiles (only pixels inside the true image are stored), destination
+        // with its own channel pitch / offset (dense-block buffers), optional even-position subsampling (stride 2), and
+        //   out = act(conv * 2^-k + bias + residual) * post_scale + residual2
+        const int Hs = p.sub ? (p.Ho >> 1) : p.Ho, Ws = p.sub ? (p.Wo >> 1) : p.Wo;
+#pragma unroll
+        for (int q = 0; q < HC; q += 32) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            stg[lane * 8 + (j ^ (lane & 7))] =
+                make_float4(acc[q + 4 * j] * wsi, acc[q + 4 * j + 1] * wsi, acc[q + 4 * j + 2] * wsi, acc[q + 4 * j + 3] * wsi);
+          __syncwarp();
+          const int colq = col0 + q + cch * 4;
+          const bool col_ok = colq < p.cout_valid;
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + colq));
+          int64_t pixs[8];
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int trow = lg * 32 + it * 4 + rsub;
+            const int hh = trow / p.BW, ww = trow - hh * p.BW;
+            int oy2 = ty * p.BH + hh, ox2 = tx * p.BW + ww;
+            if (p.up4) { oy2 = 2 * oy2 + ((mt & 3) >> 1); ox2 = 2 * ox2 + (mt & 1); }
+            bool ok = col_ok && n < p.N && oy2 < p.Ho && ox2 < p.Wo;
+            if (p.sub) { ok = ok && (((oy2 | ox2) & 1) == 0); oy2 >>= 1; ox2 >>= 1; }
+            pixs[it] = ok ? ((int64_t)n * Hs + oy2) * Ws + ox2 : (int64_t)-1;
+          }
+          float4 rres[8];
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+            rres[it] = (p.residual && pixs[it] >= 0) ? __ldg(reinterpret_cast<const float4*>(p.residual + pixs[it] * p.res_pitch + colq))
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + rsub;
+            float4 v = stg[r * 8 + (cch ^ (r & 7))];
+            v.x += bv.x + rres[it].x; v.y += bv.y + rres[it].y; v.z += bv.z + rres[it].z; v.w += bv.w + rres[it].w;
+            if (p.out_act == OUT_LRELU) {
+              v.x = v.x > 0.f ? v.x : 0.2f * v.x; v.y = v.y > 0.f ? v.y : 0.2f * v.y;
+              v.z = v.z > 0.f ? v.z : 0.2f * v.z; v.w = v.w > 0.f ? v.w : 0.2f * v.w;
+            }
+            if (pixs[it] >= 0) {
+              if (p.residual2) {
+                const float4 r2 = __ldg(reinterpret_cast<const float4*>(p.residual2 + pixs[it] * p.res2_pitch + colq));
+                v.x = fmaf(v.x, p.post_scale, r2.x); v.y = fmaf(v.y, p.post_scale, r2.y);
+                v.z = fmaf(v.z, p.post_scale, r2.z); v.w = fmaf(v.w, p.post_scale, r2.w);
+              }
+              *reinterpret_cast<float4*>(p.out + pixs[it] * p.out_pitch + p.out_c0 + colq) = v;
+            }
+          }
+          __syncwarp();
+        }
+      } else {
 #pragma unroll
       for (int q = 0; q < HC; q += 32) {
 #pragma unroll
@@ -1248,6 +1349,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           }
         }
         __syncwarp();
+      }
       }
     }
     if (omax > 65504.f) report_overflow();   // a value left the fp16 range of the operand planes: reported, never silent
@@ -1354,8 +1456,8 @@ struct TcGeom { int BW, BH; bool halo; };
 static TcGeom tc_geometry(const ConvArgs& a) {
   TcGeom g;
   const int Wt = a.mode == CONV_UP ? a.W : a.Wo, Ht = a.mode == CONV_UP ? a.H : a.Ho;   // grid the tiles live on
-  g.halo = halo_enabled() && pair_enabled() && a.ksize == 3 && (a.mode == CONV_SAME || a.mode == CONV_UP) && Wt % 8 == 0 &&
-           Ht % 16 == 0;
+  g.halo = halo_enabled() && pair_enabled() && a.ksize == 3 && (a.mode == CONV_SAME || a.mode == CONV_UP) &&
+           ((Wt % 8 == 0 && Ht % 16 == 0) || a.gen);      // gen: ragged tiles, stores are bounds-checked
   if (g.halo) { g.BW = 8; g.BH = 16; }
   else { g.BW = tile_bw(a.mode == CONV_UP ? a.W : a.Wo); g.BH = 128 / g.BW; }   // Upsample: tiles live on the low-res grid
   return g;
@@ -1373,6 +1475,7 @@ bool tc_supported(const ConvArgs& a) {
   if (a.mode == CONV_DOWN && a.ksize != 3) return false;
   if (a.Wo < 1 || a.Ho < 1) return false;
   const TcGeom g = tc_geometry(a);
+  if (a.gen) return g.halo && a.ksize == 3;
   const int BW = g.BW, BH = g.BH;
   const int Wt = a.mode == CONV_UP ? a.W : a.Wo, Ht = a.mode == CONV_UP ? a.H : a.Ho;   // grid the tiles live on
   if (a.mode == CONV_UP && a.ksize != 3) return false;
@@ -1388,6 +1491,7 @@ bool tc_supported(const ConvArgs& a) {
 // 64-wide layers, so it is used wherever the engine exists.  CFB_TC_XFORM=0 disables it, =3 restores the round-1 rule.
 bool tc_can_xform(const ConvArgs& a) {
   static const int mode = [] { const char* e = getenv("CFB_TC_XFORM"); return e ? atoi(e) : 1; }();
+  if (a.gen) return tc_supported(a);      // generalised variant: tile count is padded to an even number, CONV_UP included
   if (mode == 0 || !tc_supported(a) || a.mode != CONV_SAME || a.ksize != 3) return false;
   if (mode == 3 && !(a.Cout % 128 == 0 && a.Cin >= 128 && (int64_t)a.Ho * a.Wo >= 4096)) return false;
   const TcGeom g = tc_geometry(a);
@@ -1412,7 +1516,7 @@ static bool pair_ok(const TcParams& p) {
 
 struct TcMaps { CUtensorMap a_hi, a_lo, b_hi, b_lo, b_half; };
 
-template <int BN, int CPG, bool HALO, bool PAIR, bool XF = false>
+template <int BN, int CPG, bool HALO, bool PAIR, bool XF = false, bool GEN = false>
 static int launch_tc2(const TcMaps& m, const TcParams& p, int sm_count, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
   constexpr int SMEM = XF ? Cfg::X_SMEM_BYTES
@@ -1426,7 +1530,7 @@ static int launch_tc2(const TcMaps& m, const TcParams& p, int sm_count, cudaStre
   CFB_CUDA(cudaGetDevice(&dev));
   const uint64_t bit = 1ull << (dev & 63);
   if (!(attr_done.load(std::memory_order_acquire) & bit)) {
-    CFB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, CPG, HALO, PAIR, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    CFB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, CPG, HALO, PAIR, XF, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_done.fetch_or(bit, std::memory_order_release);
   }
   if constexpr (PAIR) {
@@ -1441,18 +1545,24 @@ static int launch_tc2(const TcMaps& m, const TcParams& p, int sm_count, cudaStre
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    CFB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, CPG, HALO, PAIR, XF>, m.a_hi, m.a_lo, m.b_hi, m.b_lo, m.b_half, p));
+    CFB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, CPG, HALO, PAIR, XF, GEN>, m.a_hi, m.a_lo, m.b_hi, m.b_lo, m.b_half, p));
     count_launch();
   } else {
     const int total = p.m_tiles * p.n_tiles;
     const int grid = total < sm_count ? total : sm_count;
-    conv_tc_kernel<BN, CPG, HALO, PAIR, XF><<<grid, THREADS, SMEM, st>>>(m.a_hi, m.a_lo, m.b_hi, m.b_lo, m.b_half, p);
+    conv_tc_kernel<BN, CPG, HALO, PAIR, XF, GEN><<<grid, THREADS, SMEM, st>>>(m.a_hi, m.a_lo, m.b_hi, m.b_lo, m.b_half, p);
     CFB_LAUNCH_CHECK();
   }
   return 0;
 }
 template <int BN, int CPG>
-static int launch_tc(const TcMaps& m, const TcParams& p, int sm_count, cudaStream_t st) {
+static int launch_tc(const TcMaps& m, const TcParams& p, int sm_count, cudaStream_t st, bool gen = false) {
+  if constexpr (CPG == 0) {
+    if (gen) {
+      CFB_REQUIRE(p.xform && p.PW == 10 && p.PH == 18 && p.m_tiles % 2 == 0, "conv_tc: generalised variant needs the halo + pair + transform engine");
+      return launch_tc2<BN, 0, true, true, true, true>(m, p, sm_count, st);
+    }
+  }
   if (p.xform) {         // fused operand transform: conv_tc() only asks for it when tc_can_xform() holds
     CFB_REQUIRE(p.PW == 10 && p.PH == 18 && pair_ok(p), "conv_tc: fused operand transform needs the halo + pair engine");
     return launch_tc2<BN, CPG, true, true, true>(m, p, sm_count, st);
@@ -1507,8 +1617,12 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
     // fused operand transform: the A operand is read straight from the fp32 NHWC activation(s); boxes of 32 channels
     // (128 B rows) x the halo patch.  Source 1 is the second half of a channel concatenation (or source 0 again).
     CFB_REQUIRE(a.in != nullptr && geo.halo, "conv_tc: fused operand transform needs the fp32 input and the halo engine");
-    const int C0 = a.in2 ? a.Cin1 : a.Cin, C1 = a.in2 ? a.Cin - a.Cin1 : a.Cin;
-    CFB_REQUIRE(C0 % 64 == 0 && C1 % 64 == 0 && C0 > 0 && C1 > 0, "conv_tc: concatenated sources must be multiples of 64 channels");
+    // gen: `in` points into a wider NHWC buffer of in_pitch channels; the 64-aligned window [0, Cin) is read (channels beyond
+    // the buffer are zero-filled by the TMA unit, channels beyond the real Cin meet zero weights)
+    const int C0 = a.in2 ? a.Cin1 : (a.gen && a.in_pitch ? a.in_pitch : a.Cin), C1 = a.in2 ? a.Cin - a.Cin1 : C0;
+    CFB_REQUIRE(!(a.gen && a.in2), "conv_tc: the generalised variant reads one source");
+    CFB_REQUIRE(a.gen || (C0 % 64 == 0 && C1 % 64 == 0 && C0 > 0 && C1 > 0), "conv_tc: concatenated sources must be multiples of 64 channels");
+    CFB_REQUIRE(C0 % 4 == 0 && C0 > 0, "conv_tc: source channel pitch must be a multiple of 4");
     const uint32_t box[4] = {32, (uint32_t)PW, (uint32_t)PH, 1};
     {
       const uint64_t dims[4] = {(uint64_t)C0, (uint64_t)Wp, (uint64_t)Hp, (uint64_t)a.N};
@@ -1548,8 +1662,24 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
   p.chunk = tc_chunk_kblocks();
   p.PW = PW; p.PH = PH;
   p.BW = BW; p.BH = BH;
-  p.tiles_x = (p.up4 ? a.W : a.Wo) / BW; p.tiles_y = (p.up4 ? a.H : a.Ho) / BH;
-  p.m_tiles = a.N * p.tiles_x * p.tiles_y * (p.up4 ? 4 : 1); p.n_tiles = a.Cout / BN; p.kblocks = a.Cin / 64;
+  p.tiles_x = ((p.up4 ? a.W : a.Wo) + BW - 1) / BW; p.tiles_y = ((p.up4 ? a.H : a.Ho) + BH - 1) / BH;   // exact unless gen (ragged)
+  {
+    int64_t lowres_tiles = (int64_t)a.N * p.tiles_x * p.tiles_y;
+    if (a.gen) lowres_tiles += lowres_tiles & 1;      // CTA pairs: an even tile count (the dummy tile stores nothing)
+    p.m_tiles = (int)(lowres_tiles * (p.up4 ? 4 : 1));
+  }
+  p.n_tiles = a.Cout / BN; p.kblocks = a.Cin / 64;
+  p.Hin = Hp; p.Win = Wp; p.pad_mode = a.pad_mode; p.sub = a.subsample ? 1 : 0;
+  p.out_pitch = a.out_pitch ? a.out_pitch : a.Cout; p.out_c0 = a.out_c0; p.cout_valid = a.cout_valid ? a.cout_valid : a.Cout;
+  p.res_pitch = a.res_pitch ? a.res_pitch : p.out_pitch; p.residual2 = a.residual2;
+  p.res2_pitch = a.res2_pitch ? a.res2_pitch : p.out_pitch; p.post_scale = a.post_scale;
+  if (a.gen) {
+    CFB_REQUIRE(a.xform && !a.gn_part && !a.out_planes && !a.sft_dec, "conv_tc: generalised variant = fused transform, fp32 output only");
+    CFB_REQUIRE(p.out_pitch % 4 == 0 && p.out_c0 % 4 == 0 && p.cout_valid % 4 == 0 && p.res_pitch % 4 == 0 && p.res2_pitch % 4 == 0,
+                "conv_tc: channel pitches / offsets must be multiples of 4");
+    CFB_REQUIRE(!a.subsample || (a.mode == CONV_SAME && a.Ho % 2 == 0 && a.Wo % 2 == 0), "conv_tc: subsampling needs even sizes");
+    CFB_REQUIRE(a.out_act == OUT_NONE || a.out_act == OUT_LRELU, "conv_tc: generalised variant has bias / residual / LeakyReLU epilogues");
+  }
   if (p.taps * p.kblocks <= 12) p.chunk = p.taps * p.kblocks;   // short K (Cin = 64): one partial sum, no 8+1 split
   p.in_scale = nullptr; p.in_shift = nullptr; p.in_act = IN_NONE; p.xform = a.xform ? 1 : 0;
   p.fault = g_inject_fault.exchange(0);
@@ -1569,6 +1699,7 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
   p.pl_lo = a.out_planes ? (__half*)((char*)a.out_planes + (((size_t)a.N * a.Ho * a.Wo * a.Cout * 2 + 1023) / 1024 * 1024)) : nullptr;
   const int cpg = a.gn_part ? a.Cout / 32 : 0;
   CFB_REQUIRE(!a.gn_part || tc_can_emit_stats(a), "conv_tc: GroupNorm partials are not available for this Cout");
+  if (a.gen) return BN == 128 ? launch_tc<128, 0>(mp, p, sm_count, st, true) : launch_tc<64, 0>(mp, p, sm_count, st, true);
   if (BN == 128) {
     switch (cpg) {
       case 0: return launch_tc<128, 0>(mp, p, sm_count, st);
@@ -1625,6 +1756,8 @@ int bmm_tc(const BmmArgs& g, int sm_count, cudaStream_t st) {
   p.BW = 16; p.BH = 8; p.tiles_x = 1; p.tiles_y = 2;
   p.m_tiles = g.N * 2; p.n_tiles = g.Cout / 128; p.kblocks = g.K / 64;
   p.in_scale = nullptr; p.in_shift = nullptr; p.in_act = IN_NONE; p.xform = 0; p.a_split = 0; p.fault = 0;
+  p.Hin = 16; p.Win = 16; p.pad_mode = 0; p.sub = 0; p.out_pitch = g.Cout; p.out_c0 = 0; p.cout_valid = g.Cout; p.res_pitch = g.Cout;
+  p.residual2 = nullptr; p.res2_pitch = g.Cout; p.post_scale = 1.f;
   p.bias = nullptr; p.residual = nullptr; p.out_act = OUT_NONE; p.sft_dec = nullptr; p.sft_scale = nullptr; p.sft_w = 0.f;
   p.wscale_inv = g.scale_dev; p.out = g.out;
   p.gn_part = nullptr; p.gn_cpg = 0;

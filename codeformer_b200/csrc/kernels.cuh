@@ -90,6 +90,18 @@ struct ConvArgs {
                            // split inside the conv kernel (tc_can_xform); in_scale == null: plain split of the raw values
   const float* in2 = nullptr;   // xform only: channels [Cin1, Cin) come from this second NHWC tensor (torch.cat of Fuse_sft_block)
   int Cin1 = 0;
+  // ---- generalised addressing (xform only; ParseNet / RRDBNet rows f3 / f4): any H x W (ragged tiles), padding mode of the
+  // 3x3 window, source / destination inside wider NHWC buffers (dense blocks), stride 2 by subsampling, second residual
+  bool gen = false;
+  int in_pitch = 0;             // channels per pixel of the buffer `in` points into (0: Cin); Cin is the 64-aligned window read
+  int pad_mode = 0;             // 0 zero, 1 reflect, 2 replicate
+  bool subsample = false;       // keep the even output positions only: out is [N, Ho/2, Wo/2, ...] (Ho, Wo even)
+  int out_pitch = 0, out_c0 = 0;   // destination channels per pixel (0: Cout) and channel offset
+  int cout_valid = 0;           // real output channels (0: Cout); Cout itself is the 64-aligned padded count of the weights
+  int res_pitch = 0;            // channels per pixel of `residual` (0: out_pitch)
+  const float* residual2 = nullptr;   // out = act(conv + bias + residual) * post_scale + residual2
+  int res2_pitch = 0;
+  float post_scale = 1.f;
 };
 
 int conv_f32(const ConvArgs& a, cudaStream_t st);                       // CUDA-core fp32 implicit GEMM
@@ -107,6 +119,15 @@ int conv_last_u8(const float* in, const float* in_scale, const float* in_shift, 
                  unsigned char* out_bgr_hwc, int N, int H, int W, int Cin, cudaStream_t st);
 int u8_to_input(const unsigned char* img_bgr_hwc, float* x_nchw, int N, int64_t HW, cudaStream_t st);
 int output_to_u8(const float* x_nchw, unsigned char* img_bgr_hwc, int N, int64_t HW, cudaStream_t st);
+
+// thin convolutions of the caller-side networks (rows f3 / f4): image channels -> 64 features and 64 features -> image channels
+int conv_thin_in(const float* x_nchw, const float* wgt_tck, const float* bias, float* out, int N, int H, int W, int Cimg, int us,
+                 int pad_mode, int out_pitch, int out_c0, cudaStream_t st);
+int conv_thin_out(const float* in_nhwc64, const float* wgt_tcp, const float* bias, float* out_nchw, int N, int H, int W, int Cout,
+                  int pad_mode, cudaStream_t st);
+int relayout_thin_out(const float* oihw, float* out, int Cout, cudaStream_t st);
+int scale_scalar(float* p, float f, cudaStream_t st);
+int scale_vec(float* p, int n, float f, cudaStream_t st);
 
 // weight re-layout: OIHW -> [taps][Cin][Cout]
 int relayout_oihw_to_tck(const float* oihw, float* out, int Cout, int Cin, int k, cudaStream_t st);

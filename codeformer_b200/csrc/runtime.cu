@@ -1042,6 +1042,220 @@ static int vqae_forward_impl(cfb_net* n, const float* x, float* out, int64_t* id
 }  // namespace cfb
 
 // =========================================================================================================
+// RRDBNet: the background / face upsampler behind RealESRGANer.enhance
+//   /root/reference/basicsr/archs/rrdbnet_arch.py:9-120, call sites /root/reference/basicsr/utils/realesrgan_utils.py:100-175
+// 23 RRDBs of three ResidualDenseBlocks: every 3x3 conv runs on the tcgen05 engine in its generalised fused-transform form
+// (fp32 activation read in place, fp16 hi/lo split inside the kernel, any H x W, zero padding by TMA out-of-bounds fill).
+// The dense concatenations torch.cat((x, x1, ..)) never exist: one NHWC buffer of 192 channels per block holds
+// [x | x1 | x2 | x3 | x4]; conv_k reads its 64-aligned channel window (weights are zero beyond the real Cin) and writes its
+// 32 growth channels at their offset; conv5 writes `x5*0.2 + x` (0.2 folded into the weight scale and bias) into the next
+// block's buffer, and the third block of an RRDB also applies `*0.2 + x_rrdb` in the same epilogue.
+// =========================================================================================================
+namespace cfb {
+struct GenConv {
+  std::string name;
+  int cin = 0, cout = 0;            // real sizes
+  int cin_p = 0, cout_p = 0;        // 64-aligned sizes of the split weights
+  float out_scale = 1.f;            // constant folded into 2^-k and the bias
+  bool up = false;                  // nearest x2 + conv (four parity convs)
+  __half* w_hi = nullptr; __half* w_lo = nullptr; float* bias = nullptr; float* wscale = nullptr;
+};
+}  // namespace cfb
+
+struct cfb_rrdb {
+  int in_ch = 3, out_ch = 3, scale = 4, feat = 64, blocks = 23, grow = 32;
+  std::mutex mu;
+  std::unordered_map<std::string, std::pair<const float*, int64_t>> raw;
+  std::vector<cfb::GenConv> convs;      // [blocks*15] dense convs, then conv_body, conv_up1, conv_up2, conv_hr
+  float* first_w = nullptr; float* first_b = nullptr;   // conv_first  [tap][cin][64]
+  float* last_w = nullptr; float* last_b = nullptr;     // conv_last   [tap][64][4]
+  float* slab = nullptr; size_t slab_bytes = 0;
+  int device = -1, sm_count = 148;
+  bool prepared = false;
+};
+
+namespace cfb {
+
+static const float* rrdb_param(cfb_rrdb* n, const std::string& name, int64_t numel) {
+  auto it = n->raw.find(name);
+  if (it == n->raw.end()) { set_error("missing parameter '" + name + "'"); return nullptr; }
+  if (it->second.second != numel) {
+    set_error("parameter '" + name + "' has " + std::to_string(it->second.second) + " elements, expected " + std::to_string(numel));
+    return nullptr;
+  }
+  return it->second.first;
+}
+
+// zero-padded OIHW copy [cout_p][cin_p][3][3] of a [cout][cin][3][3] weight, then the fp16 hi/lo split of the engine
+static int gen_conv_prepare(GenConv& c, const float* w, const float* b, float* pad_scratch, cudaStream_t st) {
+  const size_t padn = (size_t)c.cout_p * c.cin_p * 9;
+  CFB_CUDA(cudaMemsetAsync(pad_scratch, 0, padn * 4, st));
+  CFB_CUDA(cudaMemcpy2DAsync(pad_scratch, (size_t)c.cin_p * 9 * 4, w, (size_t)c.cin * 9 * 4, (size_t)c.cin * 9 * 4, c.cout,
+                             cudaMemcpyDeviceToDevice, st));
+  if (c.up) CFB_CHECK(tc_split_weights_up4(pad_scratch, c.w_hi, c.w_lo, c.cout_p, c.cin_p, c.wscale, st));
+  else CFB_CHECK(tc_split_weights(pad_scratch, c.w_hi, c.w_lo, c.cout_p, c.cin_p, 3, c.wscale, st));
+  CFB_CUDA(cudaMemsetAsync(c.bias, 0, (size_t)c.cout_p * 4, st));
+  if (b) CFB_CUDA(cudaMemcpyAsync(c.bias, b, (size_t)c.cout * 4, cudaMemcpyDeviceToDevice, st));
+  if (c.out_scale != 1.f) {
+    CFB_CHECK(scale_scalar(c.wscale + 1, c.out_scale, st));
+    CFB_CHECK(scale_vec(c.bias, c.cout, c.out_scale, st));
+  }
+  return 0;
+}
+
+static int rrdb_prepare(cfb_rrdb* n, cudaStream_t st) {
+  int dev = 0, major = 0, sms = 148;
+  CFB_CUDA(cudaGetDevice(&dev));
+  CFB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  CFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  CFB_REQUIRE(major == 10, "RRDBNet: the tcgen05 engine needs an sm_100 device (there is no other path)");
+  CFB_CHECK(async_status_init(st));
+  n->convs.clear();
+  const int us = n->scale == 2 ? 2 : (n->scale == 1 ? 4 : 1);
+  const int cin_first = n->in_ch * us * us;
+  for (int b = 0; b < n->blocks; ++b)
+    for (int r = 1; r <= 3; ++r)
+      for (int k = 1; k <= 5; ++k) {
+        GenConv c;
+        c.name = "body." + std::to_string(b) + ".rdb" + std::to_string(r) + ".conv" + std::to_string(k);
+        c.cin = n->feat + (k - 1) * n->grow; c.cout = k == 5 ? n->feat : n->grow;
+        c.out_scale = k == 5 ? 0.2f : 1.f;
+        n->convs.push_back(c);
+      }
+  for (const char* nm : {"conv_body", "conv_up1", "conv_up2", "conv_hr"}) {
+    GenConv c; c.name = nm; c.cin = n->feat; c.cout = n->feat; c.up = (c.name == "conv_up1" || c.name == "conv_up2");
+    n->convs.push_back(c);
+  }
+  size_t total = 0, padmax = 0;
+  for (GenConv& c : n->convs) {
+    c.cin_p = (c.cin + 63) / 64 * 64; c.cout_p = (c.cout + 63) / 64 * 64;
+    const size_t wn = (size_t)c.cout_p * c.cin_p * (c.up ? 16 : 9);
+    total += 2 * align256(wn * 2) + align256((size_t)c.cout_p * 4) + 256;
+    padmax = std::max(padmax, (size_t)c.cout_p * c.cin_p * 9 * 4);
+  }
+  total += align256(padmax) + align256((size_t)9 * cin_first * 64 * 4) + 256 + align256((size_t)9 * 64 * 4 * 4) + 256;
+  if (n->slab && (n->device != dev || n->slab_bytes < total)) {
+    if (n->device != dev && n->device >= 0) { cudaSetDevice(n->device); cudaFree(n->slab); cudaSetDevice(dev); }
+    else cudaFree(n->slab);
+    n->slab = nullptr; n->slab_bytes = 0;
+  }
+  if (!n->slab) { CFB_CUDA(cudaMalloc((void**)&n->slab, total)); n->slab_bytes = total; }
+  n->device = dev; n->sm_count = sms;
+  char* p = (char*)n->slab;
+  auto take = [&](size_t bytes) { char* r = p; p += align256(bytes); return r; };
+  float* pad_scratch = (float*)take(padmax);
+  for (GenConv& c : n->convs) {
+    const size_t wn = (size_t)c.cout_p * c.cin_p * (c.up ? 16 : 9);
+    c.w_hi = (__half*)take(wn * 2); c.w_lo = (__half*)take(wn * 2);
+    c.bias = (float*)take((size_t)c.cout_p * 4); c.wscale = (float*)take(8);
+    const float* w = rrdb_param(n, c.name + ".weight", (int64_t)c.cout * c.cin * 9);
+    const float* b = rrdb_param(n, c.name + ".bias", c.cout);
+    if (!w || !b) return 1;
+    CFB_CHECK(gen_conv_prepare(c, w, b, pad_scratch, st));
+  }
+  {
+    const float* w = rrdb_param(n, "conv_first.weight", (int64_t)n->feat * cin_first * 9);
+    const float* b = rrdb_param(n, "conv_first.bias", n->feat);
+    if (!w || !b) return 1;
+    n->first_w = (float*)take((size_t)9 * cin_first * 64 * 4); n->first_b = (float*)take(256);
+    CFB_CHECK(relayout_oihw_to_tck(w, n->first_w, n->feat, cin_first, 3, st));
+    CFB_CUDA(cudaMemcpyAsync(n->first_b, b, (size_t)n->feat * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  {
+    const float* w = rrdb_param(n, "conv_last.weight", (int64_t)n->out_ch * n->feat * 9);
+    const float* b = rrdb_param(n, "conv_last.bias", n->out_ch);
+    if (!w || !b) return 1;
+    n->last_w = (float*)take((size_t)9 * 64 * 4 * 4); n->last_b = (float*)take(256);
+    CFB_CHECK(relayout_thin_out(w, n->last_w, n->out_ch, st));
+    CFB_CUDA(cudaMemcpyAsync(n->last_b, b, (size_t)n->out_ch * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  CFB_CUDA(cudaStreamSynchronize(st));
+  n->prepared = true;
+  return 0;
+}
+
+struct GenLaunch {          // one generalised conv: src window -> destination slice
+  const GenConv* c; const float* in; int in_pitch; int H, W; int N;
+  float* out; int out_pitch, out_c0; int act;
+  const float* res = nullptr; int res_pitch = 0; const float* res2 = nullptr; int res2_pitch = 0; float post = 1.f;
+  int pad_mode = 0; bool sub = false;
+};
+static int gen_conv(const GenLaunch& g, int sm_count, cudaStream_t st) {
+  ConvArgs a;
+  a.in = g.in; a.N = g.N; a.H = g.H; a.W = g.W; a.Cin = g.c->cin_p;
+  a.Ho = g.c->up ? 2 * g.H : g.H; a.Wo = g.c->up ? 2 * g.W : g.W; a.Cout = g.c->cout_p; a.ksize = 3;
+  a.mode = g.c->up ? CONV_UP : CONV_SAME;
+  a.wgt_hi = g.c->w_hi; a.wgt_lo = g.c->w_lo; a.wscale_inv = g.c->wscale + 1; a.bias = g.c->bias;
+  a.residual = g.res; a.out_act = g.act; a.out = g.out;
+  a.skip_prep = true; a.xform = true; a.gen = true;
+  a.in_pitch = g.in_pitch; a.pad_mode = g.pad_mode; a.subsample = g.sub;
+  a.out_pitch = g.out_pitch; a.out_c0 = g.out_c0; a.cout_valid = g.c->cout;
+  a.res_pitch = g.res_pitch; a.residual2 = g.res2; a.res2_pitch = g.res2_pitch; a.post_scale = g.post;
+  return conv_tc(a, nullptr, sm_count, st);
+}
+
+static size_t rrdb_ws_bytes(const cfb_rrdb* n, int N, int H, int W) {
+  const int us = n->scale == 2 ? 2 : (n->scale == 1 ? 4 : 1);
+  const size_t px = (size_t)N * (H / us) * (W / us);
+  // F (64) + three dense buffers (192) + body (64) at low resolution; up1 (64 @2x); up2 + hr (64 @4x)
+  return (px * (64 + 3 * 192 + 64) + px * 4 * 64 + px * 16 * 64 * 2) * sizeof(float) + 8 * 1024;
+}
+
+static int rrdb_forward(cfb_rrdb* n, const float* x, float* out, int N, int H, int W, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  CFB_REQUIRE(n->prepared, "cfb_rrdb_prepare has not been called");
+  int dev = -1;
+  CFB_CUDA(cudaGetDevice(&dev));
+  CFB_REQUIRE(dev == n->device, "RRDBNet was prepared on another CUDA device");
+  CFB_CHECK(async_status_check("cfb_rrdb_forward"));
+  const int us = n->scale == 2 ? 2 : (n->scale == 1 ? 4 : 1);
+  CFB_REQUIRE(H % us == 0 && W % us == 0, "RRDBNet: H and W must be multiples of the pixel-unshuffle factor (arch_util.py:202)");
+  if (N == 0 || H == 0 || W == 0) return 0;
+  CFB_REQUIRE((size_t)ws_bytes >= rrdb_ws_bytes(n, N, H, W), "workspace too small (cfb_rrdb_workspace_bytes)");
+  const int h = H / us, w = W / us;
+  const size_t px = (size_t)N * h * w;
+  float* p = (float*)(((uintptr_t)ws + 1023) / 1024 * 1024);
+  float* F = p; p += px * 64;
+  float* D[3]; for (int i = 0; i < 3; ++i) { D[i] = p; p += px * 192; }
+  float* Bd = p; p += px * 64;
+  float* U1 = p; p += px * 4 * 64;
+  float* U2 = p; p += px * 16 * 64;
+  float* HR = p; p += px * 16 * 64;
+  // dense buffers start at zero: every channel a conv window can touch is finite from the first launch on
+  CFB_CUDA(cudaMemsetAsync(D[0], 0, px * 192 * 3 * sizeof(float), st));
+  CFB_CHECK(conv_thin_in(x, n->first_w, n->first_b, F, N, h, w, n->in_ch, us, 0, 64, 0, st));
+  CFB_CHECK(conv_thin_in(x, n->first_w, n->first_b, D[0], N, h, w, n->in_ch, us, 0, 192, 0, st));
+  int X = 0, Y = 1;            // x of the current RRDB lives in D[X]; D[2] is the middle buffer
+  const int Z = 2;
+  for (int b = 0; b < n->blocks; ++b) {
+    const int src[3] = {X, Y, Z}, dst[3] = {Y, Z, Y};
+    for (int r = 0; r < 3; ++r) {
+      float* S = D[src[r]];
+      for (int k = 0; k < 5; ++k) {
+        const GenConv& c = n->convs[(b * 3 + r) * 5 + k];
+        GenLaunch g{&c, S, 192, h, w, N, nullptr, 192, 0, OUT_NONE};
+        if (k < 4) { g.out = S; g.out_c0 = 64 + 32 * k; g.act = OUT_LRELU; }           // x_{k+1} = lrelu(conv_k(cat(x, x1..xk)))
+        else {
+          g.out = D[dst[r]]; g.out_c0 = 0; g.res = S; g.res_pitch = 192;               // x5 * 0.2 + x   (rrdbnet_arch.py:40)
+          if (r == 2) { g.res2 = D[X]; g.res2_pitch = 192; g.post = 0.2f; }            // out * 0.2 + x  (rrdbnet_arch.py:63)
+        }
+        CFB_CHECK(gen_conv(g, n->sm_count, st));
+      }
+    }
+    std::swap(X, Y);
+  }
+  const size_t nb = (size_t)n->blocks * 15;
+  { GenLaunch g{&n->convs[nb + 0], D[X], 192, h, w, N, Bd, 64, 0, OUT_NONE}; g.res = F; g.res_pitch = 64;   // feat + conv_body(body(feat))
+    CFB_CHECK(gen_conv(g, n->sm_count, st)); }
+  { GenLaunch g{&n->convs[nb + 1], Bd, 64, h, w, N, U1, 64, 0, OUT_LRELU}; CFB_CHECK(gen_conv(g, n->sm_count, st)); }
+  { GenLaunch g{&n->convs[nb + 2], U1, 64, 2 * h, 2 * w, N, U2, 64, 0, OUT_LRELU}; CFB_CHECK(gen_conv(g, n->sm_count, st)); }
+  { GenLaunch g{&n->convs[nb + 3], U2, 64, 4 * h, 4 * w, N, HR, 64, 0, OUT_LRELU}; CFB_CHECK(gen_conv(g, n->sm_count, st)); }
+  CFB_CHECK(conv_thin_out(HR, n->last_w, n->last_b, out, N, 4 * h, 4 * w, n->out_ch, 0, st));
+  return 0;
+}
+
+}  // namespace cfb
+
+// =========================================================================================================
 // C ABI
 // =========================================================================================================
 #define API_BEGIN try {
@@ -1098,6 +1312,58 @@ void cfb_net_destroy(cfb_net* n) {
     if (sw) cudaSetDevice(cur);
   }
   delete n;
+}
+
+cfb_rrdb* cfb_rrdb_create(int32_t num_in_ch, int32_t num_out_ch, int32_t scale, int32_t num_feat, int32_t num_block, int32_t num_grow_ch) {
+  API_BEGIN
+  if (num_feat != 64 || num_grow_ch != 32 || num_in_ch < 1 || num_in_ch > 3 || num_out_ch < 1 || num_out_ch > 4 || num_block < 1 ||
+      !(scale == 1 || scale == 2 || scale == 4)) {
+    cfb::set_error("cfb_rrdb_create: built for num_feat=64, num_grow_ch=32, <=3 image channels, scale 1/2/4");
+    return nullptr;
+  }
+  cfb_rrdb* n = new cfb_rrdb();
+  n->in_ch = num_in_ch; n->out_ch = num_out_ch; n->scale = scale; n->feat = num_feat; n->blocks = num_block; n->grow = num_grow_ch;
+  return n;
+  API_END(nullptr)
+}
+void cfb_rrdb_destroy(cfb_rrdb* n) {
+  if (!n) return;
+  if (n->slab) {
+    int cur = -1;
+    const bool sw = cudaGetDevice(&cur) == cudaSuccess && n->device >= 0 && cur != n->device;
+    if (sw) cudaSetDevice(n->device);
+    cudaFree(n->slab);
+    if (sw) cudaSetDevice(cur);
+  }
+  delete n;
+}
+int cfb_rrdb_set_param(cfb_rrdb* n, const char* name, const float* dev_ptr, int64_t numel) {
+  API_BEGIN
+  CFB_REQUIRE(n && name && dev_ptr, "cfb_rrdb_set_param: NULL argument");
+  std::lock_guard<std::mutex> lk(n->mu);
+  n->raw[name] = {dev_ptr, numel};
+  n->prepared = false;
+  return 0;
+  API_END(1)
+}
+int cfb_rrdb_prepare(cfb_rrdb* n, void* stream) {
+  API_BEGIN
+  CFB_REQUIRE(n, "cfb_rrdb_prepare: NULL net");
+  std::lock_guard<std::mutex> lk(n->mu);
+  return cfb::rrdb_prepare(n, (cudaStream_t)stream);
+  API_END(1)
+}
+int64_t cfb_rrdb_workspace_bytes(cfb_rrdb* n, int32_t batch, int32_t h, int32_t w) {
+  if (!n || batch < 0 || h < 0 || w < 0) return -1;
+  return (int64_t)cfb::rrdb_ws_bytes(n, batch, h, w);
+}
+int cfb_rrdb_forward(cfb_rrdb* n, const float* x, float* out, int32_t batch, int32_t h, int32_t w, void* workspace,
+                     int64_t workspace_bytes, void* stream) {
+  API_BEGIN
+  CFB_REQUIRE(n && (batch == 0 || (x && out && workspace)), "cfb_rrdb_forward: NULL argument");
+  std::lock_guard<std::mutex> lk(n->mu);
+  return cfb::rrdb_forward(n, x, out, batch, h, w, workspace, workspace_bytes, (cudaStream_t)stream);
+  API_END(1)
 }
 
 int cfb_check_async_status(void) {

@@ -1421,3 +1421,170 @@ int vq_select_from_dots(const float* z, const float* codebook, const float* dots
 }
 
 }  // namespace cfb
+
+// =====================================================================================================
+// Thin convolutions of the caller-side networks: the first conv of RRDBNet / ParseNet
+// (a few image channels -> 64 features, reads the caller's NCHW image, optional pixel-unshuffle) and their last convs
+// (64 features -> a few channels, writes NCHW).  ~1 % of those networks' FLOPs: plain CUDA-core kernels, any H x W.
+//   /root/reference/basicsr/archs/rrdbnet_arch.py:89,96,101-108,118   /root/reference/basicsr/archs/arch_util.py:190-206
+//   /root/reference/facelib/parsing/parsenet.py:93-105,166,188-189
+// =====================================================================================================
+namespace cfb {
+
+__device__ __forceinline__ int pad_index(int i, int n, int mode, bool& inside) {
+  inside = (unsigned)i < (unsigned)n;
+  if (inside || mode == 0) return i;
+  if (mode == 1) i = i < 0 ? -i : 2 * n - 2 - i;      // ReflectionPad2d
+  i = min(max(i, 0), n - 1);                          // replicate / degenerate sizes
+  inside = true;
+  return i;
+}
+
+// x [N, Cimg, H*us, W*us] NCHW -> out [N, H, W, out_pitch] (channels out_c0 .. out_c0+63), 3x3 pad 1.
+// us > 1: pixel_unshuffle(x, us) first -- channel c*us*us + dy*us + dx of the conv input is x[c][y*us+dy][x*us+dx].
+// weights: [tap][cin][64] (relayout_oihw_to_tck).
+__global__ void __launch_bounds__(256) conv_thin_in_kernel(const float* __restrict__ x, const float* __restrict__ wgt,
+                                                           const float* __restrict__ bias, float* __restrict__ out, int N, int H,
+                                                           int W, int Cimg, int us, int pad_mode, int out_pitch, int out_c0) {
+  extern __shared__ __align__(16) float wsm[];       // [9 * Cin][64]
+  const int Cin = Cimg * us * us;
+  for (int i = threadIdx.x; i < 9 * Cin * 64; i += 256) wsm[i] = wgt[i];
+  __syncthreads();
+  const int cq = threadIdx.x & 15;                   // 4 output channels
+  const int64_t pix = (int64_t)blockIdx.x * 16 + (threadIdx.x >> 4);
+  if (pix >= (int64_t)N * H * W) return;
+  const int n = (int)(pix / ((int64_t)H * W));
+  const int rem = (int)(pix - (int64_t)n * H * W);
+  const int oy = rem / W, ox = rem - oy * W;
+  float4 acc = bias ? __ldg(reinterpret_cast<const float4*>(bias + cq * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const int Hi = H * us, Wi = W * us;
+  for (int r = 0; r < 3; ++r) {
+    bool iny;
+    const int iy = pad_index(oy + r - 1, H, pad_mode, iny);
+    for (int s = 0; s < 3; ++s) {
+      bool inx;
+      const int ix = pad_index(ox + s - 1, W, pad_mode, inx);
+      if (!(iny && inx)) continue;
+      for (int ci = 0; ci < Cin; ++ci) {
+        const int c = ci / (us * us), d = ci - c * us * us, dy = d / us, dx = d - dy * us;
+        const float v = __ldg(x + (((int64_t)n * Cimg + c) * Hi + (iy * us + dy)) * Wi + (ix * us + dx));
+        const float4 w4 = *reinterpret_cast<const float4*>(wsm + ((r * 3 + s) * Cin + ci) * 64 + cq * 4);
+        acc.x = fmaf(v, w4.x, acc.x); acc.y = fmaf(v, w4.y, acc.y); acc.z = fmaf(v, w4.z, acc.z); acc.w = fmaf(v, w4.w, acc.w);
+      }
+    }
+  }
+  *reinterpret_cast<float4*>(out + pix * out_pitch + out_c0 + cq * 4) = acc;
+}
+int conv_thin_in(const float* x_nchw, const float* wgt_tck, const float* bias, float* out, int N, int H, int W, int Cimg, int us,
+                 int pad_mode, int out_pitch, int out_c0, cudaStream_t st) {
+  const int Cin = Cimg * us * us;
+  CFB_REQUIRE(Cin >= 1 && Cin <= 48 && out_pitch % 4 == 0 && out_c0 % 4 == 0, "conv_thin_in: at most 48 input channels");
+  const int64_t M = (int64_t)N * H * W;
+  if (M == 0) return 0;
+  const size_t smem = (size_t)9 * Cin * 64 * sizeof(float);
+  static std::atomic<uint64_t> attr_done{0};
+  int dev = 0;
+  CFB_CUDA(cudaGetDevice(&dev));
+  if (!(attr_done.load() & (1ull << (dev & 63)))) {
+    CFB_CUDA(cudaFuncSetAttribute(conv_thin_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 48 * 64 * 4));
+    attr_done.fetch_or(1ull << (dev & 63));
+  }
+  conv_thin_in_kernel<<<(unsigned)((M + 15) / 16), 256, smem, st>>>(x_nchw, wgt_tck, bias, out, N, H, W, Cimg, us, pad_mode, out_pitch, out_c0);
+  CFB_LAUNCH_CHECK();
+  return 0;
+}
+
+// in [N, H, W, 64] NHWC -> out [N, Cout, H, W] NCHW (Cout <= CP), 3x3 pad 1; weights [tap][64][CP] (zero-padded columns)
+template <int CP>
+__global__ void __launch_bounds__(128) conv_thin_out_kernel(const float* __restrict__ in, const float* __restrict__ wgt,
+                                                            const float* __restrict__ bias, float* __restrict__ out, int N, int H,
+                                                            int W, int Cout, int pad_mode) {
+  extern __shared__ __align__(16) float wsm[];       // [9 * 64][CP]
+  for (int i = threadIdx.x; i < 9 * 64 * CP; i += 128) wsm[i] = wgt[i];
+  __syncthreads();
+  const int64_t pix = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (pix >= (int64_t)N * H * W) return;
+  const int n = (int)(pix / ((int64_t)H * W));
+  const int rem = (int)(pix - (int64_t)n * H * W);
+  const int oy = rem / W, ox = rem - oy * W;
+  float acc[CP];
+#pragma unroll
+  for (int c = 0; c < CP; ++c) acc[c] = (bias && c < Cout) ? __ldg(bias + c) : 0.f;
+  for (int r = 0; r < 3; ++r) {
+    bool iny;
+    const int iy = pad_index(oy + r - 1, H, pad_mode, iny);
+    for (int s = 0; s < 3; ++s) {
+      bool inx;
+      const int ix = pad_index(ox + s - 1, W, pad_mode, inx);
+      if (!(iny && inx)) continue;
+      const float4* src = reinterpret_cast<const float4*>(in + (((int64_t)n * H + iy) * W + ix) * 64);
+      const float* wt = wsm + (r * 3 + s) * 64 * CP;
+#pragma unroll 4
+      for (int c4 = 0; c4 < 16; ++c4) {
+        const float4 v = __ldg(src + c4);
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float* wr = wt + (c4 * 4 + k) * CP;
+#pragma unroll
+          for (int c = 0; c < CP; ++c) acc[c] = fmaf(vv[k], wr[c], acc[c]);
+        }
+      }
+    }
+  }
+  for (int c = 0; c < Cout; ++c) out[(((int64_t)n * Cout + c) * H + oy) * W + ox] = acc[c];
+}
+int conv_thin_out(const float* in_nhwc64, const float* wgt_tcp, const float* bias, float* out_nchw, int N, int H, int W, int Cout,
+                  int pad_mode, cudaStream_t st) {
+  CFB_REQUIRE(Cout >= 1 && Cout <= 20, "conv_thin_out: at most 20 output channels");
+  const int64_t M = (int64_t)N * H * W;
+  if (M == 0) return 0;
+  static std::atomic<uint64_t> attr_done{0};
+  int dev = 0;
+  CFB_CUDA(cudaGetDevice(&dev));
+  if (!(attr_done.load() & (1ull << (dev & 63)))) {
+    CFB_CUDA(cudaFuncSetAttribute(conv_thin_out_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 64 * 20 * 4));
+    attr_done.fetch_or(1ull << (dev & 63));
+  }
+  if (Cout <= 4)
+    conv_thin_out_kernel<4><<<(unsigned)((M + 127) / 128), 128, 9 * 64 * 4 * 4, st>>>(in_nhwc64, wgt_tcp, bias, out_nchw, N, H, W, Cout, pad_mode);
+  else
+    conv_thin_out_kernel<20><<<(unsigned)((M + 127) / 128), 128, 9 * 64 * 20 * 4, st>>>(in_nhwc64, wgt_tcp, bias, out_nchw, N, H, W, Cout, pad_mode);
+  CFB_LAUNCH_CHECK();
+  return 0;
+}
+
+// OIHW [Cout][64][3][3] -> [tap][64][CP] with zero columns beyond Cout
+__global__ void relayout_thin_out_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int CP) {
+  const int total = 9 * 64 * CP;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % CP, ci = (i / CP) % 64, tap = i / (CP * 64);
+    out[i] = c < Cout ? w[((int64_t)c * 64 + ci) * 9 + tap] : 0.f;
+  }
+}
+int relayout_thin_out(const float* oihw, float* out, int Cout, cudaStream_t st) {
+  const int CP = Cout <= 4 ? 4 : 20;
+  relayout_thin_out_kernel<<<64, 256, 0, st>>>(oihw, out, Cout, CP);
+  CFB_LAUNCH_CHECK();
+  return 0;
+}
+
+// y[i] *= f (device scalars of the weight split: folds a constant output scale into 2^-k)
+__global__ void scale_scalar_kernel(float* p, float f) { *p *= f; }
+int scale_scalar(float* p, float f, cudaStream_t st) {
+  scale_scalar_kernel<<<1, 1, 0, st>>>(p, f);
+  CFB_LAUNCH_CHECK();
+  return 0;
+}
+__global__ void scale_vec_kernel(float* __restrict__ p, int n, float f) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] *= f;
+}
+int scale_vec(float* p, int n, float f, cudaStream_t st) {
+  if (n == 0) return 0;
+  scale_vec_kernel<<<(n + 255) / 256, 256, 0, st>>>(p, n, f);
+  CFB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace cfb

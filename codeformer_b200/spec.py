@@ -166,3 +166,18 @@ def random_state_dict(spec: 'OrderedDict[str, tuple]', seed: int = 1) -> 'Ordere
             t = 0.1 * torch.randn(shape, generator=g)
         sd[name] = t.float().contiguous()
     return sd
+
+
+def rrdbnet_spec(num_in_ch=3, num_out_ch=3, scale=4, num_feat=64, num_block=23, num_grow_ch=32) -> 'OrderedDict[str, tuple]':
+    """state_dict keys/shapes of RRDBNet (basicsr/archs/rrdbnet_arch.py:86-101) in registration order."""
+    spec: 'OrderedDict[str, tuple]' = OrderedDict()
+    cin = num_in_ch * (4 if scale == 2 else (16 if scale == 1 else 1))
+    _conv(spec, 'conv_first', cin, num_feat, 3)
+    for b in range(num_block):
+        for r in (1, 2, 3):
+            for k in range(1, 6):
+                _conv(spec, f'body.{b}.rdb{r}.conv{k}', num_feat + (k - 1) * num_grow_ch, num_feat if k == 5 else num_grow_ch, 3)
+    for nm in ('conv_body', 'conv_up1', 'conv_up2', 'conv_hr'):
+        _conv(spec, nm, num_feat, num_feat, 3)
+    _conv(spec, 'conv_last', num_feat, num_out_ch, 3)
+    return spec

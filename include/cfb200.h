@@ -177,6 +177,21 @@ int cfb_debug_umma_rate(int32_t n, int32_t nacc, int32_t reps, int64_t* out_dev,
 int cfb_debug_time_conv(const float* in, const float* weight_oihw, float* out, int32_t n, int32_t h, int32_t w, int32_t cin,
                         int32_t cout, int32_t ksize, int32_t mode, int32_t reps, void* workspace, int64_t workspace_bytes,
                         void* stream, const float* in_scale, const float* in_shift, int32_t in_act, float* ms_per_launch);
+/* ---- RRDBNet: the upsampler behind RealESRGANer.enhance ----
+ * /root/reference/basicsr/archs/rrdbnet_arch.py:67-120 (constructor :86, forward :103-119); the caller's tiling loop
+ * (basicsr/utils/realesrgan_utils.py:100-175) stays in Python (codeformer_b200/upsampler.py).
+ * Parameters are the reference's state-dict names (conv_first, body.{i}.rdb{1,2,3}.conv{1..5}, conv_body, conv_up1, conv_up2,
+ * conv_hr, conv_last; .weight OIHW / .bias).  x: [batch, num_in_ch, h, w] fp32 NCHW, any h, w (multiples of 2 for scale 2, of 4
+ * for scale 1: pixel_unshuffle); out: [batch, num_out_ch, h*scale, w*scale].  Built for num_feat = 64, num_grow_ch = 32. */
+typedef struct cfb_rrdb cfb_rrdb;
+cfb_rrdb* cfb_rrdb_create(int32_t num_in_ch, int32_t num_out_ch, int32_t scale, int32_t num_feat, int32_t num_block, int32_t num_grow_ch);
+void      cfb_rrdb_destroy(cfb_rrdb* net);
+int       cfb_rrdb_set_param(cfb_rrdb* net, const char* name, const float* dev_ptr, int64_t numel);
+int       cfb_rrdb_prepare(cfb_rrdb* net, void* stream);
+int64_t   cfb_rrdb_workspace_bytes(cfb_rrdb* net, int32_t batch, int32_t h, int32_t w);
+int       cfb_rrdb_forward(cfb_rrdb* net, const float* x, float* out, int32_t batch, int32_t h, int32_t w,
+                           void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Asynchronous failures.  Kernels never trap and never leave a sticky CUDA error behind (the reference's callers catch
  * RuntimeError and fall back to the input face, inference_codeformer.py:209-211; web-demos/hugging_face/app.py:176): a
  * barrier time-out of the tensor-core pipeline or an activation outside the fp16 operand range (|x| > 65504) sets a bit

@@ -13,6 +13,8 @@ Files
                             `out` kept at stride 4 to stay small, logits argmax + lq_feat full
   vqae.npz                  face 0, VQAutoEncoder.forward: out (stride 4), indices, loss, perplexity, mean_distance
   vq_micro.npz              VectorQuantizer.forward on the config-3 inputs (seeded), indices + z_q samples + stats
+  rrdbnet.npz               RRDBNet.forward (section 8 f4) of the reference, 23 blocks, scale 2 and scale 4, small seeded images
+                            (`python oracle/gen_golden.py rrdbnet` regenerates only this file)
   plumbing.npz              the caller's image plumbing (section 8 f1): img2tensor(face/255.)+normalize and
                             tensor2img(min_max=(-1,1)).astype(uint8) of the reference on a u8 face that holds every byte
                             value in every channel and on an fp32 tensor that holds every rounding half-way point
@@ -81,7 +83,43 @@ def gen_plumbing():
     np.savez_compressed(os.path.join(OUT, 'plumbing.npz'), face_bgr=face, x=t.numpy(), out=out, restored_bgr=restored)
 
 
+RRDB_CASES = {            # name -> (scale, input shape, weight seed, input seed): the two RealESRGAN models of the reference
+    's2': (2, (1, 3, 44, 36), 21, 31),      # set_realesrgan(): RRDBNet(3, 3, 64, 23, 32, scale=2)   inference_codeformer.py:41-48
+    's4': (4, (2, 3, 20, 28), 22, 32),      # the x4 RealESRGAN model
+}
+
+
+def rrdb_inputs(case):
+    scale, shape, wseed, xseed = RRDB_CASES[case]
+    sd = S.random_state_dict(S.rrdbnet_spec(3, 3, scale, 64, 23, 32), wseed)
+    x = torch.rand(shape, generator=torch.Generator().manual_seed(xseed))          # images in [0, 1] (realesrgan_utils.py:199)
+    return scale, sd, x
+
+
+def load_ref_rrdbnet():
+    """The UNMODIFIED reference class (basicsr/archs/rrdbnet_arch.py) through the import shim."""
+    ref_shim.load()
+    from basicsr.archs.rrdbnet_arch import RRDBNet          # noqa: E402
+    return RRDBNet
+
+
+def gen_rrdbnet():
+    """tests/golden/rrdbnet.npz: outputs of the reference RRDBNet (23 blocks) on small seeded inputs, both scales."""
+    RRDBNet = load_ref_rrdbnet()
+    out = {}
+    torch.set_grad_enabled(False)
+    for case in RRDB_CASES:
+        scale, sd, x = rrdb_inputs(case)
+        net = RRDBNet(3, 3, scale=scale, num_feat=64, num_block=23, num_grow_ch=32).eval()
+        net.load_state_dict(sd, strict=True)
+        out[case + '_out'] = net(x).numpy()
+    np.savez_compressed(os.path.join(OUT, 'rrdbnet.npz'), **out)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == 'rrdbnet':
+        gen_rrdbnet()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == 'plumbing':
         gen_plumbing()
         return
@@ -137,6 +175,7 @@ def main():
                         f'{case}_zq_b0': zq[0].numpy()})
         np.savez_compressed(os.path.join(OUT, 'vq_micro.npz'), **mic)
     gen_plumbing()
+    gen_rrdbnet()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, 'KiB')
 
