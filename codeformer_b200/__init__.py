@@ -8,6 +8,7 @@ Public surface = the reference's plugin API for this path:
 from .registry import ARCH_REGISTRY, install          # noqa: F401
 from .arch import CodeFormer, VQAutoEncoder, VectorQuantizer   # noqa: F401
 from .upsampler import RRDBNet, RealESRGANer                   # noqa: F401
+from .parsing import ParseNet, face_parse_mask, init_parsing_model   # noqa: F401
 
 
 def check_async_status():
@@ -18,4 +19,5 @@ def check_async_status():
     _lib.check(_lib.load().cfb_check_async_status(), 'check_async_status')
 
 
-__all__ = ['ARCH_REGISTRY', 'install', 'CodeFormer', 'VQAutoEncoder', 'VectorQuantizer', 'RRDBNet', 'RealESRGANer', 'check_async_status']
+__all__ = ['ARCH_REGISTRY', 'install', 'CodeFormer', 'VQAutoEncoder', 'VectorQuantizer', 'RRDBNet', 'RealESRGANer', 'ParseNet', 'face_parse_mask', 'init_parsing_model',
+           'check_async_status']

@@ -66,6 +66,16 @@ SIGNATURES = {
     'cfb_rrdb_prepare': (c_int, [_P, _P]),
     'cfb_rrdb_workspace_bytes': (c_int64, [_P, c_int32, c_int32, c_int32]),
     'cfb_rrdb_forward': (c_int, [_P, _P, _P, c_int32, c_int32, c_int32, _P, c_int64, _P]),
+    'cfb_parsenet_create': (c_void_p, [c_int32] * 8),
+    'cfb_parsenet_destroy': (None, [_P]),
+    'cfb_parsenet_set_param': (c_int, [_P, c_char_p, _P, c_int64]),
+    'cfb_parsenet_prepare': (c_int, [_P, _P]),
+    'cfb_parsenet_workspace_bytes': (c_int64, [_P, c_int32, c_int32, c_int32]),
+    'cfb_parsenet_forward': (c_int, [_P, _P, _P, _P, c_int32, c_int32, c_int32, _P, c_int64, _P]),
+    'cfb_parse_argmax': (c_int, [_P, _P, _P, c_int32, c_int32, c_int64, _P]),
+    'cfb_conv2d_gen_workspace_bytes': (c_int64, [c_int32, c_int32]),
+    'cfb_conv2d_gen_nhwc': (c_int, [_P, c_int32, _P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                    c_int32, c_int32, c_int32, _P, c_int32, _P, c_int32, c_float, _P, c_int64, _P]),
     'cfb_check_async_status': (c_int, []),
     'cfb_debug_set_wait_limit': (c_int, [c_int64]),
     'cfb_debug_inject_fault': (c_int, [c_int32]),

@@ -126,6 +126,9 @@ int conv_thin_in(const float* x_nchw, const float* wgt_tck, const float* bias, f
 int conv_thin_out(const float* in_nhwc64, const float* wgt_tcp, const float* bias, float* out_nchw, int N, int H, int W, int Cout,
                   int pad_mode, cudaStream_t st);
 int relayout_thin_out(const float* oihw, float* out, int Cout, cudaStream_t st);
+int fold_bn(const float* w, const float* gamma, const float* beta, const float* mean, const float* var, float eps, float* wout,
+            float* bout, int Cout, int per_out, cudaStream_t st);
+int parse_argmax(const float* logits_nchw, unsigned char* cls, unsigned char* mask, int N, int C, int64_t HW, cudaStream_t st);
 int scale_scalar(float* p, float f, cudaStream_t st);
 int scale_vec(float* p, int n, float f, cudaStream_t st);
 

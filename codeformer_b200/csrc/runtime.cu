@@ -1256,6 +1256,224 @@ static int rrdb_forward(cfb_rrdb* n, const float* x, float* out, int N, int H, i
 }  // namespace cfb
 
 // =========================================================================================================
+// ParseNet: the face-parsing network the paste-back step runs on every restored face
+//   /root/reference/facelib/parsing/parsenet.py:140-194 (constructor :142-186, forward :188-194), caller
+//   /root/reference/facelib/utils/face_restoration_helper.py:457-487.
+// Every ConvLayer = ReflectionPad2d(1) + 3x3 conv (+ eval-mode BatchNorm, folded into the weights at prepare) (+ LeakyReLU 0.2).
+// The 64..256-channel convs run on the generalised fused-transform tcgen05 engine: reflection padding is produced inside the
+// kernel (border pixels of the halo patch are copies of patch pixels), 'down' layers (stride 2) keep the even positions of the
+// stride-1 result, 'up' layers (nearest x2 + reflection pad) are four parity convs on the low-resolution tensor with replicate
+// padding, and the residual sums `identity + res` / `feat + body(feat)` are epilogue residuals.
+// =========================================================================================================
+namespace cfb {
+struct PnBlock { int kind; int cin, cout; GenConv sc, c1, c2; };     // kind: 0 none, 1 down, 2 up
+}
+struct cfb_parsenet {
+  int in_size = 512, out_size = 512, min_feat = 32, base_ch = 64, parsing_ch = 19, res_depth = 10, ch_min = 32, ch_max = 256;
+  std::mutex mu;
+  std::unordered_map<std::string, std::pair<const float*, int64_t>> raw;
+  std::vector<cfb::PnBlock> blocks;       // encoder[1:], body, decoder in order
+  int n_enc = 0, n_body = 0, n_dec = 0, head_ch = 64;
+  float *first_w = nullptr, *first_b = nullptr, *mask_w = nullptr, *mask_b = nullptr, *img_w = nullptr, *img_b = nullptr;
+  float* slab = nullptr; size_t slab_bytes = 0;
+  int device = -1, sm_count = 148;
+  bool prepared = false;
+  cfb::Arena arena;
+};
+namespace cfb {
+
+static const float* pn_param(cfb_parsenet* n, const std::string& name, int64_t numel) {
+  auto it = n->raw.find(name);
+  if (it == n->raw.end()) { set_error("missing parameter '" + name + "'"); return nullptr; }
+  if (it->second.second != numel) {
+    set_error("parameter '" + name + "' has " + std::to_string(it->second.second) + " elements, expected " + std::to_string(numel));
+    return nullptr;
+  }
+  return it->second.first;
+}
+
+static int pn_build(cfb_parsenet* n) {       // ParseNet.__init__  parsenet.py:151-186
+  auto clip = [&](int x) { return std::max(n->ch_min, std::min(x, n->ch_max)); };
+  const int mfs = std::min(n->in_size, n->min_feat);
+  const int down = (int)std::lround(std::floor(std::log2((double)(n->in_size / mfs))));
+  const int up = (int)std::lround(std::floor(std::log2((double)(n->out_size / mfs))));
+  n->blocks.clear();
+  int head = n->base_ch;
+  auto add = [&](const std::string& p, int kind, int cin, int cout) {
+    PnBlock b; b.kind = kind; b.cin = cin; b.cout = cout;
+    b.sc.name = p + ".shortcut_func"; b.c1.name = p + ".conv1"; b.c2.name = p + ".conv2";
+    b.sc.cin = cin; b.sc.cout = cout; b.sc.up = kind == 2;
+    b.c1.cin = cin; b.c1.cout = cout; b.c1.up = kind == 2;
+    b.c2.cin = cout; b.c2.cout = cout;
+    n->blocks.push_back(b);
+  };
+  for (int i = 0; i < down; ++i) { add("encoder." + std::to_string(i + 1), 1, clip(head), clip(head * 2)); head *= 2; }
+  n->n_enc = down;
+  for (int i = 0; i < n->res_depth; ++i) add("body." + std::to_string(i), 0, clip(head), clip(head));
+  n->n_body = n->res_depth;
+  for (int i = 0; i < up; ++i) { add("decoder." + std::to_string(i), 2, clip(head), clip(head / 2)); head /= 2; }
+  n->n_dec = up;
+  n->head_ch = clip(head);
+  CFB_REQUIRE(n->base_ch == 64 && n->head_ch == 64, "ParseNet: built for base_ch = 64 and a 64-channel head (in_size == out_size)");
+  for (const PnBlock& b : n->blocks) {
+    CFB_REQUIRE(b.cin % 64 == 0 && b.cout % 64 == 0, "ParseNet: channel counts must be multiples of 64");
+    CFB_REQUIRE(b.kind != 0 || b.cin == b.cout, "ParseNet: a body block with a channel change (conv shortcut) is not built");
+  }
+  CFB_REQUIRE(n->parsing_ch >= 1 && n->parsing_ch <= 20, "ParseNet: at most 20 parsing classes");
+  return 0;
+}
+
+static int pn_prepare(cfb_parsenet* n, cudaStream_t st) {
+  int dev = 0, major = 0, sms = 148;
+  CFB_CUDA(cudaGetDevice(&dev));
+  CFB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  CFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  CFB_REQUIRE(major == 10, "ParseNet: the tcgen05 engine needs an sm_100 device (there is no other path)");
+  CFB_CHECK(async_status_init(st));
+  CFB_CHECK(pn_build(n));
+  size_t total = 0, padmax = 0;
+  auto acct = [&](GenConv& c) {
+    c.cin_p = c.cin; c.cout_p = c.cout;
+    const size_t wn = (size_t)c.cout_p * c.cin_p * (c.up ? 16 : 9);
+    total += 2 * align256(wn * 2) + align256((size_t)c.cout_p * 4) + 256;
+    padmax = std::max(padmax, (size_t)c.cout_p * c.cin_p * 9 * 4);
+  };
+  for (PnBlock& b : n->blocks) { if (b.kind) acct(b.sc); acct(b.c1); acct(b.c2); }
+  total += 2 * align256(padmax) + align256(1024) + align256((size_t)27 * 64 * 4) + 256 + 2 * (align256((size_t)9 * 64 * 20 * 4) + 256);
+  if (n->slab && (n->device != dev || n->slab_bytes < total)) {
+    if (n->device != dev && n->device >= 0) { cudaSetDevice(n->device); cudaFree(n->slab); cudaSetDevice(dev); }
+    else cudaFree(n->slab);
+    n->slab = nullptr; n->slab_bytes = 0;
+  }
+  if (!n->slab) { CFB_CUDA(cudaMalloc((void**)&n->slab, total)); n->slab_bytes = total; }
+  n->device = dev; n->sm_count = sms;
+  char* p = (char*)n->slab;
+  auto take = [&](size_t bytes) { char* r = p; p += align256(bytes); return r; };
+  float* pad_scratch = (float*)take(padmax);
+  float* fold_w = (float*)take(padmax);
+  float* fold_b = (float*)take(1024);
+  auto prep = [&](GenConv& c, bool bn) -> int {
+    const size_t wn = (size_t)c.cout_p * c.cin_p * (c.up ? 16 : 9);
+    c.w_hi = (__half*)take(wn * 2); c.w_lo = (__half*)take(wn * 2);
+    c.bias = (float*)take((size_t)c.cout_p * 4); c.wscale = (float*)take(8);
+    const float* w = pn_param(n, c.name + ".conv2d.weight", (int64_t)c.cout * c.cin * 9);
+    if (!w) return 1;
+    if (!bn) {
+      const float* b = pn_param(n, c.name + ".conv2d.bias", c.cout);
+      if (!b) return 1;
+      return gen_conv_prepare(c, w, b, pad_scratch, st);
+    }
+    const float* g = pn_param(n, c.name + ".norm.norm.weight", c.cout);
+    const float* be = pn_param(n, c.name + ".norm.norm.bias", c.cout);
+    const float* mu = pn_param(n, c.name + ".norm.norm.running_mean", c.cout);
+    const float* var = pn_param(n, c.name + ".norm.norm.running_var", c.cout);
+    if (!g || !be || !mu || !var) return 1;
+    CFB_REQUIRE(c.cout <= 256, "ParseNet: more than 256 channels");
+    CFB_CHECK(fold_bn(w, g, be, mu, var, 1e-5f, fold_w, fold_b, c.cout, c.cin * 9, st));      // nn.BatchNorm2d default eps
+    return gen_conv_prepare(c, fold_w, fold_b, pad_scratch, st);
+  };
+  for (PnBlock& b : n->blocks) {
+    if (b.kind) CFB_CHECK(prep(b.sc, false));
+    CFB_CHECK(prep(b.c1, true));
+    CFB_CHECK(prep(b.c2, true));
+  }
+  {
+    const float* w = pn_param(n, "encoder.0.conv2d.weight", (int64_t)64 * 3 * 9);
+    const float* b = pn_param(n, "encoder.0.conv2d.bias", 64);
+    if (!w || !b) return 1;
+    n->first_w = (float*)take((size_t)27 * 64 * 4); n->first_b = (float*)take(256);
+    CFB_CHECK(relayout_oihw_to_tck(w, n->first_w, 64, 3, 3, st));
+    CFB_CUDA(cudaMemcpyAsync(n->first_b, b, 64 * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  for (int which = 0; which < 2; ++which) {
+    const std::string nm = which ? "out_img_conv" : "out_mask_conv";
+    const int co = which ? 3 : n->parsing_ch;
+    const float* w = pn_param(n, nm + ".conv2d.weight", (int64_t)co * 64 * 9);
+    const float* b = pn_param(n, nm + ".conv2d.bias", co);
+    if (!w || !b) return 1;
+    float* wd = (float*)take((size_t)9 * 64 * 20 * 4);
+    float* bd = (float*)take(256);
+    CFB_CHECK(relayout_thin_out(w, wd, co, st));
+    CFB_CUDA(cudaMemcpyAsync(bd, b, (size_t)co * 4, cudaMemcpyDeviceToDevice, st));
+    if (which) { n->img_w = wd; n->img_b = bd; } else { n->mask_w = wd; n->mask_b = bd; }
+  }
+  CFB_CUDA(cudaStreamSynchronize(st));
+  n->prepared = true;
+  return 0;
+}
+
+static int pn_forward(cfb_parsenet* n, const float* x, float* out_mask, float* out_img, int N, int H, int W, void* ws, int64_t ws_bytes,
+                      cudaStream_t st, bool dry) {
+  CFB_REQUIRE(dry || n->prepared, "cfb_parsenet_prepare has not been called");
+  if (!dry) {
+    int dev = -1;
+    CFB_CUDA(cudaGetDevice(&dev));
+    CFB_REQUIRE(dev == n->device, "ParseNet was prepared on another CUDA device");
+    CFB_CHECK(async_status_check("cfb_parsenet_forward"));
+  }
+  const int div = 1 << n->n_enc;
+  CFB_REQUIRE(H % div == 0 && W % div == 0 && H >= 2 * div && W >= 2 * div, "ParseNet: H and W must be multiples of 2^down_steps");
+  if (N == 0) return 0;
+  Arena& ar = n->arena;
+  ar.reset(ws, (size_t)ws_bytes, dry);
+  auto alloc = [&](float** p, size_t elems) -> int {
+    *p = (float*)ar.alloc(elems * sizeof(float));
+    CFB_REQUIRE(*p != nullptr, "workspace too small (cfb_parsenet_workspace_bytes)");
+    return 0;
+  };
+  float* t = nullptr;
+  int h = H, w = W, c = 64;
+  CFB_CHECK(alloc(&t, (size_t)N * h * w * 64));
+  if (!dry) CFB_CHECK(conv_thin_in(x, n->first_w, n->first_b, t, N, h, w, 3, 1, 1, 64, 0, st));
+  float* feat = nullptr;           // encoder output, added back after the body (parsenet.py:190)
+  for (size_t i = 0; i < n->blocks.size(); ++i) {
+    const PnBlock& b = n->blocks[i];
+    CFB_REQUIRE(b.cin == c, "ParseNet: channel plan mismatch");
+    const bool last_body = (int)i == n->n_enc + n->n_body - 1 && n->n_body > 0;
+    if ((int)i == n->n_enc) feat = t;
+    float *s = nullptr, *c1 = nullptr, *o = nullptr;
+    int ho = h, wo = w;
+    if (b.kind == 1) { ho = h / 2; wo = w / 2; } else if (b.kind == 2) { ho = 2 * h; wo = 2 * w; }
+    const int h1 = b.kind == 2 ? ho : h, w1 = b.kind == 2 ? wo : w;          // resolution of conv1's output
+    if (b.kind) {
+      CFB_CHECK(alloc(&s, (size_t)N * ho * wo * b.cout));
+      GenLaunch g{&b.sc, t, b.cin, h, w, N, s, b.cout, 0, OUT_NONE};
+      g.pad_mode = b.kind == 2 ? 2 : 1; g.sub = b.kind == 1;
+      if (!dry) CFB_CHECK(gen_conv(g, n->sm_count, st));
+    }
+    CFB_CHECK(alloc(&c1, (size_t)N * h1 * w1 * b.cout));
+    {
+      GenLaunch g{&b.c1, t, b.cin, h, w, N, c1, b.cout, 0, OUT_LRELU};
+      g.pad_mode = b.kind == 2 ? 2 : 1;
+      if (!dry) CFB_CHECK(gen_conv(g, n->sm_count, st));
+    }
+    CFB_CHECK(alloc(&o, (size_t)N * ho * wo * b.cout));
+    {
+      GenLaunch g{&b.c2, c1, b.cout, h1, w1, N, o, b.cout, 0, OUT_NONE};
+      g.pad_mode = 1; g.sub = b.kind == 1;
+      g.res = b.kind ? s : t; g.res_pitch = b.cout;
+      if (last_body) { g.res2 = feat; g.res2_pitch = b.cout; g.post = 1.f; }      // x = feat + body(feat)
+      if (!dry) CFB_CHECK(gen_conv(g, n->sm_count, st));
+    }
+    ar.release(c1);
+    if (s) ar.release(s);
+    if (t != feat) ar.release(t);
+    if (last_body && feat) { ar.release(feat); feat = nullptr; }
+    t = o; h = ho; w = wo; c = b.cout;
+  }
+  if (n->n_body == 0) feat = nullptr;
+  CFB_REQUIRE(c == 64, "ParseNet: head must have 64 channels");
+  if (!dry) {
+    CFB_CHECK(conv_thin_out(t, n->mask_w, n->mask_b, out_mask, N, h, w, n->parsing_ch, 1, st));
+    if (out_img) CFB_CHECK(conv_thin_out(t, n->img_w, n->img_b, out_img, N, h, w, 3, 1, st));
+  }
+  ar.release(t);
+  return 0;
+}
+
+}  // namespace cfb
+
+// =========================================================================================================
 // C ABI
 // =========================================================================================================
 #define API_BEGIN try {
@@ -1363,6 +1581,102 @@ int cfb_rrdb_forward(cfb_rrdb* n, const float* x, float* out, int32_t batch, int
   CFB_REQUIRE(n && (batch == 0 || (x && out && workspace)), "cfb_rrdb_forward: NULL argument");
   std::lock_guard<std::mutex> lk(n->mu);
   return cfb::rrdb_forward(n, x, out, batch, h, w, workspace, workspace_bytes, (cudaStream_t)stream);
+  API_END(1)
+}
+
+cfb_parsenet* cfb_parsenet_create(int32_t in_size, int32_t out_size, int32_t min_feat_size, int32_t base_ch, int32_t parsing_ch,
+                                  int32_t res_depth, int32_t ch_min, int32_t ch_max) {
+  API_BEGIN
+  cfb_parsenet* n = new cfb_parsenet();
+  n->in_size = in_size; n->out_size = out_size; n->min_feat = min_feat_size; n->base_ch = base_ch; n->parsing_ch = parsing_ch;
+  n->res_depth = res_depth; n->ch_min = ch_min; n->ch_max = ch_max;
+  if (in_size < 1 || out_size < 1 || min_feat_size < 1 || cfb::pn_build(n) != 0) { delete n; return nullptr; }
+  return n;
+  API_END(nullptr)
+}
+void cfb_parsenet_destroy(cfb_parsenet* n) {
+  if (!n) return;
+  if (n->slab) {
+    int cur = -1;
+    const bool sw = cudaGetDevice(&cur) == cudaSuccess && n->device >= 0 && cur != n->device;
+    if (sw) cudaSetDevice(n->device);
+    cudaFree(n->slab);
+    if (sw) cudaSetDevice(cur);
+  }
+  delete n;
+}
+int cfb_parsenet_set_param(cfb_parsenet* n, const char* name, const float* dev_ptr, int64_t numel) {
+  API_BEGIN
+  CFB_REQUIRE(n && name && dev_ptr, "cfb_parsenet_set_param: NULL argument");
+  std::lock_guard<std::mutex> lk(n->mu);
+  n->raw[name] = {dev_ptr, numel};
+  n->prepared = false;
+  return 0;
+  API_END(1)
+}
+int cfb_parsenet_prepare(cfb_parsenet* n, void* stream) {
+  API_BEGIN
+  CFB_REQUIRE(n, "cfb_parsenet_prepare: NULL net");
+  std::lock_guard<std::mutex> lk(n->mu);
+  return cfb::pn_prepare(n, (cudaStream_t)stream);
+  API_END(1)
+}
+int64_t cfb_parsenet_workspace_bytes(cfb_parsenet* n, int32_t batch, int32_t h, int32_t w) {
+  API_BEGIN
+  if (!n) { cfb::set_error("cfb_parsenet_workspace_bytes: NULL net"); return -1; }
+  std::lock_guard<std::mutex> lk(n->mu);
+  if (cfb::pn_forward(n, (const float*)0x1000, (float*)0x1000, (float*)0x1000, batch, h, w, nullptr, 0, nullptr, true) != 0) return -1;
+  return (int64_t)n->arena.high() + 4096;
+  API_END(-1)
+}
+int cfb_parsenet_forward(cfb_parsenet* n, const float* x, float* out_mask, float* out_img, int32_t batch, int32_t h, int32_t w,
+                         void* workspace, int64_t workspace_bytes, void* stream) {
+  API_BEGIN
+  CFB_REQUIRE(n && (batch == 0 || (x && out_mask && workspace)), "cfb_parsenet_forward: NULL argument");
+  std::lock_guard<std::mutex> lk(n->mu);
+  return cfb::pn_forward(n, x, out_mask, out_img, batch, h, w, workspace, workspace_bytes, (cudaStream_t)stream, false);
+  API_END(1)
+}
+int cfb_parse_argmax(const float* logits_nchw, uint8_t* classes, uint8_t* mask, int32_t batch, int32_t channels, int64_t hw, void* stream) {
+  API_BEGIN
+  CFB_REQUIRE(logits_nchw && (classes || mask), "cfb_parse_argmax: NULL argument");
+  return cfb::parse_argmax(logits_nchw, classes, mask, batch, channels, hw, (cudaStream_t)stream);
+  API_END(1)
+}
+
+int64_t cfb_conv2d_gen_workspace_bytes(int32_t cin, int32_t cout) {
+  const size_t cin_p = (size_t)(cin + 63) / 64 * 64, cout_p = (size_t)(cout + 63) / 64 * 64;
+  return (int64_t)(align256(cout_p * cin_p * 9 * 4) + 2 * align256(cout_p * cin_p * 16 * 2) + align256(cout_p * 4) + 256 + 4096);
+}
+
+int cfb_conv2d_gen_nhwc(const float* in, int32_t in_pitch, const float* weight_oihw, const float* bias, float* out,
+                        int32_t out_pitch, int32_t out_c0, int32_t n, int32_t h, int32_t w, int32_t cin, int32_t cout,
+                        int32_t upsample, int32_t pad_mode, int32_t subsample, int32_t out_act, const float* residual,
+                        int32_t res_pitch, const float* residual2, int32_t res2_pitch, float post_scale, void* workspace,
+                        int64_t workspace_bytes, void* stream) {
+  API_BEGIN
+  CFB_REQUIRE(in && weight_oihw && out && workspace, "cfb_conv2d_gen_nhwc: NULL argument");
+  CFB_REQUIRE(workspace_bytes >= cfb_conv2d_gen_workspace_bytes(cin, cout), "cfb_conv2d_gen_nhwc: workspace too small");
+  CFB_REQUIRE(cin >= 1 && cout >= 1 && cout % 4 == 0, "cfb_conv2d_gen_nhwc: cout must be a multiple of 4");
+  cudaStream_t st = (cudaStream_t)stream;
+  CFB_CHECK(cfb::async_status_init(st));
+  int dev = 0, sms = 148;
+  CFB_CUDA(cudaGetDevice(&dev));
+  CFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  cfb::GenConv c;
+  c.cin = cin; c.cout = cout; c.cin_p = (cin + 63) / 64 * 64; c.cout_p = (cout + 63) / 64 * 64; c.up = upsample != 0;
+  char* p = (char*)(((uintptr_t)workspace + 255) / 256 * 256);
+  float* pad = (float*)p; p += align256((size_t)c.cout_p * c.cin_p * 9 * 4);
+  const size_t wn = (size_t)c.cout_p * c.cin_p * (c.up ? 16 : 9);
+  c.w_hi = (__half*)p; p += align256(wn * 2);
+  c.w_lo = (__half*)p; p += align256(wn * 2);
+  c.bias = (float*)p; p += align256((size_t)c.cout_p * 4);
+  c.wscale = (float*)p;
+  CFB_CHECK(cfb::gen_conv_prepare(c, weight_oihw, bias, pad, st));
+  cfb::GenLaunch g{&c, in, in_pitch, h, w, n, out, out_pitch, out_c0, out_act};
+  g.res = residual; g.res_pitch = res_pitch; g.res2 = residual2; g.res2_pitch = res2_pitch; g.post = post_scale;
+  g.pad_mode = pad_mode; g.sub = subsample != 0;
+  return cfb::gen_conv(g, sms, st);
   API_END(1)
 }
 

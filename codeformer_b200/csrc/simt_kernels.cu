@@ -1588,3 +1588,52 @@ int scale_vec(float* p, int n, float f, cudaStream_t st) {
 }
 
 }  // namespace cfb
+
+namespace cfb {
+// BatchNorm2d in eval mode folded into the preceding bias-free conv (parsenet.py:87-88,98,103-104):
+//   w'[co] = w[co] * gamma[co] / sqrt(var[co] + eps),   b'[co] = beta[co] - mean[co] * gamma[co] / sqrt(var[co] + eps)
+__global__ void fold_bn_kernel(const float* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ mean, const float* __restrict__ var, float eps, float* __restrict__ wout,
+                               float* __restrict__ bout, int Cout, int per_out) {
+  const int co = blockIdx.x;
+  const float s = gamma[co] / sqrtf(var[co] + eps);
+  for (int i = threadIdx.x; i < per_out; i += blockDim.x) wout[(int64_t)co * per_out + i] = w[(int64_t)co * per_out + i] * s;
+  if (threadIdx.x == 0) bout[co] = beta[co] - mean[co] * s;
+}
+int fold_bn(const float* w, const float* gamma, const float* beta, const float* mean, const float* var, float eps, float* wout,
+            float* bout, int Cout, int per_out, cudaStream_t st) {
+  if (Cout == 0) return 0;
+  fold_bn_kernel<<<Cout, 256, 0, st>>>(w, gamma, beta, mean, var, eps, wout, bout, Cout, per_out);
+  CFB_LAUNCH_CHECK();
+  return 0;
+}
+
+// out.argmax(dim=1) of the parsing logits + the caller's class -> mask value table (face_restoration_helper.py:463-468)
+__global__ void parse_argmax_kernel(const float* __restrict__ logits, unsigned char* __restrict__ cls, unsigned char* __restrict__ mask,
+                                    int C, int64_t HW, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / HW, px = i - n * HW;
+    const float* p = logits + n * C * HW + px;
+    float best = p[0];
+    int bi = 0;
+    for (int c = 1; c < C; ++c) {
+      const float v = p[(int64_t)c * HW];
+      if (v > best) { best = v; bi = c; }           // first maximum, like torch.argmax
+    }
+    if (cls) cls[i] = (unsigned char)bi;
+    if (mask) {
+      // MASK_COLORMAP = [0, 255 x13, 0, 255, 0, 0, 0]
+      const bool on = (bi >= 1 && bi <= 13) || bi == 15;
+      mask[i] = on ? 255 : 0;
+    }
+  }
+}
+int parse_argmax(const float* logits_nchw, unsigned char* cls, unsigned char* mask, int N, int C, int64_t HW, cudaStream_t st) {
+  const int64_t total = (int64_t)N * HW;
+  if (total == 0) return 0;
+  const int64_t blocks = (total + 255) / 256;
+  parse_argmax_kernel<<<(unsigned)(blocks > 148 * 16 ? 148 * 16 : blocks), 256, 0, st>>>(logits_nchw, cls, mask, C, HW, total);
+  CFB_LAUNCH_CHECK();
+  return 0;
+}
+}  // namespace cfb

@@ -192,6 +192,38 @@ int64_t   cfb_rrdb_workspace_bytes(cfb_rrdb* net, int32_t batch, int32_t h, int3
 int       cfb_rrdb_forward(cfb_rrdb* net, const float* x, float* out, int32_t batch, int32_t h, int32_t w,
                            void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- ParseNet: face parsing of the restored face for the paste-back blend ----
+ * /root/reference/facelib/parsing/parsenet.py:140-194; built by init_parsing_model('parsenet') as ParseNet(in_size=512,
+ * out_size=512, parsing_ch=19) (facelib/parsing/__init__.py:13) and called at facelib/utils/face_restoration_helper.py:457-462.
+ * Parameters are the reference's state-dict names (encoder.0.conv2d, {encoder,body,decoder}.{i}.{shortcut_func,conv1,conv2}.
+ * conv2d.{weight,bias}, ...norm.norm.{weight,bias,running_mean,running_var}); eval-mode BatchNorm is folded at prepare.
+ * x: [batch,3,h,w] fp32 NCHW in [-1,1]; out_mask: [batch, parsing_ch, h, w] logits; out_img (optional): [batch,3,h,w].
+ * cfb_parse_argmax: classes = out_mask.argmax(1) (first maximum) and/or the caller's 0/255 face mask of
+ * face_restoration_helper.py:463-468 (MASK_COLORMAP), both uint8 [batch, h*w]. */
+typedef struct cfb_parsenet cfb_parsenet;
+cfb_parsenet* cfb_parsenet_create(int32_t in_size, int32_t out_size, int32_t min_feat_size, int32_t base_ch, int32_t parsing_ch,
+                                  int32_t res_depth, int32_t ch_min, int32_t ch_max);
+void      cfb_parsenet_destroy(cfb_parsenet* net);
+int       cfb_parsenet_set_param(cfb_parsenet* net, const char* name, const float* dev_ptr, int64_t numel);
+int       cfb_parsenet_prepare(cfb_parsenet* net, void* stream);
+int64_t   cfb_parsenet_workspace_bytes(cfb_parsenet* net, int32_t batch, int32_t h, int32_t w);
+int       cfb_parsenet_forward(cfb_parsenet* net, const float* x, float* out_mask, float* out_img, int32_t batch, int32_t h, int32_t w,
+                               void* workspace, int64_t workspace_bytes, void* stream);
+int       cfb_parse_argmax(const float* logits_nchw, uint8_t* classes, uint8_t* mask, int32_t batch, int32_t channels, int64_t hw,
+                           void* stream);
+
+/* One 3x3 conv of the generalised fused-transform engine (the building block of RRDBNet / ParseNet; test entry point).
+ * in: NHWC buffer of in_pitch channels per pixel, channels [0, cin) are read; any h x w.  upsample != 0: nearest x2 first.
+ * pad_mode 0 zero / 1 reflect / 2 replicate (of the low-resolution tensor when upsampling).  subsample != 0: stride 2 (the
+ * even output positions of the stride-1 result; h, w even).  out: NHWC buffer of out_pitch channels, the cout real channels
+ * go to [out_c0, out_c0 + cout).  out = lrelu?(conv + bias + residual) * post_scale + residual2 (post only with residual2). */
+int64_t cfb_conv2d_gen_workspace_bytes(int32_t cin, int32_t cout);
+int cfb_conv2d_gen_nhwc(const float* in, int32_t in_pitch, const float* weight_oihw, const float* bias, float* out,
+                        int32_t out_pitch, int32_t out_c0, int32_t n, int32_t h, int32_t w, int32_t cin, int32_t cout,
+                        int32_t upsample, int32_t pad_mode, int32_t subsample, int32_t out_act, const float* residual,
+                        int32_t res_pitch, const float* residual2, int32_t res2_pitch, float post_scale, void* workspace,
+                        int64_t workspace_bytes, void* stream);
+
 /* Asynchronous failures.  Kernels never trap and never leave a sticky CUDA error behind (the reference's callers catch
  * RuntimeError and fall back to the input face, inference_codeformer.py:209-211; web-demos/hugging_face/app.py:176): a
  * barrier time-out of the tensor-core pipeline or an activation outside the fp16 operand range (|x| > 65504) sets a bit

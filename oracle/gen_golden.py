@@ -15,6 +15,8 @@ Files
   vq_micro.npz              VectorQuantizer.forward on the config-3 inputs (seeded), indices + z_q samples + stats
   rrdbnet.npz               RRDBNet.forward (section 8 f4) of the reference, 23 blocks, scale 2 and scale 4, small seeded images
                             (`python oracle/gen_golden.py rrdbnet` regenerates only this file)
+  parsenet.npz              ParseNet.forward (section 8 f3) of the reference, shipped 512 configuration, face 0
+                            (`python oracle/gen_golden.py parsenet` regenerates only this file)
   plumbing.npz              the caller's image plumbing (section 8 f1): img2tensor(face/255.)+normalize and
                             tensor2img(min_max=(-1,1)).astype(uint8) of the reference on a u8 face that holds every byte
                             value in every channel and on an fp32 tensor that holds every rounding half-way point
@@ -116,7 +118,43 @@ def gen_rrdbnet():
     np.savez_compressed(os.path.join(OUT, 'rrdbnet.npz'), **out)
 
 
+def load_ref_parsenet():
+    """The UNMODIFIED reference class (facelib/parsing/parsenet.py; imports only numpy / torch)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('ref_parsenet', os.path.join(ref_shim.REF_ROOT, 'facelib', 'parsing', 'parsenet.py'))
+    mod = importlib.util.module_from_spec(spec)
+    sys.dont_write_bytecode = True
+    spec.loader.exec_module(mod)
+    return mod.ParseNet
+
+
+def parsenet_inputs():
+    """The shipped configuration (facelib/parsing/__init__.py:13) with seeded parameters, on committed face 0 in [-1,1]
+    (face_restoration_helper.py:458-460)."""
+    from codeformer_b200 import parsing as P
+    sd = P.random_parsenet_state_dict(P.parsenet_spec(512, 512, 32, 64, 19, 10, (32, 256)), 41)
+    faces = np.load(os.path.join(OUT, 'faces.npz'))['faces'][:1]
+    return sd, to_input(faces)
+
+
+def gen_parsenet():
+    """tests/golden/parsenet.npz: ParseNet(512, 512, parsing_ch=19).eval() of the reference on face 0: logits at stride 4, the
+    full-resolution argmax classes and the top-1/top-2 margin (index parity is asserted where the margin exceeds the noise)."""
+    ParseNet = load_ref_parsenet()
+    torch.set_grad_enabled(False)
+    sd, x = parsenet_inputs()
+    net = ParseNet(in_size=512, out_size=512, parsing_ch=19).eval()
+    net.load_state_dict(sd, strict=True)
+    mask, img = net(x)
+    top2 = mask.topk(2, dim=1).values
+    np.savez_compressed(os.path.join(OUT, 'parsenet.npz'), mask_s4=mask[..., ::4, ::4].numpy(), img_s8=img[..., ::8, ::8].numpy(),
+                        classes=mask.argmax(1).numpy().astype(np.uint8), margin=(top2[:, 0] - top2[:, 1]).numpy().astype(np.float16))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == 'parsenet':
+        gen_parsenet()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == 'rrdbnet':
         gen_rrdbnet()
         return
@@ -176,6 +214,7 @@ def main():
         np.savez_compressed(os.path.join(OUT, 'vq_micro.npz'), **mic)
     gen_plumbing()
     gen_rrdbnet()
+    gen_parsenet()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, 'KiB')
 
