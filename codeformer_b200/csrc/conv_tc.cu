@@ -568,6 +568,13 @@ struct TcParams {
   int chunk;              // k-blocks accumulated in TMEM before the partial sum is folded into registers
   int a_c0, b_c0;         // channel offsets of the A / B operand inside their planes (batched-GEMM mode)
   int b_batched;          // B operand is a per-image activation plane: third TMA coordinate = image index, not the tap
+  // batched GEMM over (image, head) pairs (multi-head attention): the "image" index nb of an m-tile is n * heads + h
+  int heads;              // 1: plain
+  int a_c_head, b_c_head; // channel offset per head inside the A / B planes
+  int a_img_per_head;     // A planes hold one image per (n, h) (softmax probabilities) instead of one per n
+  int b_r_head;           // row offset per head inside the B planes (V^T: rows = h*64 + c)
+  int out_per_head;       // 1: out is [n*heads + h][256][Cout]; 0: out is [n][256][Cout] and head h owns columns [h*o_c_head, ..)
+  int o_c_head;
   int up4;                // Upsample as four 2x2 convs: m-tile = (low-res tile, output parity), 4 taps, weights [16][Cout][Cin]
   int PW, PH;             // halo engine: input patch (BW+k-1) x (BH+k-1) pixels fetched once per 64-channel block
   // GEN variant (XF only; ParseNet / RRDBNet): true image sizes with ragged tiles, padding mode of the halo patch, output
@@ -580,6 +587,7 @@ struct TcParams {
   const float* residual2; // out = (conv + bias + residual) * post_scale + residual2
   int res2_pitch;
   float post_scale;
+  const float* vq_e2; const float* vq_z2; float2* vq_cand; double* vq_dpart;   // VectorQuantizer argmin epilogue (see ConvArgs)
   int fault;              // test hook (cfb_debug_inject_fault): CTA 0 drops the weight load of its first stage -> barrier time-out
   int xform;              // XF kernel variant requested (in_scale may be null: raw split)
   int a_split;            // XF: k-blocks [0, a_split) are read from fp32 source 0 (tmA_hi), the rest from source 1 (tmA_lo)
@@ -823,23 +831,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               mbar_wait<500>(smem_u32(empty + stage), phase ^ 1, aborted); if (aborted) goto teardown;
               if (elect_one()) {
                 const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                const int b3 = p.b_batched ? n : btap;
+                // multi-head batched GEMM: image index n = n_img * heads + head
+                const int hh = p.heads > 1 ? n % p.heads : 0, nimg = p.heads > 1 ? n / p.heads : n;
+                const int a_img = p.a_img_per_head ? n : nimg;
+                const int ac = p.a_c0 + hh * p.a_c_head + kb * 64, bc = p.b_c0 + hh * p.b_c_head + kb * 64;
+                const int brow = nt * BN + hh * p.b_r_head;
+                const int b3 = p.b_batched ? nimg : btap;
                 if constexpr (PAIR) {
                   // the leader's `full` barrier counts the bytes of both CTAs
                   if (rank == 0) mbar_expect_tx(smem_u32(full + stage), (uint32_t)(2 * Cfg::P_STAGE_BYTES));
                   const uint32_t fb = map_to_cta(smem_u32(full + stage), rank0);
-                  tma_load_4d_pair(sa, &tmA_hi, fb, p.a_c0 + kb * 64, x0 + s - p.pad, y0 + r - p.pad, n);
-                  tma_load_4d_pair(sa + TC_A_BYTES, &tmA_lo, fb, p.a_c0 + kb * 64, x0 + s - p.pad, y0 + r - p.pad, n);
-                  tma_load_3d_pair(sa + 2 * TC_A_BYTES, rank == 0 ? &tmB_hi : &tmB_lo, fb, p.b_c0 + kb * 64, nt * BN, b3);
-                  tma_load_3d_pair(sa + 2 * TC_A_BYTES + Cfg::P_BX_BYTES, &tmB_half, fb, p.b_c0 + kb * 64,
-                                   nt * BN + (int)rank * (BN / 2), b3);
+                  tma_load_4d_pair(sa, &tmA_hi, fb, ac, x0 + s - p.pad, y0 + r - p.pad, a_img);
+                  tma_load_4d_pair(sa + TC_A_BYTES, &tmA_lo, fb, ac, x0 + s - p.pad, y0 + r - p.pad, a_img);
+                  tma_load_3d_pair(sa + 2 * TC_A_BYTES, rank == 0 ? &tmB_hi : &tmB_lo, fb, bc, brow, b3);
+                  tma_load_3d_pair(sa + 2 * TC_A_BYTES + Cfg::P_BX_BYTES, &tmB_half, fb, bc, brow + (int)rank * (BN / 2), b3);
                 } else {
                   const uint32_t fb = smem_u32(full + stage);
                   mbar_expect_tx(fb, (uint32_t)Cfg::STAGE_BYTES);
-                  tma_load_4d(sa, &tmA_hi, fb, p.a_c0 + kb * 64, x0 + s - p.pad, y0 + r - p.pad, n);
-                  tma_load_4d(sa + TC_A_BYTES, &tmA_lo, fb, p.a_c0 + kb * 64, x0 + s - p.pad, y0 + r - p.pad, n);
-                  tma_load_3d(sa + 2 * TC_A_BYTES, &tmB_hi, fb, p.b_c0 + kb * 64, nt * BN, b3);
-                  tma_load_3d(sa + 2 * TC_A_BYTES + Cfg::B_BYTES, &tmB_lo, fb, p.b_c0 + kb * 64, nt * BN, b3);
+                  tma_load_4d(sa, &tmA_hi, fb, ac, x0 + s - p.pad, y0 + r - p.pad, a_img);
+                  tma_load_4d(sa + TC_A_BYTES, &tmA_lo, fb, ac, x0 + s - p.pad, y0 + r - p.pad, a_img);
+                  tma_load_3d(sa + 2 * TC_A_BYTES, &tmB_hi, fb, bc, brow, b3);
+                  tma_load_3d(sa + 2 * TC_A_BYTES + Cfg::B_BYTES, &tmB_lo, fb, bc, brow, b3);
                 }
               }
               __syncwarp();
@@ -1063,6 +1075,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       constexpr int RPP = 4 * XFW;                                  // patch rows per pass (8 lanes per row)
       constexpr int XF_PW = 10, XF_PH = 18, XF_ROWS = XF_PW * XF_PH;   // halo patch of an 8 x 16 tile and a 3 x 3 filter
       constexpr int NPASS = (XF_ROWS + RPP - 1) / RPP;
+      constexpr int NPASS1 = (128 + RPP - 1) / RPP;                     // 1x1 convs: the patch is the 8 x 16 tile itself
       const int t = (warp - (2 + TC_EPI_WARPS)) * 32 + lane;
       const int j = t & 7, rsub = t >> 3;
       const int pl = j >> 2, c0 = 2 * (j & 3);                      // source plane and first 16-byte chunk of this lane's 8 channels
@@ -1081,7 +1094,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int rem = mt - n * per_img;
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
         const int y0 = ty * p.BH - p.pad, x0 = tx * p.BW - p.pad;
-        const bool border = y0 < 0 || x0 < 0 || y0 + XF_PH > Hin || x0 + XF_PW > Win;
+        const bool border = y0 < 0 || x0 < 0 || y0 + p.PH > Hin || x0 + p.PW > Win;
         for (int kb = 0; kb < p.kblocks; ++kb) {
           float sc[8], sh[8];
           if (mode) {
@@ -1100,7 +1113,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const uint32_t base0 = smem_u32(smem + aslot * Cfg::H_A_SLOT);
           const uint32_t src_base = base0 + (pl ? (uint32_t)Cfg::X_A_PLANE2 : 0u);
           const uint32_t lo_base = base0 + (uint32_t)Cfg::X_A_PLANE2;
-          if (mode == 2) xf_patch<2, RPP, NPASS, XF_PW, XF_ROWS>(src_base, base0, lo_base, c0, j, rsub, sc, sh, border, y0, x0, Hin, Win, amax);
+          if (p.taps == 1) {
+            if (mode == 2) xf_patch<2, RPP, NPASS1, 8, 128>(src_base, base0, lo_base, c0, j, rsub, sc, sh, border, y0, x0, Hin, Win, amax);
+            else if (mode == 1) xf_patch<1, RPP, NPASS1, 8, 128>(src_base, base0, lo_base, c0, j, rsub, sc, sh, border, y0, x0, Hin, Win, amax);
+            else xf_patch<0, RPP, NPASS1, 8, 128>(src_base, base0, lo_base, c0, j, rsub, sc, sh, border, y0, x0, Hin, Win, amax);
+          } else if (mode == 2) xf_patch<2, RPP, NPASS, XF_PW, XF_ROWS>(src_base, base0, lo_base, c0, j, rsub, sc, sh, border, y0, x0, Hin, Win, amax);
           else if (mode == 1) xf_patch<1, RPP, NPASS, XF_PW, XF_ROWS>(src_base, base0, lo_base, c0, j, rsub, sc, sh, border, y0, x0, Hin, Win, amax);
           else xf_patch<0, RPP, NPASS, XF_PW, XF_ROWS>(src_base, base0, lo_base, c0, j, rsub, sc, sh, border, y0, x0, Hin, Win, amax);
           if constexpr (GEN) {
@@ -1156,14 +1173,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const int mt = mtile_of(pm);
       const int mtl = p.up4 ? (mt >> 2) : mt;
       const int per_img = p.tiles_x * p.tiles_y;
-      const int n = mtl / per_img;
-      const int rem = mtl - n * per_img;
+      const int nb = mtl / per_img;
+      const int rem = mtl - nb * per_img;
+      // multi-head batched GEMM writing [n][token][heads * o_c_head]: head h of image n owns its column slice
+      const bool hsplit = p.heads > 1 && !p.out_per_head;
+      const int n = hsplit ? nb / p.heads : nb;
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
       const int h = row / p.BW, w = row - h * p.BW;
       int oy = ty * p.BH + h, ox = tx * p.BW + w;
       if (p.up4) { oy = 2 * oy + ((mt & 3) >> 1); ox = 2 * ox + (mt & 1); }   // this tile writes one output parity
       const int64_t pix = ((int64_t)n * p.Ho + oy) * p.Wo + ox;
-      const int col0 = nt * BN + cbase;
+      const int col0 = nt * BN + cbase + (hsplit ? (nb % p.heads) * p.o_c_head : 0);
       const int64_t off0 = pix * p.Cout + col0;
       // pull this thread's residual / SFT row slices towards L2 now: they are consumed only after the whole K loop
       if (!GEN && p.residual) {
@@ -1206,6 +1226,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       // instruction.  Each warp instead transposes 32x32-float blocks through a private 4 KB XOR-swizzled smem patch:
       // afterwards lane l holds the 16-byte chunk (l & 7) of row (l >> 3) + 4*it, i.e. 8 lanes cover one full 128-byte
       // line and every global access (residual / SFT loads, the store) is a fully used line.
+      if (!GEN && p.vq_cand) {
+        // VectorQuantizer.forward (vqgan_arch.py:40-46): this thread owns token row `pix` and HC codes; d = (|z|^2 + |e|^2) - 2 z.e
+        // in the reference's operation order, first minimum of the slice (ascending index, strict <); no staging, no store of
+        // the [tokens, codes] matrix.  The candidates of a token (2 per n-tile) are reduced by vq_select_cand.
+        const float z2 = __ldg(p.vq_z2 + pix);
+        float best = INFINITY, dsum = 0.f;
+        int bi = col0;
+#pragma unroll
+        for (int j = 0; j < HC; ++j) {
+          const float d = (z2 + __ldg(p.vq_e2 + col0 + j)) - 2.f * (acc[j] * wsi);
+          dsum += d;
+          if (d < best) { best = d; bi = col0 + j; }
+        }
+        p.vq_cand[pix * (2 * p.n_tiles) + nt * 2 + half] = make_float2(best, __int_as_float(bi));
+        double ds = (double)dsum;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ds += __shfl_xor_sync(0xffffffffu, ds, o);
+        if (lane == 0) p.vq_dpart[((int64_t)mt * p.n_tiles + nt) * 8 + (warp - 2)] = ds;
+        continue;
+      }
       float4* stg = reinterpret_cast<float4*>(stage_buf) + (warp - 2) * 256;     // 32 rows x 8 chunks
       const int cch = lane & 7, rsub = lane >> 3;
       if constexpr (GEN) {
@@ -1456,7 +1496,8 @@ struct TcGeom { int BW, BH; bool halo; };
 static TcGeom tc_geometry(const ConvArgs& a) {
   TcGeom g;
   const int Wt = a.mode == CONV_UP ? a.W : a.Wo, Ht = a.mode == CONV_UP ? a.H : a.Ho;   // grid the tiles live on
-  g.halo = halo_enabled() && pair_enabled() && a.ksize == 3 && (a.mode == CONV_SAME || a.mode == CONV_UP) &&
+  g.halo = halo_enabled() && pair_enabled() && (a.ksize == 3 || (a.ksize == 1 && a.halo1x1 && a.mode == CONV_SAME)) &&
+           (a.mode == CONV_SAME || a.mode == CONV_UP) &&
            ((Wt % 8 == 0 && Ht % 16 == 0) || a.gen);      // gen: ragged tiles, stores are bounds-checked
   if (g.halo) { g.BW = 8; g.BH = 16; }
   else { g.BW = tile_bw(a.mode == CONV_UP ? a.W : a.Wo); g.BH = 128 / g.BW; }   // Upsample: tiles live on the low-res grid
@@ -1492,7 +1533,7 @@ bool tc_supported(const ConvArgs& a) {
 bool tc_can_xform(const ConvArgs& a) {
   static const int mode = [] { const char* e = getenv("CFB_TC_XFORM"); return e ? atoi(e) : 1; }();
   if (a.gen) return tc_supported(a);      // generalised variant: tile count is padded to an even number, CONV_UP included
-  if (mode == 0 || !tc_supported(a) || a.mode != CONV_SAME || a.ksize != 3) return false;
+  if (mode == 0 || !tc_supported(a) || a.mode != CONV_SAME || !(a.ksize == 3 || (a.ksize == 1 && a.halo1x1))) return false;
   if (mode == 3 && !(a.Cout % 128 == 0 && a.Cin >= 128 && (int64_t)a.Ho * a.Wo >= 4096)) return false;
   const TcGeom g = tc_geometry(a);
   if (!g.halo) return false;
@@ -1564,7 +1605,8 @@ static int launch_tc(const TcMaps& m, const TcParams& p, int sm_count, cudaStrea
     }
   }
   if (p.xform) {         // fused operand transform: conv_tc() only asks for it when tc_can_xform() holds
-    CFB_REQUIRE(p.PW == 10 && p.PH == 18 && pair_ok(p), "conv_tc: fused operand transform needs the halo + pair engine");
+    CFB_REQUIRE(((p.PW == 10 && p.PH == 18) || (p.PW == 8 && p.PH == 16 && p.taps == 1)) && pair_ok(p),
+                "conv_tc: fused operand transform needs the halo + pair engine");
     return launch_tc2<BN, CPG, true, true, true>(m, p, sm_count, st);
   }
   if (p.PW > 0) return pair_ok(p) ? launch_tc2<BN, CPG, true, true>(m, p, sm_count, st) : launch_tc2<BN, CPG, true, false>(m, p, sm_count, st);
@@ -1658,6 +1700,7 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
   p.taps = a.ksize * a.ksize; p.pad = a.mode == CONV_DOWN ? 0 : a.ksize / 2; p.stride = a.mode == CONV_DOWN ? 2 : 1;
   p.up4 = a.mode == CONV_UP ? 1 : 0;
   p.a_c0 = 0; p.b_c0 = 0; p.b_batched = 0;
+  p.heads = 1; p.a_c_head = 0; p.b_c_head = 0; p.a_img_per_head = 0; p.b_r_head = 0; p.out_per_head = 1; p.o_c_head = 0;
   if (p.up4) { p.taps = 4; p.pad = 1; }
   p.chunk = tc_chunk_kblocks();
   p.PW = PW; p.PH = PH;
@@ -1683,6 +1726,8 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
   if (p.taps * p.kblocks <= 12) p.chunk = p.taps * p.kblocks;   // short K (Cin = 64): one partial sum, no 8+1 split
   p.in_scale = nullptr; p.in_shift = nullptr; p.in_act = IN_NONE; p.xform = a.xform ? 1 : 0;
   p.fault = g_inject_fault.exchange(0);
+  p.vq_e2 = a.vq_e2; p.vq_z2 = a.vq_z2; p.vq_cand = a.vq_cand; p.vq_dpart = a.vq_dpart;
+  CFB_REQUIRE(!a.vq_cand || (a.vq_e2 && a.vq_z2 && a.vq_dpart && a.ksize == 1 && !a.gen && !a.xform), "conv_tc: VQ argmin epilogue needs e2, z2 and the 1x1 engine");
   p.a_split = a.in2 ? a.Cin1 / 64 : a.Cin / 64;
   if (a.xform) {
     CFB_REQUIRE(a.skip_prep && tc_can_xform(a), "conv_tc: fused operand transform not available for this conv");
@@ -1724,15 +1769,19 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
 // (/root/reference/basicsr/archs/vqgan_arch.py:209-222).
 // ------------------------------------------------------------------------------------------------------
 int bmm_tc(const BmmArgs& g, int sm_count, cudaStream_t st) {
-  CFB_REQUIRE(g.K % 64 == 0 && g.Cout % 128 == 0 && g.N >= 0, "bmm_tc: K must be a multiple of 64 and Cout of 128");
-  CFB_REQUIRE(g.a_c0 % 64 == 0 && g.b_c0 % 64 == 0 && g.a_pitch % 8 == 0 && g.b_pitch % 8 == 0, "bmm_tc: unaligned operand slice");
+  const int BN = g.Cout % 128 == 0 ? 128 : 64;
+  CFB_REQUIRE(g.K % 64 == 0 && g.Cout % 64 == 0 && g.N >= 0 && g.heads >= 1, "bmm_tc: K and Cout must be multiples of 64");
+  CFB_REQUIRE(g.a_c0 % 64 == 0 && g.b_c0 % 64 == 0 && g.a_pitch % 8 == 0 && g.b_pitch % 8 == 0 && g.a_c_head % 64 == 0 &&
+                  g.b_c_head % 64 == 0 && g.b_r_head % BN == 0 && g.o_c_head % 4 == 0,
+              "bmm_tc: unaligned operand slice");
   if (g.N == 0) return 0;
-  const size_t a_plane = ((size_t)g.N * 256 * g.a_pitch * 2 + 1023) / 1024 * 1024;
+  const int a_imgs = g.a_img_per_head ? g.N * g.heads : g.N;
+  const size_t a_plane = ((size_t)a_imgs * 256 * g.a_pitch * 2 + 1023) / 1024 * 1024;
   const size_t b_plane = ((size_t)g.N * g.b_rows * g.b_pitch * 2 + 1023) / 1024 * 1024;
   TcMaps mp;
   CUtensorMap &mA_hi = mp.a_hi, &mA_lo = mp.a_lo, &mB_hi = mp.b_hi, &mB_lo = mp.b_lo;
   {
-    const uint64_t dims[4] = {(uint64_t)g.a_pitch, 16, 16, (uint64_t)g.N};
+    const uint64_t dims[4] = {(uint64_t)g.a_pitch, 16, 16, (uint64_t)a_imgs};
     const uint64_t str[3] = {(uint64_t)g.a_pitch * 2, (uint64_t)16 * g.a_pitch * 2, (uint64_t)256 * g.a_pitch * 2};
     const uint32_t box[4] = {64, 16, 8, 1};
     CFB_CHECK(make_map(&mA_hi, g.a_planes, 4, dims, str, box));
@@ -1741,29 +1790,36 @@ int bmm_tc(const BmmArgs& g, int sm_count, cudaStream_t st) {
   {
     const uint64_t dims[3] = {(uint64_t)g.b_pitch, (uint64_t)g.b_rows, (uint64_t)g.N};
     const uint64_t str[2] = {(uint64_t)g.b_pitch * 2, (uint64_t)g.b_rows * g.b_pitch * 2};
-    const uint32_t box[3] = {64, 128, 1};
+    const uint32_t box[3] = {64, (uint32_t)BN, 1};
     CFB_CHECK(make_map(&mB_hi, g.b_planes, 3, dims, str, box));
     CFB_CHECK(make_map(&mB_lo, (const char*)g.b_planes + b_plane, 3, dims, str, box));
-    const uint32_t hbox[3] = {64, 64, 1};
+    const uint32_t hbox[3] = {64, (uint32_t)(BN / 2), 1};
     CFB_CHECK(make_map(&mp.b_half, g.b_planes, 3, dims, str, hbox));
   }
+  const int out_pitch = g.out_per_head ? g.Cout : g.heads * g.o_c_head;      // channels per token row of `out`
+  const int out_imgs = g.out_per_head ? g.N * g.heads : g.N;
+  CFB_REQUIRE(g.heads == 1 || g.out_per_head || g.o_c_head == g.Cout, "bmm_tc: a head's column slice must equal its Cout");
   TcParams p;
-  p.N = g.N; p.Ho = 16; p.Wo = 16; p.Cout = g.Cout;
+  p.N = g.N * g.heads; p.Ho = 16; p.Wo = 16; p.Cout = out_pitch;
   p.taps = 1; p.pad = 0; p.stride = 1; p.up4 = 0;
   p.a_c0 = g.a_c0; p.b_c0 = g.b_c0; p.b_batched = 1;
+  p.heads = g.heads; p.a_c_head = g.a_c_head; p.b_c_head = g.b_c_head; p.a_img_per_head = g.a_img_per_head ? 1 : 0;
+  p.b_r_head = g.b_r_head; p.out_per_head = g.out_per_head ? 1 : 0; p.o_c_head = g.o_c_head;
   p.chunk = tc_chunk_kblocks();
   p.PW = 0; p.PH = 0;
   p.BW = 16; p.BH = 8; p.tiles_x = 1; p.tiles_y = 2;
-  p.m_tiles = g.N * 2; p.n_tiles = g.Cout / 128; p.kblocks = g.K / 64;
+  p.m_tiles = g.N * g.heads * 2; p.n_tiles = g.Cout / BN; p.kblocks = g.K / 64;
+  if (p.kblocks <= 12) p.chunk = p.kblocks;
   p.in_scale = nullptr; p.in_shift = nullptr; p.in_act = IN_NONE; p.xform = 0; p.a_split = 0; p.fault = 0;
-  p.Hin = 16; p.Win = 16; p.pad_mode = 0; p.sub = 0; p.out_pitch = g.Cout; p.out_c0 = 0; p.cout_valid = g.Cout; p.res_pitch = g.Cout;
-  p.residual2 = nullptr; p.res2_pitch = g.Cout; p.post_scale = 1.f;
+  p.vq_e2 = nullptr; p.vq_z2 = nullptr; p.vq_cand = nullptr; p.vq_dpart = nullptr;
+  p.Hin = 16; p.Win = 16; p.pad_mode = 0; p.sub = 0; p.out_pitch = out_pitch; p.out_c0 = 0; p.cout_valid = out_pitch; p.res_pitch = out_pitch;
+  p.residual2 = nullptr; p.res2_pitch = out_pitch; p.post_scale = 1.f;
   p.bias = nullptr; p.residual = nullptr; p.out_act = OUT_NONE; p.sft_dec = nullptr; p.sft_scale = nullptr; p.sft_w = 0.f;
   p.wscale_inv = g.scale_dev; p.out = g.out;
   p.gn_part = nullptr; p.gn_cpg = 0;
   p.pl_hi = (__half*)g.out_planes;
-  p.pl_lo = g.out_planes ? (__half*)((char*)g.out_planes + (((size_t)g.N * 256 * g.Cout * 2 + 1023) / 1024 * 1024)) : nullptr;
-  return launch_tc<128, 0>(mp, p, sm_count, st);
+  p.pl_lo = g.out_planes ? (__half*)((char*)g.out_planes + (((size_t)out_imgs * 256 * out_pitch * 2 + 1023) / 1024 * 1024)) : nullptr;
+  return BN == 128 ? launch_tc<128, 0>(mp, p, sm_count, st) : launch_tc<64, 0>(mp, p, sm_count, st);
 }
 
 // softmax over rows of 256 fp32 scores -> fp16 hi/lo operand planes of the probabilities (one warp per row)

@@ -21,7 +21,13 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st);
 struct BmmArgs {
   const void* a_planes = nullptr; int a_pitch = 0, a_c0 = 0;   // A: [N][256][a_pitch] hi | lo
   const void* b_planes = nullptr; int b_pitch = 0, b_c0 = 0, b_rows = 0;   // B: [N][b_rows][b_pitch] hi | lo
-  int N = 0, K = 0, Cout = 0;
+  int N = 0, K = 0, Cout = 0;          // Cout: output columns of ONE (image, head) GEMM
+  // multi-head attention (codeformer_arch.py:126): one GEMM per (image, head); head h reads channels +h*a_c_head / +h*b_c_head
+  // of the A / B planes (scores) or rows +h*b_r_head of B (V^T); A may hold one image per (n, h) (the probabilities)
+  int heads = 1, a_c_head = 0, b_c_head = 0, b_r_head = 0;
+  bool a_img_per_head = false;
+  bool out_per_head = true;            // out = [N*heads][256][Cout]; false: out = [N][256][heads*o_c_head], head h -> its column slice
+  int o_c_head = 0;
   const float* scale_dev = nullptr;   // device scalar multiplied into the result
   float* out = nullptr;               // [N][256][Cout] fp32
   void* out_planes = nullptr;         // optional hi | lo planes of out

@@ -196,6 +196,7 @@ struct cfb_net {
   // small owned copies of norm params etc. live in the slab too
   std::vector<std::pair<const float**, std::pair<std::string, int64_t>>> vec_params;  // (dst, (name, numel))
   std::vector<ConvW*> convs;
+  float* mha_consts = nullptr;        // device: [0] = head_dim^-1/2, [1] = 1
   unsigned* gn_counters = nullptr;    // ticket-counter ring of the split GroupNorm finalize (in the slab, zero between uses)
   int gn_ctr_pos = 0;
   int device = -1;                    // CUDA device the slab / prepared weights live on
@@ -396,7 +397,7 @@ static int prepare(cfb_net* n, cudaStream_t st) {
   const size_t scratch = align256((size_t)3 * 512 * 512 * 4) + align256(3 * 512 * 4);
   total += scratch;
   total += 256 * (n->enc.size() + n->gen.size());      // per-AttnBlock device constants
-  total += align256((size_t)GN_COUNTERS * sizeof(unsigned));
+  total += align256((size_t)GN_COUNTERS * sizeof(unsigned)) + 256;
   // the net lives on the device that is current at prepare time (net.to(other_gpu) -> a new prepare): slab, SM count and
   // engine availability all follow it
   int dev = 0, major = 0, sms = 148;
@@ -424,6 +425,11 @@ static int prepare(cfb_net* n, cudaStream_t st) {
   CFB_CHECK(async_status_init(st));
   char* p = (char*)n->slab;
   auto take = [&](size_t bytes) { char* r = p; p += align256(bytes); return r; };
+  n->mha_consts = (float*)take(256);
+  {
+    const float hc[2] = {n->cfg.kind == 1 ? 1.0f / sqrtf((float)(n->cfg.dim_embd / n->cfg.n_head)) : 1.0f, 1.0f};
+    CFB_CUDA(cudaMemcpyAsync(n->mha_consts, hc, sizeof(hc), cudaMemcpyHostToDevice, st));
+  }
   n->gn_counters = (unsigned*)take((size_t)GN_COUNTERS * sizeof(unsigned));
   n->gn_ctr_pos = 0;
   CFB_CUDA(cudaMemsetAsync(n->gn_counters, 0, (size_t)GN_COUNTERS * sizeof(unsigned), st));
@@ -581,6 +587,8 @@ struct Fwd {
       //  raw  the producer already emitted this tensor's fp16 hi/lo planes and the consumer takes it untransformed;
       //  prep everything else: a separate operand-preparation pass over the fp32 tensor.
       const bool plain = !o.in_scale && !o.in_shift && o.in_act == IN_NONE;
+      a.halo1x1 = w.k == 1 && o.mode == CONV_SAME && o.in_scale && o.in_shift && in.p;     // AttnBlock q,k,v on GroupNorm(x)
+      if (a.halo1x1 && !tc_can_xform(a)) a.halo1x1 = false;
       const bool xf = in.p && tc_can_xform(a) && ((o.in_scale && o.in_shift) || (plain && !in.planes));   // plain: in-kernel split only
       const bool raw = !xf && in.planes && plain;
       const bool reuse = raw || xf;
@@ -890,14 +898,43 @@ struct Fwd {
         CFB_CHECK(alloc(qkin, B, lq.H, lq.W, E));
         if (!dry) CFB_CHECK(layer_norm(x.p, L.n1.gamma, L.n1.beta, t2.p, qkin.p, n->position_emb, S, T, E, st));
       }
-      { ConvOpt o; CFB_CHECK(conv(L.qk, qkin, qk, o)); }
-      { ConvOpt o; CFB_CHECK(conv(L.v, t2, v, o)); }
+      { ConvOpt o; o.want_planes = tcp; o.planes_only = tcp; CFB_CHECK(conv(L.qk, qkin, qk, o)); }
+      { ConvOpt o; o.want_planes = tcp; o.planes_only = tcp; CFB_CHECK(conv(L.v, t2, v, o)); }
       release(qkin); release(t2);
-      if (tcp) CFB_CHECK(planes_tensor(a, E, plE));
-      else CFB_CHECK(alloc(a, B, lq.H, lq.W, E));
-      if (!dry)
-        CFB_CHECK(attention(qk.p, qk.p + E, v.p, a.p, B, S, c.n_head, E / c.n_head, 2 * E, 2 * E, E, E,
-                            sqrtf(1.0f / (float)(E / c.n_head)), st, a.planes));
+      if (tcp) {
+        // nn.MultiheadAttention core (codeformer_arch.py:126) on the tcgen05 engine: per (image, head) GEMMs on operand planes --
+        // scores = (q_h k_h^T) * d^-1/2 (K = 64, the power-of-two scale commutes exactly with the product), softmax -> planes
+        // of the probabilities, out_h = P v_h written as the operand planes of out_proj (no fp32 copy of anything)
+        const int Hh = c.n_head, dh = E / c.n_head;
+        CFB_CHECK(planes_tensor(a, E, plE));
+        float* scores = nullptr;
+        void *pp = nullptr, *vt = nullptr;
+        const int64_t rows = (int64_t)B * Hh * S;
+        CFB_CHECK(alloc_raw((void**)&scores, (size_t)rows * S * 4));
+        CFB_CHECK(alloc_raw(&pp, 2 * (((size_t)rows * S * 2 + 1023) / 1024 * 1024)));
+        CFB_CHECK(alloc_raw(&vt, 2 * (((size_t)B * E * S * 2 + 1023) / 1024 * 1024)));
+        if (!dry) {
+          BmmArgs g1;
+          g1.a_planes = qk.planes; g1.a_pitch = 2 * E; g1.a_c0 = 0; g1.a_c_head = dh;
+          g1.b_planes = qk.planes; g1.b_pitch = 2 * E; g1.b_c0 = E; g1.b_c_head = dh; g1.b_rows = S;
+          g1.N = B; g1.heads = Hh; g1.K = dh; g1.Cout = S; g1.scale_dev = n->mha_consts; g1.out = scores; g1.out_per_head = true;
+          CFB_CHECK(bmm_tc(g1, n->sm_count, st));
+          CFB_CHECK(softmax256_planes(scores, pp, rows, st));
+          CFB_CHECK(transpose_planes(v.planes, B, E, 0, E, vt, st));
+          BmmArgs g2;
+          g2.a_planes = pp; g2.a_pitch = S; g2.a_c0 = 0; g2.a_img_per_head = true;
+          g2.b_planes = vt; g2.b_pitch = S; g2.b_c0 = 0; g2.b_rows = E; g2.b_r_head = dh;
+          g2.N = B; g2.heads = Hh; g2.K = S; g2.Cout = dh; g2.scale_dev = n->mha_consts + 1; g2.out = nullptr; g2.out_planes = a.planes;
+          g2.out_per_head = false; g2.o_c_head = dh;
+          CFB_CHECK(bmm_tc(g2, n->sm_count, st));
+        }
+        release_raw(scores); release_raw(pp); release_raw(vt);
+      } else {
+        CFB_CHECK(alloc(a, B, lq.H, lq.W, E));
+        if (!dry)
+          CFB_CHECK(attention(qk.p, qk.p + E, v.p, a.p, B, S, c.n_head, E / c.n_head, 2 * E, 2 * E, E, E,
+                              sqrtf(1.0f / (float)(E / c.n_head)), st, nullptr));
+      }
       release(qk); release(v);
       { ConvOpt o; o.residual = x.p; CFB_CHECK(conv(L.o, a, x2, o)); }
       release(a); release(x);
