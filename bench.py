@@ -271,8 +271,12 @@ def extra_configs(torch, cb, S, net, peaks, dev):
     vq.embedding.weight.data.copy_(E)
     vq = vq.to(dev)
     ms = _median_ms(torch, lambda: vq(z, return_min_encodings=False), 50)
+    vq.vq_graphs = False
+    ms_eager = _median_ms(torch, lambda: vq(z, return_min_encodings=False), 50)
+    vq.vq_graphs = True
     nbytes = 17.9e6            # z 8.39 + E 1.05 + z_q 8.39 + idx 0.07 MB
-    out['vq_micro'] = {'ms': ms, 'vectors_per_s': 8192 / (ms * 1e-3), 'algorithmic_bytes': nbytes,
+    out['vq_micro'] = {'ms': ms, 'ms_without_cuda_graph': ms_eager, 'launches_per_call': 4,
+                       'vectors_per_s': 8192 / (ms * 1e-3), 'algorithmic_bytes': nbytes,
                        'roofline': {'bound': 'hbm', 'achieved': nbytes / (ms * 1e-3) / 1e9, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                                     'frac': nbytes / (ms * 1e-3) / 1e9 / peaks['hbm_gbs']},
                        'what': 'BASELINE configs[2]: VectorQuantizer.forward, z [32,256,16,16] vs 1024 codes, NCHW in / NCHW out, '
@@ -286,6 +290,29 @@ def extra_configs(torch, cb, S, net, peaks, dev):
                        'step_algorithmic_tflops': 64 / (ms * 1e-3) * 580.59 / 1e3,
                        'what': 'BASELINE configs[3]: VQAutoEncoder(512,64,[1,2,2,4,4,8]).forward at batch 64, median of 3'}
     del vqae, x64
+    torch.cuda.empty_cache()
+    # ---- the caller-side networks on the same engine (random-init weights of the reference
+    # architectures, synthetic inputs; parity vs the reference goldens is in tests/test_gpu_aux.py)
+    from codeformer_b200 import parsing as P
+    pn = cb.ParseNet(in_size=512, out_size=512, parsing_ch=19)
+    pn.load_state_dict(P.random_parsenet_state_dict(P.parsenet_spec(512, 512, 32, 64, 19, 10, (32, 256)), 41), strict=True)
+    pn = pn.eval().to(dev)
+    xf = synthetic_batch(8, 13).to(dev)
+    ms = _median_ms(torch, lambda: cb.face_parse_mask(pn(xf, return_img=False)[0]), 5, warm=2)
+    out['parsenet_b8'] = {'faces_per_s': 8 / (ms * 1e-3), 'ms_per_step': ms,
+                          'what': 'row f3: ParseNet(512,512,parsing_ch=19).forward + argmax/MASK_COLORMAP on 8 restored faces '
+                                  '(facelib/utils/face_restoration_helper.py:457-468), median of 5'}
+    del pn, xf
+    rr = cb.RRDBNet(3, 3, scale=2, num_feat=64, num_block=23, num_grow_ch=32)
+    rr.load_state_dict(S.random_state_dict(S.rrdbnet_spec(3, 3, 2, 64, 23, 32), 21), strict=True)
+    rr = rr.eval().to(dev)
+    xt = torch.rand(1, 3, 480, 480, generator=torch.Generator().manual_seed(4)).to(dev)
+    ms = _median_ms(torch, lambda: rr(xt), 5, warm=2)
+    gflop = 57600 * 35.8e-3          # 240x240 feature pixels x 35.8 MFLOP (69 dense blocks + body/up/hr convs)
+    out['rrdbnet_tile'] = {'ms_per_tile': ms, 'input_mpix_per_s': 0.2304 / (ms * 1e-3), 'algorithmic_tflops': gflop / ms,
+                           'what': 'row f4: RRDBNet(3,3,scale=2, 23 blocks) on one 480x480 tile = RealESRGANer tile 400 + 2x40 pad '
+                                   '(inference_codeformer.py:36-61), output 960x960, median of 5; ~2.06 TFLOP nominal per tile'}
+    del rr, xt
     torch.cuda.empty_cache()
     return out
 

@@ -45,6 +45,11 @@ SIGNATURES = {
     'cfb_vqae_forward': (c_int, [_P, _P, _P, _P, _P, _P, c_int32, _P, c_int64, _P]),
     'cfb_vq_workspace_bytes': (c_int64, [c_int32, c_int32, c_int32, c_int32]),
     'cfb_vq_nearest': (c_int, [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, _P, _P, _P, _P, _P, c_int64, _P]),
+    'cfb_vq_fast_supported': (c_int32, [c_int32] * 5),
+    'cfb_vq_prepared_bytes': (c_int64, [c_int32, c_int32]),
+    'cfb_vq_prepare': (c_int, [_P, c_int32, c_int32, _P, c_int64, _P]),
+    'cfb_vq_fast_workspace_bytes': (c_int64, [c_int32] * 4),
+    'cfb_vq_nearest_fast': (c_int, [_P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, _P, _P, _P, _P, _P, c_int64, _P]),
     'cfb_codebook_lookup': (c_int, [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     'cfb_conv2d_nhwc': (c_int, [_P, _P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                 _P, _P, c_int32, _P, c_int32, c_int32, _P, c_int64, _P]),

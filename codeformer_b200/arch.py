@@ -169,6 +169,8 @@ class VectorQuantizer(nn.Module):
             raise RuntimeError(f'VectorQuantizer: expected {self.emb_dim} channels, got {D}')
         E = self.embedding.weight.detach().contiguous()
         with torch.cuda.device(z.device):
+            if lib.cfb_vq_fast_supported(B, H, W, D, self.codebook_size) and E.dtype == torch.float32:
+                return self._forward_fused(lib, z, E, return_min_encodings)
             zq = torch.empty_like(z)
             idx = torch.empty((B * H * W, 1), dtype=torch.int64, device=z.device)
             stats = torch.empty(4, dtype=torch.float32, device=z.device)
@@ -181,6 +183,68 @@ class VectorQuantizer(nn.Module):
                                           _lib.ptr(ws), wsb, _stream_ptr(z.device)), 'cfb_vq_nearest')
         return zq, stats[0], {'perplexity': stats[1], 'min_encodings': onehot,
                               'min_encoding_indices': idx, 'mean_distance': stats[2]}
+
+    # Fused path (include/cfb200.h: cfb_vq_nearest_fast): the split codebook + |e|^2 are prepared once per embedding version,
+    # the workspace is kept, and -- like the single-face forward -- the 4-launch sequence is replayed from a CUDA graph
+    # captured per shape, so a call costs one graph launch instead of ~25 us of host-side launches.
+    vq_graphs = True
+
+    def _forward_fused(self, lib, z, E, return_min_encodings):
+        dev = z.device
+        B, D, H, W = z.shape
+        K = self.codebook_size
+        cache = self.__dict__.setdefault('_cfb_vq', {})
+        w = self.embedding.weight
+        sig = (w.data_ptr(), w._version, str(dev))
+        if cache.get('sig') != sig:
+            prep = torch.empty(int(lib.cfb_vq_prepared_bytes(K, D)), dtype=torch.uint8, device=dev)
+            _lib.check(lib.cfb_vq_prepare(_lib.ptr(E), K, D, _lib.ptr(prep), prep.numel(), _stream_ptr(dev)), 'cfb_vq_prepare')
+            cache.clear()
+            cache.update(sig=sig, prep=prep, E=E, graphs={})
+        prep, E = cache['prep'], cache['E']
+        T = B * H * W
+
+        def launch(zs, zq, idx, stats, onehot, ws):
+            _lib.check(lib.cfb_vq_nearest_fast(_lib.ptr(zs), _lib.ptr(E), _lib.ptr(prep), B, H, W, D, K, float(self.beta),
+                                               _lib.ptr(zq), _lib.ptr(idx), _lib.ptr(stats), _lib.ptr(onehot), _lib.ptr(ws),
+                                               ws.numel(), _stream_ptr(dev)), 'cfb_vq_nearest_fast')
+
+        def buffers():
+            return (torch.empty_like(z), torch.empty((T, 1), dtype=torch.int64, device=dev),
+                    torch.empty(4, dtype=torch.float32, device=dev),
+                    torch.empty((T, K), dtype=torch.float32, device=dev) if return_min_encodings else None,
+                    torch.empty(int(lib.cfb_vq_fast_workspace_bytes(B, H * W, D, K)), dtype=torch.uint8, device=dev))
+        use_graph = T > 0 and self.vq_graphs and os.environ.get('CFB_CUDA_GRAPH', '1') != '0' \
+            and not torch.cuda.is_current_stream_capturing()
+        if use_graph:
+            key = (B, H, W, bool(return_min_encodings))
+            ent = cache['graphs'].get(key)
+            if ent is None:
+                if len(cache['graphs']) >= 4:
+                    cache['graphs'].pop(next(iter(cache['graphs'])))
+                zs = torch.empty_like(z)
+                bufs = buffers()
+                zs.copy_(z)
+                launch(zs, *bufs)                                   # eager warm-up (function attributes) before the capture
+                torch.cuda.current_stream(dev).synchronize()
+                g = torch.cuda.CUDAGraph()
+                try:
+                    with torch.cuda.graph(g):
+                        launch(zs, *bufs)
+                    ent = (g, zs, bufs)
+                except Exception:
+                    ent = False
+                cache['graphs'][key] = ent
+            if ent:
+                g, zs, (zq, idx, stats, onehot, _) = ent
+                zs.copy_(z)
+                g.replay()
+                st = stats.clone()
+                return zq.clone(), st[0], {'perplexity': st[1], 'min_encodings': None if onehot is None else onehot.clone(),
+                                            'min_encoding_indices': idx.clone(), 'mean_distance': st[2]}
+        zq, idx, stats, onehot, ws = buffers()
+        launch(z, zq, idx, stats, onehot, ws)
+        return zq, stats[0], {'perplexity': stats[1], 'min_encodings': onehot, 'min_encoding_indices': idx, 'mean_distance': stats[2]}
 
     def get_codebook_feat(self, indices, shape):
         """vqgan_arch.py:72-84: indices -> codebook rows; ``shape`` = [B,H,W,C] gives an NCHW result."""

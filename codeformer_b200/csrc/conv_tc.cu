@@ -387,6 +387,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -672,13 +681,14 @@ struct TcCfg {
 // 60 %) and each SM stages / reads only half of every B operand.  Rank 0 (leader) issues all MMAs; its `full` and `cempty`
 // barriers collect the TMA bytes / epilogue arrivals of both CTAs; `empty` and `cfull` are signalled in both CTAs by
 // multicast commits.
-template <int BN, int CPG, bool HALO, bool PAIR, bool XF, bool GEN = false>
+template <int BN, int CPG, bool HALO, bool PAIR, bool XF, bool GEN = false, bool K1 = false>
 __global__ void __launch_bounds__(XF ? TcCfg<BN>::XF_THREADS : TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                const __grid_constant__ CUtensorMap tmB_half, const TcParams p) {
   static_assert(!XF || (HALO && PAIR), "the fused operand transform exists for the halo + pair engine only");
   static_assert(!GEN || (XF && CPG == 0), "the generalised addressing exists for the fused-transform engine only");
+  static_assert(!K1 || (XF && !GEN && CPG == 0), "K1 = fused transform of a 1x1 conv (patch = tile): its own instantiation");
   using Cfg = TcCfg<BN>;
   constexpr int A_SLOTS = XF ? Cfg::X_A_SLOTS : Cfg::H_A_SLOTS;
   constexpr int STAGES = PAIR ? Cfg::P_STAGES : Cfg::STAGES;
@@ -1094,7 +1104,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int rem = mt - n * per_img;
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
         const int y0 = ty * p.BH - p.pad, x0 = tx * p.BW - p.pad;
-        const bool border = y0 < 0 || x0 < 0 || y0 + p.PH > Hin || x0 + p.PW > Win;
+        const bool border = !K1 && (y0 < 0 || x0 < 0 || y0 + XF_PH > Hin || x0 + XF_PW > Win);
         for (int kb = 0; kb < p.kblocks; ++kb) {
           float sc[8], sh[8];
           if (mode) {
@@ -1113,13 +1123,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const uint32_t base0 = smem_u32(smem + aslot * Cfg::H_A_SLOT);
           const uint32_t src_base = base0 + (pl ? (uint32_t)Cfg::X_A_PLANE2 : 0u);
           const uint32_t lo_base = base0 + (uint32_t)Cfg::X_A_PLANE2;
-          if (p.taps == 1) {
+          if constexpr (K1) {
             if (mode == 2) xf_patch<2, RPP, NPASS1, 8, 128>(src_base, base0, lo_base, c0, j, rsub, sc, sh, border, y0, x0, Hin, Win, amax);
             else if (mode == 1) xf_patch<1, RPP, NPASS1, 8, 128>(src_base, base0, lo_base, c0, j, rsub, sc, sh, border, y0, x0, Hin, Win, amax);
             else xf_patch<0, RPP, NPASS1, 8, 128>(src_base, base0, lo_base, c0, j, rsub, sc, sh, border, y0, x0, Hin, Win, amax);
-          } else if (mode == 2) xf_patch<2, RPP, NPASS, XF_PW, XF_ROWS>(src_base, base0, lo_base, c0, j, rsub, sc, sh, border, y0, x0, Hin, Win, amax);
-          else if (mode == 1) xf_patch<1, RPP, NPASS, XF_PW, XF_ROWS>(src_base, base0, lo_base, c0, j, rsub, sc, sh, border, y0, x0, Hin, Win, amax);
-          else xf_patch<0, RPP, NPASS, XF_PW, XF_ROWS>(src_base, base0, lo_base, c0, j, rsub, sc, sh, border, y0, x0, Hin, Win, amax);
+          } else {
+            if (mode == 2) xf_patch<2, RPP, NPASS, XF_PW, XF_ROWS>(src_base, base0, lo_base, c0, j, rsub, sc, sh, border, y0, x0, Hin, Win, amax);
+            else if (mode == 1) xf_patch<1, RPP, NPASS, XF_PW, XF_ROWS>(src_base, base0, lo_base, c0, j, rsub, sc, sh, border, y0, x0, Hin, Win, amax);
+            else xf_patch<0, RPP, NPASS, XF_PW, XF_ROWS>(src_base, base0, lo_base, c0, j, rsub, sc, sh, border, y0, x0, Hin, Win, amax);
+          }
           if constexpr (GEN) {
             if (p.pad_mode && border) {
               // ReflectionPad2d / replicate padding: an out-of-image pixel of the patch equals an in-image pixel of the SAME
@@ -1176,7 +1188,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const int nb = mtl / per_img;
       const int rem = mtl - nb * per_img;
       // multi-head batched GEMM writing [n][token][heads * o_c_head]: head h of image n owns its column slice
-      const bool hsplit = p.heads > 1 && !p.out_per_head;
+      const bool hsplit = !HALO && p.heads > 1 && !p.out_per_head;       // batched-GEMM kernels only (per-tap engine)
       const int n = hsplit ? nb / p.heads : nb;
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
       const int h = row / p.BW, w = row - h * p.BW;
@@ -1204,14 +1216,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         mbar_wait<250>(smem_u32(cfull + slot), slot_phase, aborted); if (aborted) goto teardown;
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(slot * Cfg::SLOT_COLS + cbase);
+        if constexpr (XF) {
+          // the transform variants run 15 / 19 warps per CTA (128 / 96 registers per thread): 16-column TMEM chunks keep the
+          // fold inside the register budget (32-column chunks spilled the accumulators)
 #pragma unroll
-        for (int c0 = 0; c0 < HC; c0 += 32) {          // main half at +0, cross half at +BN; round-to-nearest adds
-          uint32_t r0[32], r1[32];
-          tmem_ld32(taddr + c0, r0);
-          tmem_ld32(taddr + BN + c0, r1);
-          tmem_ld_wait();
+          for (int c0 = 0; c0 < HC; c0 += 16) {
+            uint32_t r0[16], r1[16];
+            tmem_ld16(taddr + c0, r0);
+            tmem_ld16(taddr + BN + c0, r1);
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+            for (int j = 0; j < 16; ++j) acc[c0 + j] += __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+          }
+        } else {
+#pragma unroll
+          for (int c0 = 0; c0 < HC; c0 += 32) {          // main half at +0, cross half at +BN; round-to-nearest adds
+            uint32_t r0[32], r1[32];
+            tmem_ld32(taddr + c0, r0);
+            tmem_ld32(taddr + BN + c0, r1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -1226,7 +1252,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       // instruction.  Each warp instead transposes 32x32-float blocks through a private 4 KB XOR-swizzled smem patch:
       // afterwards lane l holds the 16-byte chunk (l & 7) of row (l >> 3) + 4*it, i.e. 8 lanes cover one full 128-byte
       // line and every global access (residual / SFT loads, the store) is a fully used line.
-      if (!GEN && p.vq_cand) {
+      if (!HALO && !GEN && p.vq_cand) {
         // VectorQuantizer.forward (vqgan_arch.py:40-46): this thread owns token row `pix` and HC codes; d = (|z|^2 + |e|^2) - 2 z.e
         // in the reference's operation order, first minimum of the slice (ascending index, strict <); no staging, no store of
         // the [tokens, codes] matrix.  The candidates of a token (2 per n-tile) are reduced by vq_select_cand.
@@ -1311,27 +1337,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int colq = col0 + q + cch * 4;                  // first of this lane's 4 channels
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + colq));
-        // global offsets of the 8 (row, chunk) items of this lane, then ALL residual loads in flight at once
-        int64_t offs[8];
+        // global offsets of the (row, chunk) items of this lane, then their residual loads in flight at once: all 8 rows, or two
+        // batches of 4 in the register-capped transform variants
+        constexpr int RB = XF ? 4 : 8;
+        float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
+        for (int ib = 0; ib < 8; ib += RB) {
+        int64_t offs[RB];
+#pragma unroll
+        for (int k = 0; k < RB; ++k) {
+          const int it = ib + k;
           const int trow = lg * 32 + it * 4 + rsub;
           const int hh = trow / p.BW, ww = trow - hh * p.BW;
           int oy2 = ty * p.BH + hh, ox2 = tx * p.BW + ww;
           if (p.up4) { oy2 = 2 * oy2 + ((mt & 3) >> 1); ox2 = 2 * ox2 + (mt & 1); }
-          offs[it] = (((int64_t)n * p.Ho + oy2) * p.Wo + ox2) * p.Cout + colq;
+          offs[k] = (((int64_t)n * p.Ho + oy2) * p.Wo + ox2) * p.Cout + colq;
         }
-        float4 rres[8];
+        float4 rres[RB];
 #pragma unroll
-        for (int it = 0; it < 8; ++it)
-          rres[it] = p.residual ? __ldg(reinterpret_cast<const float4*>(p.residual + offs[it])) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+        for (int k = 0; k < RB; ++k)
+          rres[k] = p.residual ? __ldg(reinterpret_cast<const float4*>(p.residual + offs[k])) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
+        for (int k = 0; k < RB; ++k) {
+          const int it = ib + k;
           const int r = it * 4 + rsub;                        // row within this warp's 32-row quadrant
           float4 v = stg[r * 8 + (cch ^ (r & 7))];
-          const int64_t off = offs[it];
-          v.x += bv.x + rres[it].x; v.y += bv.y + rres[it].y; v.z += bv.z + rres[it].z; v.w += bv.w + rres[it].w;
+          const int64_t off = offs[k];
+          v.x += bv.x + rres[k].x; v.y += bv.y + rres[k].y; v.z += bv.z + rres[k].z; v.w += bv.w + rres[k].w;
           if (p.out_act == OUT_LRELU) {
             v.x = v.x > 0.f ? v.x : 0.2f * v.x; v.y = v.y > 0.f ? v.y : 0.2f * v.y;
             v.z = v.z > 0.f ? v.z : 0.2f * v.z; v.w = v.w > 0.f ? v.w : 0.2f * v.w;
@@ -1366,6 +1398,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             s0 += (v.x + v.y) + (v.z + v.w);
             q0 += fmaf(v.x, v.x, v.y * v.y) + fmaf(v.z, v.z, v.w * v.w);
           }
+        }
         }
         if constexpr (CPG > 0) {
           // GroupNorm partial sums of the values just stored: reduce over the 4 row-lanes (xor 8, 16) and, for groups
@@ -1533,7 +1566,7 @@ bool tc_supported(const ConvArgs& a) {
 bool tc_can_xform(const ConvArgs& a) {
   static const int mode = [] { const char* e = getenv("CFB_TC_XFORM"); return e ? atoi(e) : 1; }();
   if (a.gen) return tc_supported(a);      // generalised variant: tile count is padded to an even number, CONV_UP included
-  if (mode == 0 || !tc_supported(a) || a.mode != CONV_SAME || !(a.ksize == 3 || (a.ksize == 1 && a.halo1x1))) return false;
+  if (mode == 0 || !tc_supported(a) || a.mode != CONV_SAME || !(a.ksize == 3 || (a.ksize == 1 && a.halo1x1 && a.Cout % 128 == 0))) return false;
   if (mode == 3 && !(a.Cout % 128 == 0 && a.Cin >= 128 && (int64_t)a.Ho * a.Wo >= 4096)) return false;
   const TcGeom g = tc_geometry(a);
   if (!g.halo) return false;
@@ -1557,7 +1590,7 @@ static bool pair_ok(const TcParams& p) {
 
 struct TcMaps { CUtensorMap a_hi, a_lo, b_hi, b_lo, b_half; };
 
-template <int BN, int CPG, bool HALO, bool PAIR, bool XF = false, bool GEN = false>
+template <int BN, int CPG, bool HALO, bool PAIR, bool XF = false, bool GEN = false, bool K1 = false>
 static int launch_tc2(const TcMaps& m, const TcParams& p, int sm_count, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
   constexpr int SMEM = XF ? Cfg::X_SMEM_BYTES
@@ -1571,7 +1604,7 @@ static int launch_tc2(const TcMaps& m, const TcParams& p, int sm_count, cudaStre
   CFB_CUDA(cudaGetDevice(&dev));
   const uint64_t bit = 1ull << (dev & 63);
   if (!(attr_done.load(std::memory_order_acquire) & bit)) {
-    CFB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, CPG, HALO, PAIR, XF, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    CFB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, CPG, HALO, PAIR, XF, GEN, K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_done.fetch_or(bit, std::memory_order_release);
   }
   if constexpr (PAIR) {
@@ -1586,12 +1619,12 @@ static int launch_tc2(const TcMaps& m, const TcParams& p, int sm_count, cudaStre
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    CFB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, CPG, HALO, PAIR, XF, GEN>, m.a_hi, m.a_lo, m.b_hi, m.b_lo, m.b_half, p));
+    CFB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, CPG, HALO, PAIR, XF, GEN, K1>, m.a_hi, m.a_lo, m.b_hi, m.b_lo, m.b_half, p));
     count_launch();
   } else {
     const int total = p.m_tiles * p.n_tiles;
     const int grid = total < sm_count ? total : sm_count;
-    conv_tc_kernel<BN, CPG, HALO, PAIR, XF, GEN><<<grid, THREADS, SMEM, st>>>(m.a_hi, m.a_lo, m.b_hi, m.b_lo, m.b_half, p);
+    conv_tc_kernel<BN, CPG, HALO, PAIR, XF, GEN, K1><<<grid, THREADS, SMEM, st>>>(m.a_hi, m.a_lo, m.b_hi, m.b_lo, m.b_half, p);
     CFB_LAUNCH_CHECK();
   }
   return 0;
@@ -1607,6 +1640,10 @@ static int launch_tc(const TcMaps& m, const TcParams& p, int sm_count, cudaStrea
   if (p.xform) {         // fused operand transform: conv_tc() only asks for it when tc_can_xform() holds
     CFB_REQUIRE(((p.PW == 10 && p.PH == 18) || (p.PW == 8 && p.PH == 16 && p.taps == 1)) && pair_ok(p),
                 "conv_tc: fused operand transform needs the halo + pair engine");
+    if (p.taps == 1) {      // 1x1 conv with a GroupNorm-affine input (AttnBlock q,k,v): patch = tile
+      if constexpr (BN == 128 && CPG == 0) return launch_tc2<128, 0, true, true, true, false, true>(m, p, sm_count, st);
+      else { CFB_REQUIRE(false, "conv_tc: the 1x1 fused transform is built for 128-wide tiles without statistics"); }
+    }
     return launch_tc2<BN, CPG, true, true, true>(m, p, sm_count, st);
   }
   if (p.PW > 0) return pair_ok(p) ? launch_tc2<BN, CPG, true, true>(m, p, sm_count, st) : launch_tc2<BN, CPG, true, false>(m, p, sm_count, st);

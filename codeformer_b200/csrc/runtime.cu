@@ -1990,6 +1990,79 @@ int cfb_vq_nearest(const float* z, const float* codebook, int32_t batch, int32_t
   API_END(1)
 }
 
+// ---- VectorQuantizer.forward, fused path (BASELINE config 3): 4 launches on NCHW tensors ------------------------------------
+int32_t cfb_vq_fast_supported(int32_t batch, int32_t h, int32_t w, int32_t dim, int32_t codes) {
+  cfb::ConvArgs a;
+  if (!vq_tc_args(a, batch, h, w, dim, codes)) return 0;
+  return (codes % 128 == 0 && dim % 64 == 0 && dim <= 352 && (h * w) % 128 == 0 && batch >= 0) ? 1 : 0;
+}
+int64_t cfb_vq_prepared_bytes(int32_t codes, int32_t dim) {
+  return (int64_t)(2 * align256((size_t)codes * dim * 2) + 256 + align256((size_t)codes * 4));
+}
+int cfb_vq_prepare(const float* codebook, int32_t codes, int32_t dim, void* prepared, int64_t prepared_bytes, void* stream) {
+  API_BEGIN
+  CFB_REQUIRE(codebook && prepared && prepared_bytes >= cfb_vq_prepared_bytes(codes, dim), "cfb_vq_prepare: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* p = (char*)prepared;
+  __half* whi = (__half*)p; p += align256((size_t)codes * dim * 2);
+  __half* wlo = (__half*)p; p += align256((size_t)codes * dim * 2);
+  float* wsc = (float*)p; p += 256;
+  float* e2 = (float*)p;
+  CFB_CHECK(cfb::tc_split_weights(codebook, whi, wlo, codes, dim, 1, wsc, st));
+  CFB_CHECK(cfb::vq_e2(codebook, e2, codes, dim, st));
+  return 0;
+  API_END(1)
+}
+int64_t cfb_vq_fast_workspace_bytes(int32_t batch, int32_t hw, int32_t dim, int32_t codes) {
+  const int64_t T = (int64_t)batch * hw;
+  const int64_t planes = 2 * ((T * dim * 2 + 1023) / 1024 * 1024);
+  const int64_t ncand = 2 * (codes / 128);
+  return planes + align256(T * 4) + align256(T * ncand * 8) + align256((T / 128 + 1) * (codes / 128) * 8 * 8) + align256((T / 32 + 1) * 8) +
+         align256((size_t)codes * 4) + 8192;
+}
+int cfb_vq_nearest_fast(const float* z, const float* codebook, const void* prepared, int32_t batch, int32_t h, int32_t w, int32_t dim,
+                        int32_t codes, float beta, float* z_q, int64_t* idx, float* stats, float* min_encodings, void* workspace,
+                        int64_t workspace_bytes, void* stream) {
+  API_BEGIN
+  cudaStream_t st = (cudaStream_t)stream;
+  const int HW = h * w;
+  const int64_t T = (int64_t)batch * HW;
+  if (T == 0) return 0;
+  CFB_REQUIRE(z && codebook && prepared && z_q && idx && stats && workspace, "cfb_vq_nearest_fast: NULL argument");
+  CFB_REQUIRE(cfb_vq_fast_supported(batch, h, w, dim, codes), "cfb_vq_nearest_fast: shape not on the fused path (use cfb_vq_nearest)");
+  CFB_REQUIRE(workspace_bytes >= cfb_vq_fast_workspace_bytes(batch, HW, dim, codes), "cfb_vq_nearest_fast: workspace too small");
+  CFB_CHECK(cfb::async_status_init(st));
+  const char* q = (const char*)prepared;
+  const __half* whi = (const __half*)q; q += align256((size_t)codes * dim * 2);
+  const __half* wlo = (const __half*)q; q += align256((size_t)codes * dim * 2);
+  const float* wsc = (const float*)q; q += 256;
+  const float* e2 = (const float*)q;
+  char* p = (char*)(((uintptr_t)workspace + 1023) / 1024 * 1024);
+  void* planes = p; p += 2 * (((size_t)T * dim * 2 + 1023) / 1024 * 1024);
+  float* z2 = (float*)p; p += align256((size_t)T * 4);
+  const int ncand = 2 * (codes / 128);
+  float2* cand = (float2*)p; p += align256((size_t)T * ncand * 8);
+  const int n_d = (int)(T / 128) * (codes / 128) * 8;
+  double* dpart = (double*)p; p += align256((size_t)(T / 128 + 1) * (codes / 128) * 8 * 8);
+  const int n_se = (int)(T / 32);
+  double* separt = (double*)p; p += align256((size_t)(T / 32 + 1) * 8);
+  unsigned* hist = (unsigned*)p;
+  int dev = 0, sms = 148;
+  CFB_CUDA(cudaGetDevice(&dev));
+  CFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  CFB_CHECK(cfb::vq_prep_nchw(z, planes, z2, hist, batch, dim, HW, codes, st));
+  cfb::ConvArgs a;
+  a.N = batch; a.H = h; a.W = w; a.Cin = dim; a.Ho = h; a.Wo = w; a.Cout = codes; a.ksize = 1; a.mode = cfb::CONV_SAME;
+  a.wgt_hi = whi; a.wgt_lo = wlo; a.wscale_inv = wsc + 1; a.skip_prep = true;
+  a.vq_e2 = e2; a.vq_z2 = z2; a.vq_cand = cand; a.vq_dpart = dpart;
+  CFB_CHECK(cfb::conv_tc(a, planes, sms, st));
+  CFB_CHECK(cfb::vq_select_cand(z, codebook, cand, ncand, batch, dim, HW, codes, idx, z_q, separt, hist, st));
+  CFB_CHECK(cfb::vq_final2(separt, n_se, dpart, n_d, hist, (int)T, dim, codes, beta, stats, st));
+  if (min_encodings) CFB_CHECK(cfb::onehot_from_idx(idx, min_encodings, (int)T, codes, st));
+  return 0;
+  API_END(1)
+}
+
 int cfb_codebook_lookup(const int64_t* idx, const float* codebook, int32_t batch, int32_t h, int32_t w, int32_t dim,
                         int32_t codes, float* z_q, void* stream) {
   API_BEGIN

@@ -126,6 +126,18 @@ int cfb_vq_nearest(const float* z, const float* codebook, int32_t batch, int32_t
                    int32_t dim, int32_t codes, float beta, float* z_q, int64_t* idx, float* stats,
                    float* min_encodings, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* VectorQuantizer.forward, fused path (vqgan_arch.py:33-70; BASELINE configs[2]): the codebook is split for the tensor cores and
+ * its |e|^2 computed ONCE (cfb_vq_prepare, redo when the embedding changes); a call is then 4 launches on the caller's NCHW
+ * tensors: z -> operand planes + |z|^2, distance GEMM on tcgen05 with the argmin in its epilogue (the [tokens, codes] matrix is
+ * never stored), candidate reduction + codebook gather + straight-through z_q + loss partials, statistics.  Same outputs as
+ * cfb_vq_nearest.  cfb_vq_fast_supported: 16x16-style latents (h*w % 128 == 0), dim % 64 == 0, codes % 128 == 0, sm_100. */
+int32_t cfb_vq_fast_supported(int32_t batch, int32_t h, int32_t w, int32_t dim, int32_t codes);
+int64_t cfb_vq_prepared_bytes(int32_t codes, int32_t dim);
+int     cfb_vq_prepare(const float* codebook, int32_t codes, int32_t dim, void* prepared, int64_t prepared_bytes, void* stream);
+int64_t cfb_vq_fast_workspace_bytes(int32_t batch, int32_t hw, int32_t dim, int32_t codes);
+int     cfb_vq_nearest_fast(const float* z, const float* codebook, const void* prepared, int32_t batch, int32_t h, int32_t w,
+                            int32_t dim, int32_t codes, float beta, float* z_q, int64_t* idx, float* stats, float* min_encodings,
+                            void* workspace, int64_t workspace_bytes, void* stream);
 /* ---- VectorQuantizer.get_codebook_feat (vqgan_arch.py:72-84) ---- idx [n] int64 -> z_q [B,D,H,W] NCHW */
 int cfb_codebook_lookup(const int64_t* idx, const float* codebook, int32_t batch, int32_t h, int32_t w,
                         int32_t dim, int32_t codes, float* z_q, void* stream);

@@ -213,3 +213,38 @@ def test_vq_edge_cases():
     # empty batch
     zq, loss, st = vq(torch.empty(0, 256, 16, 16, device='cuda'))
     assert zq.shape == (0, 256, 16, 16) and st['min_encoding_indices'].shape == (0, 1)
+
+
+def test_vq_fused_path_equals_the_unfused_one():
+    """The 4-launch path (argmin in the GEMM epilogue, NCHW in/out, prepared codebook, CUDA-graph replay) against the round-1
+    path (stored dot products) on the config-3 inputs: same indices, z_q and statistics; a changed embedding is picked up."""
+    import codeformer_b200 as cb
+    lib = _lib.load()
+    E, z = vq_micro_inputs('B')
+    vq = cb.VectorQuantizer(1024, 256, 0.25)
+    vq.embedding.weight.data.copy_(E)
+    vq = vq.cuda()
+    zd = z.cuda()
+    assert lib.cfb_vq_fast_supported(32, 16, 16, 256, 1024) == 1
+    zq, loss, st = vq(zd)                                           # fused (graph captured on this call)
+    zq2, loss2, st2 = vq(zd)                                        # graph replay
+    assert torch.equal(zq, zq2) and torch.equal(st['min_encoding_indices'], st2['min_encoding_indices']) and float(loss) == float(loss2)
+    Ed = vq.embedding.weight.detach().contiguous()
+    zq_o = torch.empty_like(zd)
+    idx_o = torch.empty((8192, 1), dtype=torch.int64, device='cuda')
+    stats_o = torch.empty(4, device='cuda')
+    wsb = lib.cfb_vq_workspace_bytes(32, 256, 256, 1024)
+    ws = torch.empty(int(wsb), dtype=torch.uint8, device='cuda')
+    _lib.check(lib.cfb_vq_nearest(_lib.ptr(zd), _lib.ptr(Ed), 32, 16, 16, 256, 1024, 0.25, _lib.ptr(zq_o), _lib.ptr(idx_o),
+                                  _lib.ptr(stats_o), None, _lib.ptr(ws), wsb, G.stream()), 'cfb_vq_nearest')
+    torch.cuda.synchronize()
+    assert torch.equal(st['min_encoding_indices'], idx_o) and torch.equal(zq, zq_o)
+    assert abs(float(loss) - float(stats_o[0])) < 1e-6 * float(stats_o[0])
+    assert abs(float(st['mean_distance']) - float(stats_o[2])) < 1e-5 * float(stats_o[2])
+    with torch.no_grad():
+        vq.embedding.weight.mul_(-1.0)                              # in-place update bumps the version: re-prepared
+    idx_neg = vq(zd)[2]['min_encoding_indices']
+    assert not torch.equal(idx_neg, st['min_encoding_indices'])
+    d = ((z.permute(0, 2, 3, 1).reshape(-1, 256).double() ** 2).sum(1, keepdim=True) + (E.double() ** 2).sum(1)
+         + 2 * z.permute(0, 2, 3, 1).reshape(-1, 256).double() @ E.double().t())
+    assert torch.equal(idx_neg.cpu()[:, 0], d.argmin(1))
