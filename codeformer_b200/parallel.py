@@ -74,6 +74,37 @@ def pipelined_forward_gather(net, x_local: torch.Tensor, out_full: Optional[torc
     return out_full, (torch.cat(locals_, dim=0) if len(locals_) > 1 else locals_[0])
 
 
+class StreamedGather:
+    """Collation for a STREAM of batches (video frames, a folder of faces): the all-gather of batch i is issued asynchronously
+    after forward i and completes on NCCL's stream while forward i+1 runs, so the collective never sits on the critical path and
+    every forward keeps the full per-rank batch (measured on 2 x B200: splitting 32 faces into two 16-face forwards costs more
+    than the 0.33 ms gather it hides).  ``submit(local)`` returns the gathered tensor of the PREVIOUS batch (or None);
+    ``flush()`` returns the last one.  Two rotating output buffers; results are bit-identical to a blocking gather."""
+
+    def __init__(self, group: Optional[dist.ProcessGroup] = None):
+        self.group, self.world = group, dist.get_world_size(group)
+        self.bufs, self.work, self.k, self.keep = [None, None], None, 0, None
+
+    def submit(self, local: torch.Tensor):
+        done = self.flush()
+        buf = self.bufs[self.k]
+        shape = (self.world * local.shape[0],) + tuple(local.shape[1:])
+        if buf is None or tuple(buf.shape) != shape or buf.device != local.device:
+            buf = self.bufs[self.k] = local.new_empty(shape)
+        self.keep = local.contiguous()                       # alive until the collective has read it
+        self.work = (dist.all_gather_into_tensor(buf, self.keep, group=self.group, async_op=True), buf)
+        self.k ^= 1
+        return done
+
+    def flush(self):
+        if self.work is None:
+            return None
+        w, buf = self.work
+        w.wait()
+        self.work = None
+        return buf
+
+
 def sharded_forward(net, x_full: torch.Tensor, group: Optional[dist.ProcessGroup] = None, **fwd_kwargs) -> torch.Tensor:
     """Run ``net`` on this rank's shard of ``x_full`` (same tensor on every rank) and return the gathered
     restored faces ``[B,3,512,512]``."""

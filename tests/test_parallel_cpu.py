@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from codeformer_b200.parallel import gather_faces, pipelined_forward_gather, shard_bounds, sharded_forward
+from codeformer_b200.parallel import StreamedGather, gather_faces, pipelined_forward_gather, shard_bounds, sharded_forward
 
 
 def test_shard_bounds_cover_and_balance():
@@ -48,6 +48,15 @@ def _worker(rank, world, port, batch, ret):
         for chunks in (1, 2, 3):
             got, mine = pipelined_forward_gather(_FakeNet(), xg[rank * per:(rank + 1) * per], chunks=chunks, w=0.5)
             ok = ok and torch.equal(got, fullg) and torch.equal(mine, fullg[rank * per:(rank + 1) * per])
+        # stream of batches: gather i overlaps forward i+1, results arrive one submit later and equal the blocking gather
+        sg, got = StreamedGather(), []
+        for i in range(3):
+            xi = xg + i
+            prev = sg.submit(_FakeNet()(xi[rank * per:(rank + 1) * per], w=0.5)[0])
+            if prev is not None:
+                got.append(prev.clone())
+        got.append(sg.flush().clone())
+        ok = ok and len(got) == 3 and all(torch.equal(got[i], _FakeNet()(xg + i, w=0.5)[0]) for i in range(3))
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
