@@ -1924,6 +1924,329 @@ int transpose_planes(const void* in_planes, int N, int pitch, int c0, int C, voi
 }
 
 // ------------------------------------------------------------------------------------------------------
+// VectorQuantizer.forward as ONE kernel (BASELINE configs[2]; /root/reference/basicsr/archs/vqgan_arch.py:33-70)
+//   d = |z|^2 + |e|^2 - 2 z.E^T ; argmin ; z_q = z + (E[idx] - z) ; loss ; perplexity ; mean_distance
+// on the caller's NCHW tensors.  One cluster of two CTAs owns 256 consecutive tokens of one image (128 per CTA) and ALL codes:
+//   phase 0  every thread reads its (token, 8-channel) items of z straight from NCHW (coalesced along the tokens), splits them
+//            into fp16 hi / lo and writes them into shared memory in the K-major 128B-swizzled layout the MMA descriptors read
+//            (the whole 128 x 256 A tile of the CTA stays resident: 128 KB), accumulates |z|^2;
+//   phase 1  warp 0 streams the prepared codebook planes ([B_hi ; B_lo] halves per CTA + its half of B_hi, as in the conv engine)
+//            through a 3-stage TMA ring, warp 1 of the leader issues tcgen05.mma.cta_group::2 (M = 256) into a double-buffered
+//            TMEM slot per 128-code chunk, warps 2..5 read the finished slot and keep (first minimum, index) per token row;
+//   phase 2  all threads gather E[idx], write the straight-through z_q in NCHW and the squared-error partial sums; the last CTA
+//            of the grid (ticket) turns the partial sums and the code histogram into the three statistics and clears them.
+// The [tokens, codes] distance matrix never leaves TMEM; no other kernel, copy or transpose runs.
+// ------------------------------------------------------------------------------------------------------
+struct VqParams {
+  const float* z; const float* codebook; const float* e2; const float* wscale_inv;
+  float* zq; int64_t* idx; float* stats;
+  double* part;          // [ctas][2]: squared error, sum of all distances
+  unsigned* hist;        // [K]: zero on entry, cleared again by the last CTA
+  unsigned* ticket;      // zero on entry
+  int N, D, HW, K, kblocks, nchunks;
+  float beta;
+};
+constexpr int VQ_THREADS = 256;
+constexpr int VQ_BX = 128 * 128, VQ_BY = 64 * 128, VQ_STAGE = VQ_BX + VQ_BY, VQ_STAGES = 3;
+constexpr int VQ_A_KB = 128 * 128;      // one 64-channel k-block of one plane: 128 token rows x 128 B
+
+__global__ void __launch_bounds__(VQ_THREADS, 1)
+vq_fused_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                const __grid_constant__ CUtensorMap tmB_half, const VqParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_hi = smem;                                   // [kblocks][128][128 B]
+  uint8_t* a_lo = smem + 4 * VQ_A_KB;
+  uint8_t* ring = smem + 8 * VQ_A_KB;                     // VQ_STAGES x (X | Y)
+  float* e2s = reinterpret_cast<float*>(ring + VQ_STAGES * VQ_STAGE);      // [K <= 1024]
+  float* z2p = e2s + 1024;                                // [2][128]
+  int* bidx = reinterpret_cast<int*>(z2p + 256);          // [128]
+  double* red = reinterpret_cast<double*>(bidx + 128);    // [8][2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red + 16);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + VQ_STAGES;
+  uint64_t* cfull = bars + 2 * VQ_STAGES;
+  uint64_t* cempty = cfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cempty + 2);
+  int* s_flags = reinterpret_cast<int*>(tmem_slot + 1);   // [0] abort seen, [1] last CTA
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cl = blockIdx.x >> 1;
+  const int per_img = p.HW / 256;
+  const int n = cl / per_img;
+  const int hw0 = (cl - n * per_img) * 256 + (int)rank * 128;
+  bool aborted = false;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < VQ_STAGES; ++s) { mbar_init(smem_u32(full + s), 1); mbar_init(smem_u32(empty + s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(cfull + a), 1); mbar_init(smem_u32(cempty + a), 8); }
+    s_flags[0] = 0; s_flags[1] = 0;
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_half) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  // ---- phase 0: z (NCHW) -> fp16 hi / lo operand tile in shared memory, |z|^2, |e|^2 table
+  {
+    const int tl = threadIdx.x & 127, gp = threadIdx.x >> 7;
+    const float* zb = p.z + (int64_t)n * p.D * p.HW + hw0 + tl;
+    const int groups = p.D >> 3;
+    float ss = 0.f;
+    for (int g = gp; g < groups; g += 4) {
+      float v[2][8];
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[u][j] = (g + 2 * u < groups) ? __ldg(zb + (int64_t)((g + 2 * u) * 8 + j) * p.HW) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int gg = g + 2 * u;
+        if (gg >= groups) break;
+        uint32_t hw_[4], lw_[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float y0 = v[u][2 * q], y1 = v[u][2 * q + 1];
+          ss = fmaf(y0, y0, ss); ss = fmaf(y1, y1, ss);
+          hw_[q] = pack_f16x2(y0, y1);
+          const float d0 = f16_minus_f32(hw_[q] & 0xffffu, y0), d1 = f16_minus_f32(hw_[q] >> 16, y1);
+          lw_[q] = pack_f16x2(d0, d1) ^ 0x80008000u;
+        }
+        const uint32_t off = (uint32_t)((gg >> 3) * VQ_A_KB + tl * 128 + ((((uint32_t)gg & 7u) ^ ((uint32_t)tl & 7u)) << 4));
+        sts128(smem_u32(a_hi) + off, make_uint4(hw_[0], hw_[1], hw_[2], hw_[3]));
+        sts128(smem_u32(a_lo) + off, make_uint4(lw_[0], lw_[1], lw_[2], lw_[3]));
+      }
+    }
+    z2p[gp * 128 + tl] = ss;
+    for (int k = threadIdx.x; k < p.K; k += VQ_THREADS) e2s[k] = __ldg(p.e2 + k);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes of the A tile -> tensor core
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                               // both CTAs: A tiles written, barriers initialised, TMEM allocated
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // ---- phase 1
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int ch = 0; ch < p.nchunks; ++ch)
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        mbar_wait<200>(smem_u32(empty + stage), phase ^ 1, aborted); if (aborted) goto role_done;
+        if (elect_one()) {
+          const uint32_t sb = smem_u32(ring + stage * VQ_STAGE);
+          if (rank == 0) mbar_expect_tx(smem_u32(full + stage), (uint32_t)(2 * VQ_STAGE));
+          const uint32_t fb = map_to_cta(smem_u32(full + stage), 0u);
+          tma_load_3d_pair(sb, rank == 0 ? &tmB_hi : &tmB_lo, fb, kb * 64, ch * 128, 0);
+          tma_load_3d_pair(sb + VQ_BX, &tmB_half, fb, kb * 64, ch * 128 + (int)rank * 64, 0);
+        }
+        __syncwarp();
+        if (++stage == VQ_STAGES) { stage = 0; phase ^= 1; }
+      }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      constexpr uint32_t pdesc2 = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      constexpr uint32_t pdesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      int stage = 0, slot = 0;
+      uint32_t phase = 0, slot_phase = 0;
+      for (int ch = 0; ch < p.nchunks; ++ch) {
+        mbar_wait_cl(smem_u32(cempty + slot), slot_phase ^ 1, aborted); if (aborted) goto role_done;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait_cl(smem_u32(full + stage), phase, aborted); if (aborted) goto role_done;
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t d_tmem = tmem_base + (uint32_t)(slot * 256);
+            const uint32_t ah = desc_lo(smem_u32(a_hi) + kb * VQ_A_KB), al = desc_lo(smem_u32(a_lo) + kb * VQ_A_KB);
+            const uint32_t sb = smem_u32(ring + stage * VQ_STAGE);
+            const uint32_t bx = desc_lo(sb), by = desc_lo(sb + VQ_BX);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              tc_mma_f16_pair_w(d_tmem, ah + 2 * k, DESC_HI_SW128, bx + 2 * k, DESC_HI_SW128, pdesc2, (kb > 0 || k > 0) ? 1u : 0u);
+              tc_mma_f16_pair_w(d_tmem + 128, al + 2 * k, DESC_HI_SW128, by + 2 * k, DESC_HI_SW128, pdesc, 1u);
+            }
+            tc_commit_pair(smem_u32(empty + stage), (uint16_t)3);
+            if (kb == p.kblocks - 1) tc_commit_pair(smem_u32(cfull + slot), (uint16_t)3);
+          }
+          __syncwarp();
+          if (++stage == VQ_STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++slot == 2) { slot = 0; slot_phase ^= 1; }
+      }
+    }
+  } else if (warp < 6) {
+    const int lg = warp & 3;                                  // TMEM lane quadrant of this warp
+    const int tl = lg * 32 + lane;                            // token row of the tile
+    const float z2 = z2p[tl] + z2p[128 + tl];
+    const float wsi = __ldg(p.wscale_inv);
+    const uint32_t cempty_leader = map_to_cta(smem_u32(cempty), 0u);
+    float best = INFINITY, dsum = 0.f;
+    int bi = 0, slot = 0;
+    uint32_t slot_phase = 0;
+    for (int ch = 0; ch < p.nchunks; ++ch) {
+      mbar_wait<100>(smem_u32(cfull + slot), slot_phase, aborted); if (aborted) goto role_done;
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(slot * 256);
+#pragma unroll
+      for (int c0 = 0; c0 < 128; c0 += 16) {
+        uint32_t r0[16], r1[16];
+        tmem_ld16(taddr + c0, r0);
+        tmem_ld16(taddr + 128 + c0, r1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int code = ch * 128 + c0 + j;
+          const float dot = (__uint_as_float(r0[j]) + __uint_as_float(r1[j])) * wsi;
+          const float d = (z2 + e2s[code]) - 2.f * dot;       // the reference's operation order (vqgan_arch.py:40-41)
+          dsum += d;
+          if (d < best) { best = d; bi = code; }              // ascending codes, strict <: first minimum = torch.argmin
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(cempty_leader + (uint32_t)(slot * 8));
+      if (++slot == 2) { slot = 0; slot_phase ^= 1; }
+    }
+    bi = min(max(bi, 0), p.K - 1);
+    bidx[tl] = bi;
+    const int64_t tok = (int64_t)n * p.HW + hw0 + tl;
+    p.idx[tok] = (int64_t)bi;
+    atomicAdd(p.hist + bi, 1u);
+    double ds = (double)dsum;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ds += __shfl_xor_sync(0xffffffffu, ds, o);
+    if (lane == 0) red[(warp - 2) * 2 + 1] = ds;
+  }
+role_done:
+  if (aborted && lane == 0) s_flags[0] = 1;
+  tc_fence_before();
+  __syncthreads();
+  // ---- phase 2: straight-through z_q (NCHW) and the squared error, all 256 threads
+  if (!s_flags[0]) {
+    const int tl = threadIdx.x & 127, gp = threadIdx.x >> 7;
+    const int my = bidx[tl];
+    const float* zb = p.z + (int64_t)n * p.D * p.HW + hw0 + tl;
+    float* qb = p.zq + (int64_t)n * p.D * p.HW + hw0 + tl;
+    const float* er = p.codebook + (int64_t)my * p.D;
+    double se = 0.0;
+    for (int g = gp; g < (p.D >> 3); g += 2) {
+      const float4 e0 = __ldg(reinterpret_cast<const float4*>(er + g * 8)), e1 = __ldg(reinterpret_cast<const float4*>(er + g * 8 + 4));
+      const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+      float zz[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) zz[j] = __ldg(zb + (int64_t)(g * 8 + j) * p.HW);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float diff = ev[j] - zz[j];
+        se += (double)(diff * diff);
+        qb[(int64_t)(g * 8 + j) * p.HW] = zz[j] + diff;       // z + (z_q - z), vqgan_arch.py:57
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+    __shared__ double se_w[8];
+    if (lane == 0) se_w[warp] = se;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 0.0, b = 0.0;
+      for (int i = 0; i < 8; ++i) a += se_w[i];
+      for (int i = 0; i < 4; ++i) b += red[i * 2 + 1];
+      p.part[(int64_t)blockIdx.x * 2] = a;
+      p.part[(int64_t)blockIdx.x * 2 + 1] = b;
+      __threadfence();
+      s_flags[1] = (atomicAdd(p.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_flags[1]) {
+      // last CTA of the grid: statistics (vqgan_arch.py:42,55,60-61) from the partial sums and the histogram, then clear both
+      __threadfence();
+      __shared__ double sred[3][VQ_THREADS];
+      const int T = p.N * p.HW;
+      double ent = 0.0, s_se = 0.0, s_d = 0.0;
+      for (int k = threadIdx.x; k < p.K; k += VQ_THREADS) {
+        const float em = (float)__ldcg(p.hist + k) / (float)T;
+        ent += (double)(em * logf(em + 1e-10f));
+        p.hist[k] = 0u;
+      }
+      for (int i = threadIdx.x; i < (int)gridDim.x; i += VQ_THREADS) { s_se += __ldcg(p.part + 2 * i); s_d += __ldcg(p.part + 2 * i + 1); }
+      sred[0][threadIdx.x] = ent; sred[1][threadIdx.x] = s_se; sred[2][threadIdx.x] = s_d;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double e = 0.0, s2 = 0.0, d2 = 0.0;
+        for (int i = 0; i < VQ_THREADS; ++i) { e += sred[0][i]; s2 += sred[1][i]; d2 += sred[2][i]; }      // fixed order
+        const float mse = (float)(s2 / ((double)T * p.D));
+        p.stats[0] = mse + p.beta * mse;
+        p.stats[1] = expf(-(float)e);
+        p.stats[2] = (float)(d2 / ((double)T * p.K));
+        p.stats[3] = 0.f;
+        *p.ticket = 0u;
+      }
+    }
+  }
+  if (aborted) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < 400000) {}
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+bool vq_fused_supported(int N, int D, int HW, int K) {
+  return halo_enabled() && pair_enabled() && N >= 0 && D % 64 == 0 && D >= 64 && D <= 256 && HW % 256 == 0 && K % 128 == 0 && K <= 1024;
+}
+
+int vq_fused(const float* z, const float* codebook, const void* whi, const void* wlo, const float* wscale_inv, const float* e2,
+             unsigned* hist, unsigned* ticket, double* part, int N, int D, int HW, int K, float beta, float* zq, int64_t* idx,
+             float* stats, cudaStream_t st) {
+  CFB_REQUIRE(vq_fused_supported(N, D, HW, K), "vq_fused: shape not supported");
+  if (N == 0) return 0;
+  TcMaps mp;
+  {
+    const uint64_t dims[3] = {(uint64_t)D, (uint64_t)K, 1};
+    const uint64_t str[2] = {(uint64_t)D * 2, (uint64_t)K * D * 2};
+    const uint32_t box[3] = {64, 128, 1}, hbox[3] = {64, 64, 1};
+    CFB_CHECK(make_map(&mp.b_hi, whi, 3, dims, str, box));
+    CFB_CHECK(make_map(&mp.b_lo, wlo, 3, dims, str, box));
+    CFB_CHECK(make_map(&mp.b_half, whi, 3, dims, str, hbox));
+  }
+  VqParams p;
+  p.z = z; p.codebook = codebook; p.e2 = e2; p.wscale_inv = wscale_inv; p.zq = zq; p.idx = idx; p.stats = stats; p.part = part;
+  p.hist = hist; p.ticket = ticket; p.N = N; p.D = D; p.HW = HW; p.K = K; p.kblocks = D / 64; p.nchunks = K / 128; p.beta = beta;
+  constexpr int SMEM = 8 * VQ_A_KB + VQ_STAGES * VQ_STAGE + 1024 * 4 + 256 * 4 + 128 * 4 + 16 * 8 + 16 * 8 + 64 + 1024;
+  static_assert(SMEM <= 232448, "shared memory budget");
+  static std::atomic<uint64_t> attr_done{0};
+  int dev = 0;
+  CFB_CUDA(cudaGetDevice(&dev));
+  const uint64_t bit = 1ull << (dev & 63);
+  if (!(attr_done.load(std::memory_order_acquire) & bit)) {
+    CFB_CUDA(cudaFuncSetAttribute(vq_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr_done.fetch_or(bit, std::memory_order_release);
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * N * (HW / 256)));
+  cfg.blockDim = dim3(VQ_THREADS);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  CFB_CUDA(cudaLaunchKernelEx(&cfg, vq_fused_kernel, mp.b_hi, mp.b_lo, mp.b_half, p));
+  count_launch();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
 // Diagnostics: which shared-memory rows does a K-major SWIZZLE_128B UMMA descriptor read when its start address is
 // NOT 1024-byte aligned (row-shifted views of one TMA-written tile) and how does the `base_offset` field enter?
 // D = A_view * I, so D[m][n] reveals the (row, 16-byte chunk) of A that reached the tensor core.

@@ -36,6 +36,11 @@ int bmm_tc(const BmmArgs& g, int sm_count, cudaStream_t st);
 int concat_planes(const float* a, const float* b, void* planes, int64_t pixels, int Ca, int Cb, cudaStream_t st);
 int softmax256_planes(const float* scores, void* planes, int64_t rows, cudaStream_t st);
 int transpose_planes(const void* in_planes, int N, int pitch, int c0, int C, void* out_planes, cudaStream_t st);
+// VectorQuantizer.forward as one kernel on NCHW tensors (see conv_tc.cu); hist / ticket: zero on entry, left zero
+bool vq_fused_supported(int N, int D, int HW, int K);
+int vq_fused(const float* z, const float* codebook, const void* whi, const void* wlo, const float* wscale_inv, const float* e2,
+             unsigned* hist, unsigned* ticket, double* part, int N, int D, int HW, int K, float beta, float* zq, int64_t* idx,
+             float* stats, cudaStream_t st);
 // diagnostics (tools/umma_probe.py): row-shifted SWIZZLE_128B descriptor views
 int umma_probe(const void* a_f16, int rowsA, const void* b_f16, const int* cfg_dev, int ncfg, float* out, cudaStream_t st);
 int umma_pair(int N, int reps, float* vals_dev, long long* info_dev, int ctas, cudaStream_t st);

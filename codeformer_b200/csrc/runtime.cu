@@ -1997,7 +1997,8 @@ int32_t cfb_vq_fast_supported(int32_t batch, int32_t h, int32_t w, int32_t dim, 
   return (codes % 128 == 0 && dim % 64 == 0 && dim <= 352 && (h * w) % 128 == 0 && batch >= 0) ? 1 : 0;
 }
 int64_t cfb_vq_prepared_bytes(int32_t codes, int32_t dim) {
-  return (int64_t)(2 * align256((size_t)codes * dim * 2) + 256 + align256((size_t)codes * 4));
+  // split codebook (hi, lo), weight scale, |e|^2, and the self-cleaning code histogram + ticket of the one-kernel path
+  return (int64_t)(2 * align256((size_t)codes * dim * 2) + 256 + 2 * align256((size_t)codes * 4) + 256);
 }
 int cfb_vq_prepare(const float* codebook, int32_t codes, int32_t dim, void* prepared, int64_t prepared_bytes, void* stream) {
   API_BEGIN
@@ -2010,6 +2011,7 @@ int cfb_vq_prepare(const float* codebook, int32_t codes, int32_t dim, void* prep
   float* e2 = (float*)p;
   CFB_CHECK(cfb::tc_split_weights(codebook, whi, wlo, codes, dim, 1, wsc, st));
   CFB_CHECK(cfb::vq_e2(codebook, e2, codes, dim, st));
+  CFB_CUDA(cudaMemsetAsync((char*)e2 + align256((size_t)codes * 4), 0, align256((size_t)codes * 4) + 256, st));   // histogram + ticket
   return 0;
   API_END(1)
 }
@@ -2038,6 +2040,14 @@ int cfb_vq_nearest_fast(const float* z, const float* codebook, const void* prepa
   const float* wsc = (const float*)q; q += 256;
   const float* e2 = (const float*)q;
   char* p = (char*)(((uintptr_t)workspace + 1023) / 1024 * 1024);
+  if (cfb::vq_fused_supported(batch, dim, HW, codes) && !(getenv("CFB_VQ_FUSED") && atoi(getenv("CFB_VQ_FUSED")) == 0)) {
+    // ONE kernel (conv_tc.cu: vq_fused_kernel): histogram / ticket live in the prepared buffer (zero between calls)
+    unsigned* fh = (unsigned*)((char*)e2 + align256((size_t)codes * 4));
+    unsigned* ticket = (unsigned*)((char*)fh + align256((size_t)codes * 4));
+    CFB_CHECK(cfb::vq_fused(z, codebook, whi, wlo, wsc + 1, e2, fh, ticket, (double*)p, batch, dim, HW, codes, beta, z_q, idx, stats, st));
+    if (min_encodings) CFB_CHECK(cfb::onehot_from_idx(idx, min_encodings, (int)T, codes, st));
+    return 0;
+  }
   void* planes = p; p += 2 * (((size_t)T * dim * 2 + 1023) / 1024 * 1024);
   float* z2 = (float*)p; p += align256((size_t)T * 4);
   const int ncand = 2 * (codes / 128);

@@ -215,10 +215,13 @@ def test_vq_edge_cases():
     assert zq.shape == (0, 256, 16, 16) and st['min_encoding_indices'].shape == (0, 1)
 
 
-def test_vq_fused_path_equals_the_unfused_one():
-    """The 4-launch path (argmin in the GEMM epilogue, NCHW in/out, prepared codebook, CUDA-graph replay) against the round-1
-    path (stored dot products) on the config-3 inputs: same indices, z_q and statistics; a changed embedding is picked up."""
+@pytest.mark.parametrize('one_kernel', [True, False])
+def test_vq_fused_path_equals_the_unfused_one(one_kernel, monkeypatch):
+    """The fused paths -- ONE kernel (z tile in shared memory, argmin out of TMEM, statistics by the last CTA) and the 4-launch
+    variant (argmin in the GEMM epilogue) -- with the prepared codebook and CUDA-graph replay, against the round-1 path (stored
+    dot products) on the config-3 inputs: same indices, z_q and statistics; a changed embedding is picked up."""
     import codeformer_b200 as cb
+    monkeypatch.setenv('CFB_VQ_FUSED', '1' if one_kernel else '0')
     lib = _lib.load()
     E, z = vq_micro_inputs('B')
     vq = cb.VectorQuantizer(1024, 256, 0.25)
