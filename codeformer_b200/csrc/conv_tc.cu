@@ -1959,8 +1959,8 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constan
   uint8_t* a_lo = smem + 4 * VQ_A_KB;
   uint8_t* ring = smem + 8 * VQ_A_KB;                     // VQ_STAGES x (X | Y)
   float* e2s = reinterpret_cast<float*>(ring + VQ_STAGES * VQ_STAGE);      // [K <= 1024]
-  float* z2p = e2s + 1024;                                // [2][128]
-  int* bidx = reinterpret_cast<int*>(z2p + 256);          // [128]
+  float* z2p = e2s + 1024;                                // [4 k-blocks][128 tokens]
+  int* bidx = reinterpret_cast<int*>(z2p + 512);          // [128]
   double* red = reinterpret_cast<double*>(bidx + 128);    // [8][2]
   uint64_t* bars = reinterpret_cast<uint64_t*>(red + 16);
   uint64_t* full = bars;
@@ -1993,37 +1993,58 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constan
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   // ---- phase 0: z (NCHW) -> fp16 hi / lo operand tile in shared memory, |z|^2, |e|^2 table
+  // One warp item = 16 tokens x one 64-channel k-block: lane (a = lane>>3, b = lane&7) reads 8 channels (b*8..) of 4 consecutive
+  // tokens (a) with 16-byte loads along the token axis (64 B segments: every sector fully used) and writes, per token, the
+  // 16-byte chunk b of that token's row -- 8 lanes cover a 128 B row, 4 rows per instruction: conflict-free STS.128.
   {
-    const int tl = threadIdx.x & 127, gp = threadIdx.x >> 7;
-    const float* zb = p.z + (int64_t)n * p.D * p.HW + hw0 + tl;
-    const int groups = p.D >> 3;
-    float ss = 0.f;
-    for (int g = gp; g < groups; g += 4) {
-      float v[2][8];
-#pragma unroll
-      for (int u = 0; u < 2; ++u)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[u][j] = (g + 2 * u < groups) ? __ldg(zb + (int64_t)((g + 2 * u) * 8 + j) * p.HW) : 0.f;
+    const int la = lane >> 3, lb = lane & 7;
+    for (int k = threadIdx.x; k < p.K; k += VQ_THREADS) e2s[k] = __ldg(p.e2 + k);
+    const int items = 8 * p.kblocks;                      // 8 groups of 16 tokens x kblocks
+    const float* zn = p.z + (int64_t)n * p.D * p.HW + hw0;
+    for (int it0 = warp; it0 < items; it0 += 16) {        // two items in flight per warp
+      float4 v[2][8];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const int gg = g + 2 * u;
-        if (gg >= groups) break;
-        uint32_t hw_[4], lw_[4];
+        const int item = it0 + 8 * u;
+        if (item < items) {
+          const int kb = item % p.kblocks, t4 = ((item / p.kblocks) * 4 + la) * 4;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float y0 = v[u][2 * q], y1 = v[u][2 * q + 1];
-          ss = fmaf(y0, y0, ss); ss = fmaf(y1, y1, ss);
-          hw_[q] = pack_f16x2(y0, y1);
-          const float d0 = f16_minus_f32(hw_[q] & 0xffffu, y0), d1 = f16_minus_f32(hw_[q] >> 16, y1);
-          lw_[q] = pack_f16x2(d0, d1) ^ 0x80008000u;
+          for (int j = 0; j < 8; ++j)
+            v[u][j] = __ldg(reinterpret_cast<const float4*>(zn + (int64_t)(kb * 64 + lb * 8 + j) * p.HW + t4));
         }
-        const uint32_t off = (uint32_t)((gg >> 3) * VQ_A_KB + tl * 128 + ((((uint32_t)gg & 7u) ^ ((uint32_t)tl & 7u)) << 4));
-        sts128(smem_u32(a_hi) + off, make_uint4(hw_[0], hw_[1], hw_[2], hw_[3]));
-        sts128(smem_u32(a_lo) + off, make_uint4(lw_[0], lw_[1], lw_[2], lw_[3]));
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int item = it0 + 8 * u;
+        if (item < items) {
+          const int kb = item % p.kblocks, t4 = ((item / p.kblocks) * 4 + la) * 4;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int tl = t4 + k;
+            float y[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y[j] = k == 0 ? v[u][j].x : (k == 1 ? v[u][j].y : (k == 2 ? v[u][j].z : v[u][j].w));
+            uint32_t hw_[4], lw_[4];
+            float ss = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float y0 = y[2 * q], y1 = y[2 * q + 1];
+              ss = fmaf(y0, y0, ss); ss = fmaf(y1, y1, ss);
+              hw_[q] = pack_f16x2(y0, y1);
+              const float d0 = f16_minus_f32(hw_[q] & 0xffffu, y0), d1 = f16_minus_f32(hw_[q] >> 16, y1);
+              lw_[q] = pack_f16x2(d0, d1) ^ 0x80008000u;
+            }
+            const uint32_t off = (uint32_t)(kb * VQ_A_KB + tl * 128 + ((((uint32_t)lb) ^ ((uint32_t)tl & 7u)) << 4));
+            sts128(smem_u32(a_hi) + off, make_uint4(hw_[0], hw_[1], hw_[2], hw_[3]));
+            sts128(smem_u32(a_lo) + off, make_uint4(lw_[0], lw_[1], lw_[2], lw_[3]));
+            ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+            ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+            ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+            if (lb == 0) z2p[kb * 128 + tl] = ss;           // one writer per (k-block, token)
+          }
+        }
       }
     }
-    z2p[gp * 128 + tl] = ss;
-    for (int k = threadIdx.x; k < p.K; k += VQ_THREADS) e2s[k] = __ldg(p.e2 + k);
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes of the A tile -> tensor core
   tc_fence_before();
@@ -2082,7 +2103,8 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constan
   } else if (warp < 6) {
     const int lg = warp & 3;                                  // TMEM lane quadrant of this warp
     const int tl = lg * 32 + lane;                            // token row of the tile
-    const float z2 = z2p[tl] + z2p[128 + tl];
+    float z2 = 0.f;
+    for (int kb = 0; kb < p.kblocks; ++kb) z2 += z2p[kb * 128 + tl];
     const float wsi = __ldg(p.wscale_inv);
     const uint32_t cempty_leader = map_to_cta(smem_u32(cempty), 0u);
     float best = INFINITY, dsum = 0.f;
@@ -2128,23 +2150,34 @@ role_done:
   __syncthreads();
   // ---- phase 2: straight-through z_q (NCHW) and the squared error, all 256 threads
   if (!s_flags[0]) {
-    const int tl = threadIdx.x & 127, gp = threadIdx.x >> 7;
-    const int my = bidx[tl];
-    const float* zb = p.z + (int64_t)n * p.D * p.HW + hw0 + tl;
-    float* qb = p.zq + (int64_t)n * p.D * p.HW + hw0 + tl;
-    const float* er = p.codebook + (int64_t)my * p.D;
+    // same item shape as phase 0: (4 consecutive tokens) x (8 channels); 16-byte loads / stores along the token axis
+    const int la = lane >> 3, lb = lane & 7;
+    const int items = 8 * p.kblocks;
+    const float* zn = p.z + (int64_t)n * p.D * p.HW + hw0;
+    float* qn = p.zq + (int64_t)n * p.D * p.HW + hw0;
     double se = 0.0;
-    for (int g = gp; g < (p.D >> 3); g += 2) {
-      const float4 e0 = __ldg(reinterpret_cast<const float4*>(er + g * 8)), e1 = __ldg(reinterpret_cast<const float4*>(er + g * 8 + 4));
-      const float ev[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-      float zz[8];
+    for (int item = warp; item < items; item += 8) {
+      const int kb = item % p.kblocks, t4 = ((item / p.kblocks) * 4 + la) * 4;
+      const int c0 = kb * 64 + lb * 8;
+      float4 zz[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) zz[j] = __ldg(zb + (int64_t)(g * 8 + j) * p.HW);
+      for (int j = 0; j < 8; ++j) zz[j] = __ldg(reinterpret_cast<const float4*>(zn + (int64_t)(c0 + j) * p.HW + t4));
+      float ev[4][8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float* er = p.codebook + (int64_t)bidx[t4 + k] * p.D + c0;
+        const float4 e0 = __ldg(reinterpret_cast<const float4*>(er)), e1 = __ldg(reinterpret_cast<const float4*>(er + 4));
+        ev[k][0] = e0.x; ev[k][1] = e0.y; ev[k][2] = e0.z; ev[k][3] = e0.w; ev[k][4] = e1.x; ev[k][5] = e1.y; ev[k][6] = e1.z; ev[k][7] = e1.w;
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float diff = ev[j] - zz[j];
-        se += (double)(diff * diff);
-        qb[(int64_t)(g * 8 + j) * p.HW] = zz[j] + diff;       // z + (z_q - z), vqgan_arch.py:57
+        float4 o;
+        float diff;
+        diff = ev[0][j] - zz[j].x; se += (double)(diff * diff); o.x = zz[j].x + diff;      // z + (z_q - z), vqgan_arch.py:57
+        diff = ev[1][j] - zz[j].y; se += (double)(diff * diff); o.y = zz[j].y + diff;
+        diff = ev[2][j] - zz[j].z; se += (double)(diff * diff); o.z = zz[j].z + diff;
+        diff = ev[3][j] - zz[j].w; se += (double)(diff * diff); o.w = zz[j].w + diff;
+        *reinterpret_cast<float4*>(qn + (int64_t)(c0 + j) * p.HW + t4) = o;
       }
     }
 #pragma unroll
@@ -2222,7 +2255,7 @@ int vq_fused(const float* z, const float* codebook, const void* whi, const void*
   VqParams p;
   p.z = z; p.codebook = codebook; p.e2 = e2; p.wscale_inv = wscale_inv; p.zq = zq; p.idx = idx; p.stats = stats; p.part = part;
   p.hist = hist; p.ticket = ticket; p.N = N; p.D = D; p.HW = HW; p.K = K; p.kblocks = D / 64; p.nchunks = K / 128; p.beta = beta;
-  constexpr int SMEM = 8 * VQ_A_KB + VQ_STAGES * VQ_STAGE + 1024 * 4 + 256 * 4 + 128 * 4 + 16 * 8 + 16 * 8 + 64 + 1024;
+  constexpr int SMEM = 8 * VQ_A_KB + VQ_STAGES * VQ_STAGE + 1024 * 4 + 512 * 4 + 128 * 4 + 16 * 8 + 16 * 8 + 64 + 1024;
   static_assert(SMEM <= 232448, "shared memory budget");
   static std::atomic<uint64_t> attr_done{0};
   int dev = 0;
