@@ -1946,7 +1946,7 @@ struct VqParams {
   int N, D, HW, K, kblocks, nchunks;
   float beta;
 };
-constexpr int VQ_THREADS = 256;
+constexpr int VQ_THREADS = 512;      // 16 warps: 0 TMA, 1 MMA, 2..5 epilogue; all 16 move z / z_q in phases 0 and 2
 constexpr int VQ_BX = 128 * 128, VQ_BY = 64 * 128, VQ_STAGE = VQ_BX + VQ_BY, VQ_STAGES = 3;
 constexpr int VQ_A_KB = 128 * 128;      // one 64-channel k-block of one plane: 128 token rows x 128 B
 
@@ -2001,11 +2001,11 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constan
     for (int k = threadIdx.x; k < p.K; k += VQ_THREADS) e2s[k] = __ldg(p.e2 + k);
     const int items = 8 * p.kblocks;                      // 8 groups of 16 tokens x kblocks
     const float* zn = p.z + (int64_t)n * p.D * p.HW + hw0;
-    for (int it0 = warp; it0 < items; it0 += 16) {        // two items in flight per warp
+    for (int it0 = warp; it0 < items; it0 += 32) {        // two items in flight per warp (all of them at D = 256)
       float4 v[2][8];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const int item = it0 + 8 * u;
+        const int item = it0 + 16 * u;
         if (item < items) {
           const int kb = item % p.kblocks, t4 = ((item / p.kblocks) * 4 + la) * 4;
 #pragma unroll
@@ -2015,7 +2015,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constan
       }
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const int item = it0 + 8 * u;
+        const int item = it0 + 16 * u;
         if (item < items) {
           const int kb = item % p.kblocks, t4 = ((item / p.kblocks) * 4 + la) * 4;
 #pragma unroll
@@ -2156,7 +2156,7 @@ role_done:
     const float* zn = p.z + (int64_t)n * p.D * p.HW + hw0;
     float* qn = p.zq + (int64_t)n * p.D * p.HW + hw0;
     double se = 0.0;
-    for (int item = warp; item < items; item += 8) {
+    for (int item = warp; item < items; item += VQ_THREADS / 32) {
       const int kb = item % p.kblocks, t4 = ((item / p.kblocks) * 4 + la) * 4;
       const int c0 = kb * 64 + lb * 8;
       float4 zz[8];
@@ -2182,12 +2182,12 @@ role_done:
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
-    __shared__ double se_w[8];
+    __shared__ double se_w[VQ_THREADS / 32];
     if (lane == 0) se_w[warp] = se;
     __syncthreads();
     if (threadIdx.x == 0) {
       double a = 0.0, b = 0.0;
-      for (int i = 0; i < 8; ++i) a += se_w[i];
+      for (int i = 0; i < VQ_THREADS / 32; ++i) a += se_w[i];
       for (int i = 0; i < 4; ++i) b += red[i * 2 + 1];
       p.part[(int64_t)blockIdx.x * 2] = a;
       p.part[(int64_t)blockIdx.x * 2 + 1] = b;
