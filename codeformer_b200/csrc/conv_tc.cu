@@ -1945,6 +1945,7 @@ struct VqParams {
   unsigned* ticket;      // zero on entry
   int N, D, HW, K, kblocks, nchunks;
   float beta;
+  long long* dbg;        // optional [ctas][6] clock64 stamps of the phase boundaries (tools/gpu_r2_vq.sh)
 };
 constexpr int VQ_THREADS = 512;      // 16 warps: 0 TMA, 1 MMA, 2..5 epilogue; all 16 move z / z_q in phases 0 and 2
 constexpr int VQ_BX = 128 * 128, VQ_BY = 64 * 128, VQ_STAGE = VQ_BX + VQ_BY, VQ_STAGES = 3;
@@ -1978,6 +1979,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constan
   const int n = cl / per_img;
   const int hw0 = (cl - n * per_img) * 256 + (int)rank * 128;
   bool aborted = false;
+  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 6 + 0] = clock64();
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < VQ_STAGES; ++s) { mbar_init(smem_u32(full + s), 1); mbar_init(smem_u32(empty + s), 1); }
@@ -2052,12 +2054,14 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constan
   cluster_sync_all();                                               // both CTAs: A tiles written, barriers initialised, TMEM allocated
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 6 + 1] = clock64();
 
   // ---- phase 1
   if (warp == 0) {
     int stage = 0;
     uint32_t phase = 0;
-    for (int ch = 0; ch < p.nchunks; ++ch)
+    for (int c = 0; c < p.nchunks; ++c) {
+      const int ch = (c + cl) % p.nchunks;        // clusters walk the codebook in rotated order: no L2 line is hit by all at once
       for (int kb = 0; kb < p.kblocks; ++kb) {
         mbar_wait<200>(smem_u32(empty + stage), phase ^ 1, aborted); if (aborted) goto role_done;
         if (elect_one()) {
@@ -2070,6 +2074,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constan
         __syncwarp();
         if (++stage == VQ_STAGES) { stage = 0; phase ^= 1; }
       }
+    }
   } else if (warp == 1) {
     if (rank == 0) {
       constexpr uint32_t pdesc2 = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
@@ -2108,12 +2113,15 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constan
     const float wsi = __ldg(p.wscale_inv);
     const uint32_t cempty_leader = map_to_cta(smem_u32(cempty), 0u);
     float best = INFINITY, dsum = 0.f;
-    int bi = 0, slot = 0;
+    int bi = 0x7fffffff, slot = 0;
     uint32_t slot_phase = 0;
-    for (int ch = 0; ch < p.nchunks; ++ch) {
+    for (int c = 0; c < p.nchunks; ++c) {
+      const int ch = (c + cl) % p.nchunks;        // same rotated order as the TMA producer
       mbar_wait<100>(smem_u32(cfull + slot), slot_phase, aborted); if (aborted) goto role_done;
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(slot * 256);
+      float cbest = INFINITY;
+      int cbi = 0;
 #pragma unroll
       for (int c0 = 0; c0 < 128; c0 += 16) {
         uint32_t r0[16], r1[16];
@@ -2126,9 +2134,10 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constan
           const float dot = (__uint_as_float(r0[j]) + __uint_as_float(r1[j])) * wsi;
           const float d = (z2 + e2s[code]) - 2.f * dot;       // the reference's operation order (vqgan_arch.py:40-41)
           dsum += d;
-          if (d < best) { best = d; bi = code; }              // ascending codes, strict <: first minimum = torch.argmin
+          if (d < cbest) { cbest = d; cbi = code; }           // ascending codes inside the chunk, strict <
         }
       }
+      if (cbest < best || (cbest == best && cbi < bi)) { best = cbest; bi = cbi; }   // lowest index on ties = torch.argmin, any chunk order
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(cempty_leader + (uint32_t)(slot * 8));
@@ -2146,6 +2155,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constan
   }
 role_done:
   if (aborted && lane == 0) s_flags[0] = 1;
+  if (p.dbg && lane == 0 && warp < 6) p.dbg[blockIdx.x * 6 + 2 + (warp >= 2 ? 1 : 0)] = clock64();     // [2] producers, [3] epilogue done
   tc_fence_before();
   __syncthreads();
   // ---- phase 2: straight-through z_q (NCHW) and the squared error, all 256 threads
@@ -2221,6 +2231,7 @@ role_done:
       }
     }
   }
+  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 6 + 4] = clock64();
   if (aborted) {
     const long long t0 = clock64();
     while (clock64() - t0 < 400000) {}
@@ -2232,6 +2243,7 @@ role_done:
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
+  if (p.dbg && threadIdx.x == 32) p.dbg[blockIdx.x * 6 + 5] = clock64();
 }
 
 bool vq_fused_supported(int N, int D, int HW, int K) {
@@ -2240,7 +2252,7 @@ bool vq_fused_supported(int N, int D, int HW, int K) {
 
 int vq_fused(const float* z, const float* codebook, const void* whi, const void* wlo, const float* wscale_inv, const float* e2,
              unsigned* hist, unsigned* ticket, double* part, int N, int D, int HW, int K, float beta, float* zq, int64_t* idx,
-             float* stats, cudaStream_t st) {
+             float* stats, cudaStream_t st, long long* dbg) {
   CFB_REQUIRE(vq_fused_supported(N, D, HW, K), "vq_fused: shape not supported");
   if (N == 0) return 0;
   TcMaps mp;
@@ -2255,6 +2267,7 @@ int vq_fused(const float* z, const float* codebook, const void* whi, const void*
   VqParams p;
   p.z = z; p.codebook = codebook; p.e2 = e2; p.wscale_inv = wscale_inv; p.zq = zq; p.idx = idx; p.stats = stats; p.part = part;
   p.hist = hist; p.ticket = ticket; p.N = N; p.D = D; p.HW = HW; p.K = K; p.kblocks = D / 64; p.nchunks = K / 128; p.beta = beta;
+  p.dbg = dbg;
   constexpr int SMEM = 8 * VQ_A_KB + VQ_STAGES * VQ_STAGE + 1024 * 4 + 512 * 4 + 128 * 4 + 16 * 8 + 16 * 8 + 64 + 1024;
   static_assert(SMEM <= 232448, "shared memory budget");
   static std::atomic<uint64_t> attr_done{0};

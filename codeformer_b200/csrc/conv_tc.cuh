@@ -40,7 +40,7 @@ int transpose_planes(const void* in_planes, int N, int pitch, int c0, int C, voi
 bool vq_fused_supported(int N, int D, int HW, int K);
 int vq_fused(const float* z, const float* codebook, const void* whi, const void* wlo, const float* wscale_inv, const float* e2,
              unsigned* hist, unsigned* ticket, double* part, int N, int D, int HW, int K, float beta, float* zq, int64_t* idx,
-             float* stats, cudaStream_t st);
+             float* stats, cudaStream_t st, long long* dbg = nullptr);
 // diagnostics (tools/umma_probe.py): row-shifted SWIZZLE_128B descriptor views
 int umma_probe(const void* a_f16, int rowsA, const void* b_f16, const int* cfg_dev, int ncfg, float* out, cudaStream_t st);
 int umma_pair(int N, int reps, float* vals_dev, long long* info_dev, int ctas, cudaStream_t st);

@@ -2044,7 +2044,9 @@ int cfb_vq_nearest_fast(const float* z, const float* codebook, const void* prepa
     // ONE kernel (conv_tc.cu: vq_fused_kernel): histogram / ticket live in the prepared buffer (zero between calls)
     unsigned* fh = (unsigned*)((char*)e2 + align256((size_t)codes * 4));
     unsigned* ticket = (unsigned*)((char*)fh + align256((size_t)codes * 4));
-    CFB_CHECK(cfb::vq_fused(z, codebook, whi, wlo, wsc + 1, e2, fh, ticket, (double*)p, batch, dim, HW, codes, beta, z_q, idx, stats, st));
+    // CFB_VQ_TIMING=1 (tools/gpu_r2_vq.sh): clock64 stamps of the phase boundaries per CTA, 4 KB into the workspace
+    long long* dbg = (getenv("CFB_VQ_TIMING") && atoi(getenv("CFB_VQ_TIMING"))) ? (long long*)(p + 4096) : nullptr;
+    CFB_CHECK(cfb::vq_fused(z, codebook, whi, wlo, wsc + 1, e2, fh, ticket, (double*)p, batch, dim, HW, codes, beta, z_q, idx, stats, st, dbg));
     if (min_encodings) CFB_CHECK(cfb::onehot_from_idx(idx, min_encodings, (int)T, codes, st));
     return 0;
   }

@@ -34,6 +34,16 @@ zq = torch.empty_like(z); idx = torch.empty((8192, 1), dtype=torch.int64, device
 ws = torch.empty(int(lib.cfb_vq_fast_workspace_bytes(32, 256, 256, 1024)), dtype=torch.uint8, device='cuda')
 call = lambda: _lib.check(lib.cfb_vq_nearest_fast(_lib.ptr(z), _lib.ptr(Ed), _lib.ptr(prep), 32, 16, 16, 256, 1024, 0.25, _lib.ptr(zq), _lib.ptr(idx), _lib.ptr(stats), None, _lib.ptr(ws), ws.numel(), st))
 print(f'C ABI, one kernel, back-to-back launches: {t(call):.1f} us per call')
+os.environ['CFB_VQ_TIMING'] = '1'
+call(); torch.cuda.synchronize()
+base = (ws.data_ptr() + 1023) // 1024 * 1024 - ws.data_ptr() + 4096
+stamps = ws[base:base + 64 * 6 * 8].view(torch.int64).view(64, 6).cpu().double()
+d = stamps - stamps[:, :1]
+print('phase stamps (cycles from CTA start; mean over 64 CTAs): after phase0+cluster sync %.0f, producers done %.0f, epilogue done %.0f, phase 2 done %.0f, end %.0f'
+      % tuple(d[:, k].mean().item() for k in (1, 2, 3, 4, 5)))
+print('  max over CTAs: %s' % [int(d[:, k].max().item()) for k in (1, 2, 3, 4, 5)])
+os.environ['CFB_VQ_TIMING'] = '0'
+
 gr = torch.cuda.CUDAGraph()
 call(); torch.cuda.synchronize()
 with torch.cuda.graph(gr):
