@@ -430,8 +430,18 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) { 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
+// Remote arrival after this warp's shared-memory writes (+ fence.proxy.async): CTA-scope release, as the data it publishes is
+// this CTA's own shared memory, read by this SM's tensor core -- the remote thread only issues the instruction.  The
+// .release.cluster form costs MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR, ~1000 cycles per arrival (profiles/round2_c64_xf_full).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+  asm volatile("mbarrier.arrive.release.cta.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// Arrival that orders nothing but itself: for barriers that only hand TMEM back to the MMA issuer.  The tcgen05.ld results are
+// already in registers (tcgen05.wait::ld) and tcgen05.fence::before_thread_sync orders the tensor-memory accesses; the default
+// .release form additionally drains every global store this thread still has in flight (MEMBAR + ERRBAR: 30 % of the epilogue
+// warps' time in profiles/round2_c64_xf_full, and it delays the accumulator slot the MMA warp is waiting for).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 // wait on a LOCAL barrier whose arrivals may come from the peer CTA (cluster-scope acquire)
 __device__ __forceinline__ void mbar_wait_cl(uint32_t bar, uint32_t parity, bool& aborted) {
@@ -1242,7 +1252,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if constexpr (PAIR) mbar_arrive_cluster(cempty_leader + (uint32_t)(slot * 8));
+          if constexpr (PAIR) mbar_arrive_cluster_relaxed(cempty_leader + (uint32_t)(slot * 8));
           else mbar_arrive(smem_u32(cempty + slot));
         }
         if (++slot == TC_SLOTS) { slot = 0; slot_phase ^= 1; }
@@ -2140,7 +2150,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tmB_hi, const __grid_constan
       if (cbest < best || (cbest == best && cbi < bi)) { best = cbest; bi = cbi; }   // lowest index on ties = torch.argmin, any chunk order
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(cempty_leader + (uint32_t)(slot * 8));
+      if (lane == 0) mbar_arrive_cluster_relaxed(cempty_leader + (uint32_t)(slot * 8));
       if (++slot == 2) { slot = 0; slot_phase ^= 1; }
     }
     bi = min(max(bi, 0), p.K - 1);
