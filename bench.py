@@ -271,16 +271,20 @@ def extra_configs(torch, cb, S, net, peaks, dev):
     vq.embedding.weight.data.copy_(E)
     vq = vq.to(dev)
     ms = _median_ms(torch, lambda: vq(z, return_min_encodings=False), 50)
-    vq.vq_graphs = False
-    ms_eager = _median_ms(torch, lambda: vq(z, return_min_encodings=False), 50)
-    vq.vq_graphs = True
+
+    def burst():                       # 20 calls back to back: the launches pipeline, the GPU time per call remains
+        for _ in range(20):
+            vq(z, return_min_encodings=False)
+    ms_pipe = _median_ms(torch, burst, 10) / 20
     nbytes = 17.9e6            # z 8.39 + E 1.05 + z_q 8.39 + idx 0.07 MB
-    out['vq_micro'] = {'ms': ms, 'ms_without_cuda_graph': ms_eager, 'launches_per_call': 1,
-                       'vectors_per_s': 8192 / (ms * 1e-3), 'algorithmic_bytes': nbytes,
-                       'roofline': {'bound': 'hbm', 'achieved': nbytes / (ms * 1e-3) / 1e9, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                                    'frac': nbytes / (ms * 1e-3) / 1e9 / peaks['hbm_gbs']},
-                       'what': 'BASELINE configs[2]: VectorQuantizer.forward, z [32,256,16,16] vs 1024 codes, NCHW in / NCHW out, '
-                               'median of 50 (indices bit-exact vs the reference golden in tests/test_gpu_kernels.py)'}
+    out['vq_micro'] = {'ms': ms, 'ms_pipelined': ms_pipe, 'launches_per_call': 1,
+                       'vectors_per_s': 8192 / (ms_pipe * 1e-3), 'algorithmic_bytes': nbytes,
+                       'roofline': {'bound': 'hbm', 'achieved': nbytes / (ms_pipe * 1e-3) / 1e9, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                                    'frac': nbytes / (ms_pipe * 1e-3) / 1e9 / peaks['hbm_gbs'], 'of': 'ms_pipelined'},
+                       'what': 'BASELINE configs[2]: VectorQuantizer.forward (one kernel), z [32,256,16,16] vs 1024 codes, NCHW in / NCHW '
+                               'out; ms = one call from a cold queue incl. the host side of the module call (median of 50), '
+                               'ms_pipelined = per call of 20 back-to-back calls (indices bit-exact vs the reference golden in '
+                               'tests/test_gpu_kernels.py)'}
     del vq, z
     vqae = cb.VQAutoEncoder(512, 64, [1, 2, 2, 4, 4, 8], 'nearest', 2, [16], 1024).to(dev).eval()
     vqae.load_state_dict(S.random_state_dict(S.vqae_spec(), 2), strict=True)

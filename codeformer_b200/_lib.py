@@ -84,6 +84,7 @@ SIGNATURES = {
     'cfb_check_async_status': (c_int, []),
     'cfb_debug_set_wait_limit': (c_int, [c_int64]),
     'cfb_debug_inject_fault': (c_int, [c_int32]),
+    'cfb_debug_set_stamps': (c_int, [_P]),
     'cfb_nchw_to_nhwc': (c_int, [_P, _P, c_int32, c_int32, c_int32, _P]),
     'cfb_nhwc_to_nchw': (c_int, [_P, _P, c_int32, c_int32, c_int32, _P]),
 }
@@ -106,8 +107,13 @@ def load():
         except Exception as e:  # noqa: BLE001
             raise RuntimeError(f'{LIB_PATH} is missing and could not be built with nvcc ({e}); there is no CPU or '
                                'PyTorch fallback for this path -- run `python -m codeformer_b200.build`') from e
-    lib = ctypes.CDLL(LIB_PATH)
+    # CFB_LIB: load another build of the SAME library (A/B timing of two kernel versions on one box, tools/gpu_ab_lib.sh);
+    # only there may a diagnostics entry point (cfb_debug_*) be absent from an older build
+    override = os.environ.get('CFB_LIB')
+    lib = ctypes.CDLL(override if override else LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
+        if override and name.startswith('cfb_debug_') and not hasattr(lib, name):
+            continue
         fn = getattr(lib, name)            # AttributeError if the library does not export a declared symbol
         fn.restype = res
         fn.argtypes = args

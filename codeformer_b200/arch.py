@@ -184,10 +184,11 @@ class VectorQuantizer(nn.Module):
         return zq, stats[0], {'perplexity': stats[1], 'min_encodings': onehot,
                               'min_encoding_indices': idx, 'mean_distance': stats[2]}
 
-    # Fused path (include/cfb200.h: cfb_vq_nearest_fast): the split codebook + |e|^2 are prepared once per embedding version,
-    # the workspace is kept, and -- like the single-face forward -- the 4-launch sequence is replayed from a CUDA graph
-    # captured per shape, so a call costs one graph launch instead of ~25 us of host-side launches.
-    vq_graphs = True
+    # Fused path (include/cfb200.h: cfb_vq_nearest_fast): the split codebook + |e|^2 are prepared once per embedding version and
+    # the workspace is kept per shape.  The library runs the whole forward as ONE kernel (conv_tc.cu: vq_fused_kernel), so a call
+    # is one launch on the caller's tensors; replaying it from a CUDA graph would only add the staging copies of z / z_q
+    # (measured: no gain), hence ``vq_graphs`` is off by default.  CFB_VQ_FUSED=0 (the 4-launch sequence) still profits from it.
+    vq_graphs = False
 
     def _forward_fused(self, lib, z, E, return_min_encodings):
         dev = z.device
@@ -209,13 +210,19 @@ class VectorQuantizer(nn.Module):
                                                _lib.ptr(zq), _lib.ptr(idx), _lib.ptr(stats), _lib.ptr(onehot), _lib.ptr(ws),
                                                ws.numel(), _stream_ptr(dev)), 'cfb_vq_nearest_fast')
 
-        def buffers():
+        def buffers(keep_ws=False):
+            ws = cache.setdefault('ws', {}).get((B, H, W)) if keep_ws else None
+            if ws is None:
+                ws = torch.empty(int(lib.cfb_vq_fast_workspace_bytes(B, H * W, D, K)), dtype=torch.uint8, device=dev)
+                if keep_ws:
+                    if len(cache['ws']) >= 4:
+                        cache['ws'].pop(next(iter(cache['ws'])))
+                    cache['ws'][(B, H, W)] = ws
             return (torch.empty_like(z), torch.empty((T, 1), dtype=torch.int64, device=dev),
                     torch.empty(4, dtype=torch.float32, device=dev),
-                    torch.empty((T, K), dtype=torch.float32, device=dev) if return_min_encodings else None,
-                    torch.empty(int(lib.cfb_vq_fast_workspace_bytes(B, H * W, D, K)), dtype=torch.uint8, device=dev))
-        use_graph = T > 0 and self.vq_graphs and os.environ.get('CFB_CUDA_GRAPH', '1') != '0' \
-            and not torch.cuda.is_current_stream_capturing()
+                    torch.empty((T, K), dtype=torch.float32, device=dev) if return_min_encodings else None, ws)
+        use_graph = T > 0 and (self.vq_graphs or os.environ.get('CFB_VQ_FUSED', '1') == '0') \
+            and os.environ.get('CFB_CUDA_GRAPH', '1') != '0' and not torch.cuda.is_current_stream_capturing()
         if use_graph:
             key = (B, H, W, bool(return_min_encodings))
             ent = cache['graphs'].get(key)
@@ -242,7 +249,8 @@ class VectorQuantizer(nn.Module):
                 st = stats.clone()
                 return zq.clone(), st[0], {'perplexity': st[1], 'min_encodings': None if onehot is None else onehot.clone(),
                                             'min_encoding_indices': idx.clone(), 'mean_distance': st[2]}
-        zq, idx, stats, onehot, ws = buffers()
+        # the kept workspace is only scratch of one launch; calls of one module are ordered by the caller's stream
+        zq, idx, stats, onehot, ws = buffers(keep_ws=not torch.cuda.is_current_stream_capturing())
         launch(z, zq, idx, stats, onehot, ws)
         return zq, stats[0], {'perplexity': stats[1], 'min_encodings': onehot, 'min_encoding_indices': idx, 'mean_distance': stats[2]}
 

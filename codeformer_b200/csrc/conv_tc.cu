@@ -210,6 +210,8 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const float* __restrict__ 
 __global__ void __launch_bounds__(256) concat_planes_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                             __half* __restrict__ hi, __half* __restrict__ lo, int64_t pixels,
                                                             int Ca, int Cb) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int C8 = (Ca + Cb) >> 3;
   const int64_t total = pixels * C8;
   float vmax = 0.f;
@@ -238,9 +240,8 @@ int concat_planes(const float* a, const float* b, void* planes, int64_t pixels, 
   const size_t plane = ((size_t)pixels * (Ca + Cb) * 2 + 1023) / 1024 * 1024;
   const int64_t total = pixels * ((Ca + Cb) >> 3);
   const int64_t blocks = (total + 255) / 256;
-  concat_planes_kernel<<<(unsigned)(blocks > 148 * 32 ? 148 * 32 : blocks), 256, 0, st>>>(a, b, (__half*)planes,
-                                                                                         (__half*)((char*)planes + plane), pixels, Ca, Cb);
-  CFB_LAUNCH_CHECK();
+  CFB_LAUNCH_PDL(concat_planes_kernel, dim3((unsigned)(blocks > 148 * 32 ? 148 * 32 : blocks)), dim3(256), 0, st, a, b, (__half*)planes,
+                 (__half*)((char*)planes + plane), pixels, Ca, Cb);
   return 0;
 }
 
@@ -504,6 +505,18 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// float4 forms for the epilogue's transpose patches.  The dynamic shared-memory base is realigned through an integer cast, so
+// plain pointer accesses compile to GENERIC ld/st (LD.E / ST.E with 64-bit address arithmetic); these stay in the shared window.
+// No "memory" clobber: volatile asms keep their mutual order and every write -> read hand-off of a patch crosses a
+// __syncwarp(), while the compiler stays free to move the residual / SFT global loads of a row batch ahead of them.
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128f(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d));
+}
 // 8 raw values -> y = act(x * sc + sh) -> fp16 hi / lo words.  MODE 2: affine + SiLU, 1: affine, 0: plain split.
 // SiLU = y / (1 + 2^(-y log2 e)) with ex2.approx / rcp.approx (~2^-21 relative: below the hi/lo operand error of 2^-22..2^-21).
 // lo = rn(y - hi) is formed as -(hi - y) with one mixed-precision subtract per element and a sign flip of the packed pair.
@@ -581,6 +594,7 @@ struct TcParams {
   int N, Ho, Wo, Cout;
   int taps, pad, stride;  // 9/1/1 (3x3 'same'), 1/0/1 (1x1), 9/0/2 (Downsample: pad right/bottom = TMA OOB zero fill)
   int BW, BH;             // pixel tile = BH rows x BW cols = 128
+  int bw_shift;           // log2(BW) when BW is a power of two, else -1
   int tiles_x, tiles_y;   // per image
   int m_tiles, n_tiles;
   int kblocks;            // Cin / 64
@@ -625,7 +639,10 @@ struct TcParams {
   __half* pl_lo;
   float* gn_part;           // optional GroupNorm(32) partial sums of `out`: [m_tile*4 + warp][32][2]
   int gn_cpg;               // channels per group = Cout/32
+  long long* dbg;           // diagnostics (cfb_debug_set_stamps): CTA 0 writes clock64() at its role hand-offs; null in production
 };
+// phase stamps of CTA 0 (tools/tc_stamps.py): one lane per role writes the SM cycle counter
+#define TC_STAMP(i) do { if (p.dbg != nullptr && blockIdx.x == 0) p.dbg[i] = clock64(); } while (0)
 
 constexpr int TC_EPI_WARPS = 8;                       // 4 TMEM lane quadrants x 2 column halves
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;   // warp0 TMA, warp1 MMA, warps 2..9 epilogue
@@ -672,8 +689,15 @@ struct TcCfg {
   // fused operand transform (XF, halo + pair only): the A patches arrive as RAW fp16 hi/lo planes of the producing conv's
   // output and four transform warps apply GroupNorm-affine + SiLU + the hi/lo re-split in place before the MMAs read them;
   // one more A slot for the short-K (Cin = 64) layers, whose MMA time per patch is below TMA + transform latency
-  static constexpr int XF_WARPS = (BN == 64) ? 8 : 4;
-  static constexpr int XF_THREADS = TC_THREADS + 32 * XF_WARPS + 32;
+  // 20 warps = 5 warp groups with their own register budgets (setmaxnreg, see conv_tc_kernel).  The kernel is launched with
+  // 96 registers per thread (640 threads); setmaxnreg only moves registers INSIDE that allocation (the CTA's pool), so the
+  // budgets must add up to at most 20 x 96 warp-registers: producers 48, epilogue 128, transform 88.
+  static constexpr int XF_WARPS = 8;
+  static constexpr int XF_THREADS = 640;
+  static constexpr int XF_REGS_LAUNCH = 96;
+  static constexpr int XF_REGS_PRODUCER = 48, XF_REGS_EPILOGUE = 128, XF_REGS_TRANSFORM = 88;
+  static_assert(4 * XF_REGS_PRODUCER + 8 * XF_REGS_EPILOGUE + 8 * XF_REGS_TRANSFORM <= 20 * XF_REGS_LAUNCH,
+                "setmaxnreg budgets exceed the CTA's register allocation: the epilogue's request could never be granted");
   static constexpr int X_A_SLOTS = (BN == 64) ? 3 : 2;
   static constexpr int X_A_PLANE2 = H_A_PLANE + XF_SKEW;   // second plane of an XF slot (ends at 46720 <= H_A_SLOT)
   static constexpr int X_B_SLOTS = 4;
@@ -724,15 +748,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(araw + 3);
   uint8_t* stage_buf = reinterpret_cast<uint8_t*>(bars) + 512;      // epilogue transpose patches (16-byte aligned)
 
-  // Roles are numbered logically (0 TMA, 1 MMA, 2..9 epilogue, 10.. transform, then the patch loader) but sit on the warp
-  // ids in REVERSE order: the sub-partition arbiter favours the highest warp id among its eligible warps, and the role that
-  // must never wait for an issue slot is the MMA issuer, then the TMA producer, then the epilogue; the instruction-heavy
-  // transform warps come last.  (TMEM lane quadrants follow the PHYSICAL warp id: lg below.)
+  // Roles are numbered logically (0 TMA, 1 MMA, 2..9 epilogue, 10.. transform, then the patch loader).  Without the transform
+  // they sit on the warp ids in REVERSE order: the sub-partition arbiter favours the highest warp id among its eligible warps,
+  // and the role that must never wait for an issue slot is the MMA issuer, then the TMA producer, then the epilogue.  The
+  // transform variants (20 warps) align the roles with warp GROUPS of four, the unit of setmaxnreg: physical warps 0..3 =
+  // TMA, MMA, patch loader, spare; 4..11 = epilogue; 12..19 = transform.  (TMEM lane quadrants follow the PHYSICAL warp id.)
   constexpr int NWARPS = (XF ? TcCfg<BN>::XF_THREADS : TC_THREADS) / 32;
   const int pwarp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
-  const int warp = NWARPS - 1 - pwarp;
+  constexpr int XF_LOADER = 2 + TC_EPI_WARPS + TcCfg<BN>::XF_WARPS;         // logical id of the patch loader
+  const int warp = !XF ? NWARPS - 1 - pwarp
+                       : (pwarp >= 4 ? pwarp - 2 : (pwarp < 2 ? pwarp : (pwarp == 2 ? XF_LOADER : XF_LOADER + 1)));
   const int lane = threadIdx.x & 31;
   bool aborted = false;      // set when a barrier wait timed out anywhere on the device: leave the role loop (see mbar_wait)
+  if (threadIdx.x == 0) {
+    TC_STAMP(0);
+    if (p.dbg != nullptr && blockIdx.x == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); p.dbg[14] = (long long)gt; }
+  }
 
   if (warp == 0 && lane == 0) {
     for (int a = 0; a < 3; ++a) {
@@ -770,6 +801,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if constexpr (PAIR) cluster_sync_all();      // both CTAs: barriers initialised, TMEM allocated
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above touched only this CTA's shared / tensor memory and the kernel parameters.
+  // The next grid of the stream may start its own set-up now; this one waits here until the previous grid has completed.
+  pdl_launch_dependents();
+  pdl_wait();
+  if (threadIdx.x == 0) TC_STAMP(1);
 
   // pair mode enumerates PAIRS of m-tiles: pm -> m-tiles (2pm, 2pm+1); Upsample keeps both CTAs on the same output
   // parity (shared weights): pm -> parity pm&3 of low-res tiles 2(pm>>2), 2(pm>>2)+1
@@ -780,6 +816,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     else return pm;
   };
 
+  // Register budgets per warp group in the transform variants (the kernel is launched at <= 96 registers per thread for its 640
+  // threads): each role class re-sizes its allocation as the first thing in its branch -- the producer and transform groups
+  // give registers back, the epilogue groups take them (64 accumulators + a full row batch in flight, no spills).
+  if (XF ? pwarp < 4 : warp < 2) {
+  if constexpr (XF) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TcCfg<BN>::XF_REGS_PRODUCER));
   if (warp == 0) {
     // ============================ TMA producer (warp converged, one elected lane issues) ============================
     {
@@ -823,6 +864,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               const int btap = p.up4 ? (mt & 3) * 4 + tap : tap;      // Upsample: weight slice of this output parity
               mbar_wait<500>(smem_u32(empty + stage), phase ^ 1, aborted); if (aborted) goto teardown;
               if (elect_one()) {
+                if (tile == first_tile && tap == 0 && kb == 0) TC_STAMP(2);
                 const uint32_t sb = smem_u32(ring_base + stage * RING_BYTES);
                 if constexpr (PAIR) {
                   if (rank == 0) mbar_expect_tx(smem_u32(full + stage), (uint32_t)(2 * Cfg::HP_B_SLOT));
@@ -850,6 +892,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             for (int kb = 0; kb < p.kblocks; ++kb) {
               mbar_wait<500>(smem_u32(empty + stage), phase ^ 1, aborted); if (aborted) goto teardown;
               if (elect_one()) {
+                if (tile == first_tile && tap == 0 && kb == 0) TC_STAMP(2);
                 const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
                 // multi-head batched GEMM: image index n = n_img * heads + head
                 const int hh = p.heads > 1 ? n % p.heads : 0, nimg = p.heads > 1 ? n / p.heads : n;
@@ -920,6 +963,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                   mbar_wait_cl(smem_u32(full + stage), phase, aborted); if (aborted) goto teardown;
                   tc_fence_after();
                   if (elect_one()) {
+                    if (tile == first_tile && it == 0) TC_STAMP(3);
                     const uint32_t d_tmem = tmem_base + (uint32_t)(slot * Cfg::SLOT_COLS);
                     const uint32_t aoff = (uint32_t)((r * p.PW + sft) * 128);
                     const uint32_t ah = desc_lo(a_hi0 + aoff), al = desc_lo(a_lo0 + aoff);
@@ -933,6 +977,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     tc_commit_pair(smem_u32(empty + stage), (uint16_t)3);
                     if ((it % p.chunk) == p.chunk - 1 || it == nk - 1) tc_commit_pair(smem_u32(cfull + slot), (uint16_t)3);
                     if (tap == p.taps - 1) tc_commit_pair(smem_u32(aempty + aslot), (uint16_t)3);
+                    if (tile == first_tile && it == nk - 1) TC_STAMP(4);
                   }
                   __syncwarp();
                   if (++stage == NRING) { stage = 0; phase ^= 1; }
@@ -998,6 +1043,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 mbar_wait_cl(smem_u32(full + stage), phase, aborted); if (aborted) goto teardown;
                 tc_fence_after();
                 if (elect_one()) {
+                  if (tile == first_tile && it == 0) TC_STAMP(3);
                   const uint32_t d_tmem = tmem_base + (uint32_t)(slot * Cfg::SLOT_COLS);
                   const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
                   const uint32_t ah = desc_lo(sa), al = desc_lo(sa + TC_A_BYTES);
@@ -1009,6 +1055,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                   }
                   tc_commit_pair(smem_u32(empty + stage), (uint16_t)3);             // stage reusable in BOTH CTAs
                   if (it == it1 - 1) tc_commit_pair(smem_u32(cfull + slot), (uint16_t)3);   // both epilogues fold their rows
+                  if (tile == first_tile && it == nk - 1) TC_STAMP(4);
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -1045,7 +1092,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
       }
     }
-  } else if (XF && warp == 2 + TC_EPI_WARPS + TcCfg<BN>::XF_WARPS) {
+  } else if (XF && warp == XF_LOADER) {
     // ============================ XF: A-patch loader (own warp: patches must be requested a whole patch ahead) ==========
     // The patch of one 64-channel block arrives as RAW fp32 NHWC values of the producing conv's output: two TMA boxes of
     // 32 channels (128 B rows, 128B swizzle) into the two planes of the slot.  tmA_hi / tmA_lo are the fp32 tensor maps of
@@ -1070,6 +1117,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             const bool src0 = kb < p.a_split;
             const CUtensorMap* src = src0 ? &tmA_hi : &tmA_lo;
             const int c0 = (src0 ? kb : kb - p.a_split) * 64;
+            if (tile == first_tile && kb == 0) TC_STAMP(10);
             mbar_expect_tx(rb, (uint32_t)(2 * p.PW * p.PH * 128));
             tma_load_4d(sa, src, rb, c0, x0 - p.pad, y0 - p.pad, n);
             tma_load_4d(sa + Cfg::X_A_PLANE2, src, rb, c0 + 32, x0 - p.pad, y0 - p.pad, n);
@@ -1079,7 +1127,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
       }
     }
+  }      // (the fourth warp of the producers' group has no role)
   } else if (XF && warp >= 2 + TC_EPI_WARPS) {
+    if constexpr (XF) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TcCfg<BN>::XF_REGS_TRANSFORM));
     // ============================ XF: operand transform (warps 10..) ============================
     // raw fp32 patch (zero outside the image: TMA out-of-bounds fill) -> y = act(x * scale[n,c] + shift[n,c]) (GroupNorm folded
     // into scale/shift, vqgan_arch.py:14-20,153-160) -> fp16 hi = rn(y), lo = rn(y - hi), written back IN PLACE in the
@@ -1130,6 +1180,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             for (int k = 0; k < 8; ++k) { sc[k] = 1.f; sh[k] = 0.f; }
           }
           mbar_wait<250>(smem_u32(araw + aslot), aphase, aborted); if (aborted) goto teardown;
+          if (t == 0 && tile == first_tile && kb == 0) TC_STAMP(11);
+          if (t == 0 && tile == first_tile + tile_step && kb == 0) TC_STAMP(19);
           const uint32_t base0 = smem_u32(smem + aslot * Cfg::H_A_SLOT);
           const uint32_t src_base = base0 + (pl ? (uint32_t)Cfg::X_A_PLANE2 : 0u);
           const uint32_t lo_base = base0 + (uint32_t)Cfg::X_A_PLANE2;
@@ -1173,6 +1225,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(afull_leader + (uint32_t)(aslot * 8));
+          if (t == 0 && tile == first_tile && kb == 0) TC_STAMP(12);
+          if (t == 0 && tile == first_tile + tile_step && kb == 0) TC_STAMP(20);
           if (++aslot == A_SLOTS) { aslot = 0; aphase ^= 1; }
         }
       }
@@ -1180,12 +1234,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
   } else {
     // ============================ epilogue (warps 2..9) ============================
+    if constexpr (XF) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TcCfg<BN>::XF_REGS_EPILOGUE));
     constexpr int HC = BN / 2;               // columns owned by this thread
     const int lg = pwarp & 3;                // TMEM lane quadrant this warp may access: lanes [32*lg, 32*lg+32) (physical warp id)
     const int half = (warp - 2) >> 2;        // which half of the tile's columns (logical warps e and e+4 share a quadrant)
     const int row = lg * 32 + lane;          // pixel row of the tile
     const int cbase = half * HC;
     const float wsi = __ldg(p.wscale_inv);
+    // tile geometry: 8 x 16 pixels on the halo engine (compile-time), else BW = 2^bw_shift columns (or any BW: division)
+    const int BW = HALO ? 8 : p.BW, BH = HALO ? 16 : p.BH;
+    const int bw_shift = HALO ? 3 : p.bw_shift;
+    // element strides of one tile row / column in `out` (Upsample tiles write every second pixel of the output)
+    const int64_t SW = (int64_t)(p.up4 ? 2 : 1) * p.Cout, SH = SW * p.Wo;
     int slot = 0;
     uint32_t slot_phase = 0;
     float omax = 0.f;                        // largest magnitude emitted into fp16 operand planes (range guard)
@@ -1201,10 +1261,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const bool hsplit = !HALO && p.heads > 1 && !p.out_per_head;       // batched-GEMM kernels only (per-tap engine)
       const int n = hsplit ? nb / p.heads : nb;
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-      const int h = row / p.BW, w = row - h * p.BW;
-      int oy = ty * p.BH + h, ox = tx * p.BW + w;
+      const int h = bw_shift >= 0 ? (row >> bw_shift) : row / BW, w = row - h * BW;
+      int oy = ty * BH + h, ox = tx * BW + w;
       if (p.up4) { oy = 2 * oy + ((mt & 3) >> 1); ox = 2 * ox + (mt & 1); }   // this tile writes one output parity
       const int64_t pix = ((int64_t)n * p.Ho + oy) * p.Wo + ox;
+      // first pixel of the tile in `out` (elements); the (row, chunk) items of the store loop are hh * SH + ww * SW away
+      const int64_t off_tile = (((int64_t)n * p.Ho + (p.up4 ? 2 * ty * BH + ((mt & 3) >> 1) : ty * BH)) * p.Wo +
+                                (p.up4 ? 2 * tx * BW + (mt & 1) : tx * BW)) * p.Cout;
       const int col0 = nt * BN + cbase + (hsplit ? (nb % p.heads) * p.o_c_head : 0);
       const int64_t off0 = pix * p.Cout + col0;
       // pull this thread's residual / SFT row slices towards L2 now: they are consumed only after the whole K loop
@@ -1224,11 +1287,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       for (int j = 0; j < HC; ++j) acc[j] = 0.f;
       for (int it0 = 0; it0 < nk; it0 += p.chunk) {
         mbar_wait<250>(smem_u32(cfull + slot), slot_phase, aborted); if (aborted) goto teardown;
+        if (warp == 2 && lane == 0 && tile == first_tile) { if (it0 == 0) TC_STAMP(5); if (it0 + p.chunk >= nk) TC_STAMP(6); }
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(slot * Cfg::SLOT_COLS + cbase);
-        if constexpr (XF) {
-          // the transform variants run 15 / 19 warps per CTA (128 / 96 registers per thread): 16-column TMEM chunks keep the
-          // fold inside the register budget (32-column chunks spilled the accumulators)
+        if constexpr (XF && BN == 128) {
+          // 144 registers per epilogue thread in the transform variants: 64 accumulators + 2 x 16 columns in flight
 #pragma unroll
           for (int c0 = 0; c0 < HC; c0 += 16) {
             uint32_t r0[16], r1[16];
@@ -1257,6 +1320,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
         if (++slot == TC_SLOTS) { slot = 0; slot_phase ^= 1; }
       }
+      if (warp == 2 && lane == 0 && tile == first_tile) TC_STAMP(7);
+      if (warp == 2 && lane == 0 && tile == first_tile + tile_step) TC_STAMP(17);
       // ---- finalize this tile: scale, bias, residual, activation, SFT, store (fp32 NHWC), GroupNorm partials.
       // A TMEM lane owns a pixel ROW, so storing straight from registers would touch 32 different 128-byte lines per
       // instruction.  Each warp instead transposes 32x32-float blocks through a private 4 KB XOR-swizzled smem patch:
@@ -1282,7 +1347,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (lane == 0) p.vq_dpart[((int64_t)mt * p.n_tiles + nt) * 8 + (warp - 2)] = ds;
         continue;
       }
-      float4* stg = reinterpret_cast<float4*>(stage_buf) + (warp - 2) * 256;     // 32 rows x 8 chunks
+      const uint32_t stg = smem_u32(stage_buf) + (uint32_t)(warp - 2) * 4096u;     // 32 rows x 8 chunks of 16 B
+      const uint32_t stg_w = stg + (uint32_t)lane * 128u;                          // this lane's row (write side)
       const int cch = lane & 7, rsub = lane >> 3;
       if constexpr (GEN) {
         // generalised placement (ParseNet / RRDBNet): ragged tiles (only pixels inside the true image are stored), destination
@@ -1293,8 +1359,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         for (int q = 0; q < HC; q += 32) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            stg[lane * 8 + (j ^ (lane & 7))] =
-                make_float4(acc[q + 4 * j] * wsi, acc[q + 4 * j + 1] * wsi, acc[q + 4 * j + 2] * wsi, acc[q + 4 * j + 3] * wsi);
+            sts128f(stg_w + (uint32_t)((j ^ (lane & 7)) << 4), acc[q + 4 * j] * wsi, acc[q + 4 * j + 1] * wsi, acc[q + 4 * j + 2] * wsi,
+                    acc[q + 4 * j + 3] * wsi);
           __syncwarp();
           const int colq = col0 + q + cch * 4;
           const bool col_ok = colq < p.cout_valid;
@@ -1304,8 +1370,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int trow = lg * 32 + it * 4 + rsub;
-            const int hh = trow / p.BW, ww = trow - hh * p.BW;
-            int oy2 = ty * p.BH + hh, ox2 = tx * p.BW + ww;
+            const int hh = trow / BW, ww = trow - hh * BW;
+            int oy2 = ty * BH + hh, ox2 = tx * BW + ww;
             if (p.up4) { oy2 = 2 * oy2 + ((mt & 3) >> 1); ox2 = 2 * ox2 + (mt & 1); }
             bool ok = col_ok && n < p.N && oy2 < p.Ho && ox2 < p.Wo;
             if (p.sub) { ok = ok && (((oy2 | ox2) & 1) == 0); oy2 >>= 1; ox2 >>= 1; }
@@ -1319,7 +1385,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int r = it * 4 + rsub;
-            float4 v = stg[r * 8 + (cch ^ (r & 7))];
+            float4 v = lds128f(stg + (uint32_t)(r * 128 + ((cch ^ (r & 7)) << 4)));
             v.x += bv.x + rres[it].x; v.y += bv.y + rres[it].y; v.z += bv.z + rres[it].z; v.w += bv.w + rres[it].w;
             if (p.out_act == OUT_LRELU) {
               v.x = v.x > 0.f ? v.x : 0.2f * v.x; v.y = v.y > 0.f ? v.y : 0.2f * v.y;
@@ -1341,15 +1407,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       for (int q = 0; q < HC; q += 32) {
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          stg[lane * 8 + (j ^ (lane & 7))] =
-              make_float4(acc[q + 4 * j] * wsi, acc[q + 4 * j + 1] * wsi, acc[q + 4 * j + 2] * wsi, acc[q + 4 * j + 3] * wsi);
+          sts128f(stg_w + (uint32_t)((j ^ (lane & 7)) << 4), acc[q + 4 * j] * wsi, acc[q + 4 * j + 1] * wsi, acc[q + 4 * j + 2] * wsi,
+                  acc[q + 4 * j + 3] * wsi);
         __syncwarp();
         const int colq = col0 + q + cch * 4;                  // first of this lane's 4 channels
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + colq));
         // global offsets of the (row, chunk) items of this lane, then their residual loads in flight at once: all 8 rows, or two
         // batches of 4 in the register-capped transform variants
-        constexpr int RB = XF ? 4 : 8;
+        constexpr int RB = 8;
         float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
 #pragma unroll
         for (int ib = 0; ib < 8; ib += RB) {
@@ -1358,10 +1424,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         for (int k = 0; k < RB; ++k) {
           const int it = ib + k;
           const int trow = lg * 32 + it * 4 + rsub;
-          const int hh = trow / p.BW, ww = trow - hh * p.BW;
-          int oy2 = ty * p.BH + hh, ox2 = tx * p.BW + ww;
-          if (p.up4) { oy2 = 2 * oy2 + ((mt & 3) >> 1); ox2 = 2 * ox2 + (mt & 1); }
-          offs[k] = (((int64_t)n * p.Ho + oy2) * p.Wo + ox2) * p.Cout + colq;
+          const int hh = bw_shift >= 0 ? (trow >> bw_shift) : trow / BW, ww = trow - hh * BW;
+          offs[k] = off_tile + colq + hh * SH + ww * SW;
         }
         float4 rres[RB];
 #pragma unroll
@@ -1371,7 +1435,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         for (int k = 0; k < RB; ++k) {
           const int it = ib + k;
           const int r = it * 4 + rsub;                        // row within this warp's 32-row quadrant
-          float4 v = stg[r * 8 + (cch ^ (r & 7))];
+          float4 v = lds128f(stg + (uint32_t)(r * 128 + ((cch ^ (r & 7)) << 4)));
           const int64_t off = offs[k];
           v.x += bv.x + rres[k].x; v.y += bv.y + rres[k].y; v.z += bv.z + rres[k].z; v.w += bv.w + rres[k].w;
           if (p.out_act == OUT_LRELU) {
@@ -1434,8 +1498,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         __syncwarp();
       }
       }
+      if (warp == 2 && lane == 0 && tile == first_tile) TC_STAMP(16);
+      if (warp == 2 && lane == 0 && tile == first_tile + tile_step) TC_STAMP(18);
     }
     if (omax > 65504.f) report_overflow();   // a value left the fp16 range of the operand planes: reported, never silent
+    if (warp == 2 && lane == 0) TC_STAMP(13);
   }
 
 teardown:
@@ -1445,7 +1512,12 @@ teardown:
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) TC_STAMP(8);
   if constexpr (PAIR) cluster_sync_all();      // the peer may still read this CTA's operands / signal its barriers
+  if (threadIdx.x == 0) {
+    TC_STAMP(9);
+    if (p.dbg != nullptr && blockIdx.x == 0) { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); p.dbg[15] = (long long)gt; }
+  }
   if (warp == 1) {
     tc_fence_after();
     if constexpr (PAIR)
@@ -1468,6 +1540,8 @@ int tc_bind_status_word(unsigned* host_mapped_dev_ptr, long long wait_limit_cycl
   return 0;
 }
 static std::atomic<int> g_inject_fault{0};
+static std::atomic<long long*> g_stamps{nullptr};      // diagnostics: device buffer of >= 32 int64 (cfb_debug_set_stamps)
+int tc_set_stamps(long long* dev_ptr) { g_stamps.store(dev_ptr); return 0; }
 int tc_inject_fault(int kind) { g_inject_fault.store(kind); return 0; }
 int tc_clear_abort() {
   const unsigned zero = 0;
@@ -1533,6 +1607,11 @@ static bool pair_enabled() {
 // conv, +5 % on the step).  It is therefore used exactly when the pair engine is (CFB_TC_HALO=0 / CFB_TC_PAIR=0 switch it off).
 static bool halo_enabled() {
   static bool v = [] { const char* e = getenv("CFB_TC_HALO"); return !(e && atoi(e) == 0); }();
+  return v;
+}
+// 64-wide n-tiles for few-tile launches of wider layers (CFB_TC_SMALLN=0 keeps 128)
+static bool small_n_enabled() {
+  static const bool v = [] { const char* e = getenv("CFB_TC_SMALLN"); return !(e && atoi(e) == 0); }();
   return v;
 }
 struct TcGeom { int BW, BH; bool halo; };
@@ -1625,17 +1704,19 @@ static int launch_tc2(const TcMaps& m, const TcParams& p, int sm_count, cudaStre
     cfg.blockDim = dim3(THREADS);
     cfg.dynamicSmemBytes = SMEM;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     CFB_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, CPG, HALO, PAIR, XF, GEN, K1>, m.a_hi, m.a_lo, m.b_hi, m.b_lo, m.b_half, p));
     count_launch();
   } else {
     const int total = p.m_tiles * p.n_tiles;
     const int grid = total < sm_count ? total : sm_count;
-    conv_tc_kernel<BN, CPG, HALO, PAIR, XF, GEN, K1><<<grid, THREADS, SMEM, st>>>(m.a_hi, m.a_lo, m.b_hi, m.b_lo, m.b_half, p);
-    CFB_LAUNCH_CHECK();
+    CFB_LAUNCH_PDL((conv_tc_kernel<BN, CPG, HALO, PAIR, XF, GEN, K1>), dim3((unsigned)grid), dim3(THREADS), (size_t)SMEM, st, m.a_hi, m.a_lo,
+                   m.b_hi, m.b_lo, m.b_half, p);
   }
   return 0;
 }
@@ -1699,7 +1780,15 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
   const TcGeom geo = tc_geometry(a);
   const int BW = geo.BW, BH = geo.BH;
   const int PW = geo.halo ? BW + a.ksize - 1 : 0, PH = geo.halo ? BH + a.ksize - 1 : 0;
-  const int BN = (a.Cout % 128 == 0) ? 128 : 64;
+  int BN = (a.Cout % 128 == 0) ? 128 : 64;
+  // Few-tile launches (a single face; the 16x16 .. 64x64 layers of a small batch): with 128-wide n-tiles a handful of CTA pairs
+  // carry the whole K loop while most SMs idle (512 -> 512 @16x16, one face: 4 pairs, 30 us of MMAs each).  64-wide n-tiles
+  // double the number of pairs.  Every output element keeps its accumulation order and every GroupNorm partial its summation
+  // tree, so the result is bit-identical whichever width runs (the batch-invariance tests cover both).
+  if (BN == 128 && a.xform && !a.gen && a.ksize == 3 && a.mode == CONV_SAME && geo.halo && small_n_enabled()) {
+    const int64_t pairs128 = ((int64_t)a.N * (a.Wo / BW) * (a.Ho / BH) / 2) * (a.Cout / 128);
+    if (pairs128 * 2 <= sm_count / 2) BN = 64;
+  }
   TcMaps mp;
   CUtensorMap &mA_hi = mp.a_hi, &mA_lo = mp.a_lo, &mB_hi = mp.b_hi, &mB_lo = mp.b_lo;
   if (a.xform) {
@@ -1752,6 +1841,7 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
   p.chunk = tc_chunk_kblocks();
   p.PW = PW; p.PH = PH;
   p.BW = BW; p.BH = BH;
+  p.bw_shift = (BW & (BW - 1)) == 0 ? __builtin_ctz((unsigned)BW) : -1;
   p.tiles_x = ((p.up4 ? a.W : a.Wo) + BW - 1) / BW; p.tiles_y = ((p.up4 ? a.H : a.Ho) + BH - 1) / BH;   // exact unless gen (ragged)
   {
     int64_t lowres_tiles = (int64_t)a.N * p.tiles_x * p.tiles_y;
@@ -1773,6 +1863,7 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
   if (p.taps * p.kblocks <= 12) p.chunk = p.taps * p.kblocks;   // short K (Cin = 64): one partial sum, no 8+1 split
   p.in_scale = nullptr; p.in_shift = nullptr; p.in_act = IN_NONE; p.xform = a.xform ? 1 : 0;
   p.fault = g_inject_fault.exchange(0);
+  p.dbg = g_stamps.load();
   p.vq_e2 = a.vq_e2; p.vq_z2 = a.vq_z2; p.vq_cand = a.vq_cand; p.vq_dpart = a.vq_dpart;
   CFB_REQUIRE(!a.vq_cand || (a.vq_e2 && a.vq_z2 && a.vq_dpart && a.ksize == 1 && !a.gen && !a.xform), "conv_tc: VQ argmin epilogue needs e2, z2 and the 1x1 engine");
   p.a_split = a.in2 ? a.Cin1 / 64 : a.Cin / 64;
@@ -1802,6 +1893,12 @@ int conv_tc(const ConvArgs& a, void* scratch, int sm_count, cudaStream_t st) {
   } else {
     if (cpg == 0) return launch_tc<64, 0>(mp, p, sm_count, st);
     if (cpg == 2) return launch_tc<64, 2>(mp, p, sm_count, st);
+    // 64-wide tiles of a wider layer (few-tile launches, see above): fused-transform engine only
+    if (p.xform && p.taps == 9 && p.PW == 10 && p.PH == 18 && pair_ok(p)) {
+      if (cpg == 4) return launch_tc2<64, 4, true, true, true>(mp, p, sm_count, st);
+      if (cpg == 8) return launch_tc2<64, 8, true, true, true>(mp, p, sm_count, st);
+      if (cpg == 16) return launch_tc2<64, 16, true, true, true>(mp, p, sm_count, st);
+    }
   }
   CFB_REQUIRE(false, "conv_tc: no kernel variant for this configuration");
   return 1;
@@ -1854,10 +1951,10 @@ int bmm_tc(const BmmArgs& g, int sm_count, cudaStream_t st) {
   p.b_r_head = g.b_r_head; p.out_per_head = g.out_per_head ? 1 : 0; p.o_c_head = g.o_c_head;
   p.chunk = tc_chunk_kblocks();
   p.PW = 0; p.PH = 0;
-  p.BW = 16; p.BH = 8; p.tiles_x = 1; p.tiles_y = 2;
+  p.BW = 16; p.BH = 8; p.bw_shift = 4; p.tiles_x = 1; p.tiles_y = 2;
   p.m_tiles = g.N * g.heads * 2; p.n_tiles = g.Cout / BN; p.kblocks = g.K / 64;
   if (p.kblocks <= 12) p.chunk = p.kblocks;
-  p.in_scale = nullptr; p.in_shift = nullptr; p.in_act = IN_NONE; p.xform = 0; p.a_split = 0; p.fault = 0;
+  p.in_scale = nullptr; p.in_shift = nullptr; p.in_act = IN_NONE; p.xform = 0; p.a_split = 0; p.fault = 0; p.dbg = g_stamps.load();
   p.vq_e2 = nullptr; p.vq_z2 = nullptr; p.vq_cand = nullptr; p.vq_dpart = nullptr;
   p.Hin = 16; p.Win = 16; p.pad_mode = 0; p.sub = 0; p.out_pitch = out_pitch; p.out_c0 = 0; p.cout_valid = out_pitch; p.res_pitch = out_pitch;
   p.residual2 = nullptr; p.res2_pitch = out_pitch; p.post_scale = 1.f;
@@ -1872,6 +1969,8 @@ int bmm_tc(const BmmArgs& g, int sm_count, cudaStream_t st) {
 // softmax over rows of 256 fp32 scores -> fp16 hi/lo operand planes of the probabilities (one warp per row)
 __global__ void __launch_bounds__(256) softmax256_planes_kernel(const float* __restrict__ s, __half* __restrict__ hi,
                                                                 __half* __restrict__ lo, int64_t rows) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int l = threadIdx.x & 31;
   if (row >= rows) return;
@@ -1903,14 +2002,16 @@ __global__ void __launch_bounds__(256) softmax256_planes_kernel(const float* __r
 int softmax256_planes(const float* scores, void* planes, int64_t rows, cudaStream_t st) {
   if (rows == 0) return 0;
   const size_t plane = ((size_t)rows * 256 * 2 + 1023) / 1024 * 1024;
-  softmax256_planes_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(scores, (__half*)planes, (__half*)((char*)planes + plane), rows);
-  CFB_LAUNCH_CHECK();
+  CFB_LAUNCH_PDL(softmax256_planes_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, scores, (__half*)planes,
+                 (__half*)((char*)planes + plane), rows);
   return 0;
 }
 
 // V^T operand planes: in planes [N][256 tokens][pitch] (channels c0..c0+C) -> out planes [N][C][256], hi and lo
 __global__ void transpose_planes_kernel(const __half* __restrict__ in, __half* __restrict__ out, int pitch, int c0, int C) {
   __shared__ __half tile[32][34];
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = blockIdx.z, t0 = blockIdx.y * 32, cb = blockIdx.x * 32;
   const __half* ib = in + (int64_t)n * 256 * pitch;
   __half* ob = out + (int64_t)n * C * 256;
@@ -1926,9 +2027,8 @@ int transpose_planes(const void* in_planes, int N, int pitch, int c0, int C, voi
   dim3 grid(C / 32, 8, N);
   CFB_REQUIRE(N <= 65535, "transpose_planes: batch too large");
   for (int h = 0; h < 2; ++h) {
-    transpose_planes_kernel<<<grid, dim3(32, 8), 0, st>>>((const __half*)((const char*)in_planes + h * ip),
-                                                          (__half*)((char*)out_planes + h * op), pitch, c0, C);
-    CFB_LAUNCH_CHECK();
+    CFB_LAUNCH_PDL(transpose_planes_kernel, grid, dim3(32, 8), 0, st, (const __half*)((const char*)in_planes + h * ip),
+                   (__half*)((char*)out_planes + h * op), pitch, c0, C);
   }
   return 0;
 }

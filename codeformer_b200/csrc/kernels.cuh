@@ -48,11 +48,49 @@ int async_status_init(cudaStream_t st);      // per-device one-time setup (idemp
 int async_status_check(const char* where);   // non-zero + set_error() when a kernel reported a failure since the last check
 int tc_bind_status_word(unsigned* host_mapped_dev_ptr, long long wait_limit_cycles);   // conv_tc.cu: device symbols of this device
 int tc_clear_abort();
+int tc_set_stamps(long long* dev_ptr);     // diagnostics: phase stamps of CTA 0 (cfb_debug_set_stamps)
 int tc_inject_fault(int kind);               // test hook: the next tcgen05 conv launch drops one TMA load (-> barrier time-out)
 
 void count_launch();
 int64_t launch_count();
 void reset_launch_count();
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------
+// The forward is a chain of ~340 dependent launches; with plain stream order each one pays the launch latency and its own
+// set-up (barrier init, TMEM allocation, tensor-map prefetch: 3-5 us measured, tools/tc_stamps.py) after the previous grid has
+// drained.  Kernels launched through CFB_LAUNCH_PDL carry cudaLaunchAttributeProgrammaticStreamSerialization: their CTAs may
+// start as soon as every CTA of the previous grid has executed pdl_launch_dependents() (SM resources permitting), do their
+// set-up, and block in pdl_wait() until the previous grid has COMPLETED and its memory is visible.  Rules kept everywhere:
+//   * every thread calls pdl_wait() before its first access to global memory another kernel may have written (and before its
+//     own first global write), and before any early return;
+//   * a kernel without the attribute behaves as before (the instructions are no-ops there), so the two kinds mix freely.
+// CFB_PDL=0 switches the attribute off (A/B timing).
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// launch + error plumbing + launch counter (kernel must call pdl_wait())
+#define CFB_LAUNCH_PDL(kernel, grid, block, smem, st, ...)                                          \
+  do {                                                                                              \
+    cudaError_t _e = ::cfb::launch_pdl(kernel, grid, block, smem, st, __VA_ARGS__);                 \
+    if (_e != cudaSuccess) {                                                                        \
+      ::cfb::set_error(std::string("kernel launch failed: ") + cudaGetErrorString(_e) + " @" +      \
+                       __FILE__ + ":" + std::to_string(__LINE__));                                  \
+      return 1;                                                                                     \
+    }                                                                                               \
+    ::cfb::count_launch();                                                                          \
+  } while (0)
+#endif
 
 enum InAct { IN_NONE = 0, IN_SILU = 1 };
 enum OutAct { OUT_NONE = 0, OUT_LRELU = 1, OUT_GELU = 2 };
@@ -114,15 +152,17 @@ struct ConvArgs {
 
 int conv_f32(const ConvArgs& a, cudaStream_t st);                       // CUDA-core fp32 implicit GEMM
 // first conv: x NCHW [N,3,H,W] -> NHWC [N,H,W,Cout], 3x3 p1; weight [27][Cout] (tap-major, then cin)
+// gn_part (optional): GroupNorm(32) partial sums of `out`, [N * H*W/32 slots][32 groups][sum, sum of squares] (the layout
+// gn_coef_from_partials reads; slots per image = H*W/32)
 int conv_first(const float* x_nchw, const float* wgt, const float* bias, float* out, int N, int H, int W, int Cout,
-               cudaStream_t st);
+               cudaStream_t st, float* gn_part = nullptr);
 // last conv: NHWC [N,H,W,Cin] (+ fused affine) -> NCHW [N,3,H,W], 3x3 p1; weight [9][Cin][3]
 int conv_last(const float* in, const float* in_scale, const float* in_shift, const float* wgt, const float* bias,
               float* out_nchw, int N, int H, int W, int Cin, cudaStream_t st);
 // the same two kernels with the caller's image plumbing fused in (inference_codeformer.py:199-206,
 // basicsr/utils/img_util.py:9-35,38-94): uint8 HWC BGR face in, uint8 HWC BGR restored face out
 int conv_first_u8(const unsigned char* x_bgr_hwc, const float* wgt, const float* bias, float* out, int N, int H, int W,
-                  int Cout, cudaStream_t st);
+                  int Cout, cudaStream_t st, float* gn_part = nullptr);
 int conv_last_u8(const float* in, const float* in_scale, const float* in_shift, const float* wgt, const float* bias,
                  unsigned char* out_bgr_hwc, int N, int H, int W, int Cin, cudaStream_t st);
 int u8_to_input(const unsigned char* img_bgr_hwc, float* x_nchw, int N, int64_t HW, cudaStream_t st);

@@ -31,6 +31,10 @@ void set_error(const std::string& msg) { g_err = msg; }
 const std::string& last_error() { return g_err; }
 static std::atomic<int64_t> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+bool pdl_enabled() {
+  static const bool v = [] { const char* e = getenv("CFB_PDL"); return !(e && atoi(e) == 0); }();
+  return v;
+}
 int64_t launch_count() { return g_launches.load(); }
 void reset_launch_count() { g_launches.store(0); }
 
@@ -782,9 +786,16 @@ struct Fwd {
     const cfb_config& c = n->cfg;
     Tensor x;
     CFB_CHECK(alloc(x, B, c.img_size, c.img_size, c.nf));
+    // on the tensor-core path every GroupNorm takes its statistics from partial sums of the producing kernel's epilogue: the
+    // first conv emits them too (no pass over the 64-channel full-resolution tensor for the first ResBlock's norm1)
+    const int64_t hw = (int64_t)c.img_size * c.img_size;
+    if (engine != 1 && n->tc_ok && c.nf == 64 && hw % 256 == 0 && B <= GN_COUNTERS / 2) {
+      x.gn_slots = (int)(hw / 32);
+      CFB_CHECK(alloc_raw((void**)&x.gn_part, (size_t)B * x.gn_slots * 64 * sizeof(float)));
+    }
     if (!dry) {
-      if (in_u8) CFB_CHECK(conv_first_u8(in_u8, n->enc[0].conv.w_f32, n->enc[0].conv.bias, x.p, B, c.img_size, c.img_size, c.nf, st));
-      else CFB_CHECK(conv_first(x_nchw, n->enc[0].conv.w_f32, n->enc[0].conv.bias, x.p, B, c.img_size, c.img_size, c.nf, st));
+      if (in_u8) CFB_CHECK(conv_first_u8(in_u8, n->enc[0].conv.w_f32, n->enc[0].conv.bias, x.p, B, c.img_size, c.img_size, c.nf, st, x.gn_part));
+      else CFB_CHECK(conv_first(x_nchw, n->enc[0].conv.w_f32, n->enc[0].conv.bias, x.p, B, c.img_size, c.img_size, c.nf, st, x.gn_part));
     }
     CFB_CHECK(capture("enc.0", x));
     float *ps = nullptr, *ph = nullptr;   // pending GroupNorm of a 'norm' block
@@ -1742,6 +1753,11 @@ int cfb_debug_set_wait_limit(int64_t cycles) {
 int cfb_debug_inject_fault(int32_t kind) {
   API_BEGIN
   return cfb::tc_inject_fault(kind);
+  API_END(1)
+}
+int cfb_debug_set_stamps(int64_t* stamps) {
+  API_BEGIN
+  return cfb::tc_set_stamps((long long*)stamps);
   API_END(1)
 }
 

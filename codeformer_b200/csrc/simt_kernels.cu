@@ -242,11 +242,13 @@ __device__ __forceinline__ unsigned model_output_to_u8(float v) {
 template <int COUT, bool U8>
 __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ x, const float* __restrict__ wgt,
                                                          const float* __restrict__ bias, float* __restrict__ out,
-                                                         int N, int H, int W) {
+                                                         int N, int H, int W, float* __restrict__ gn_part) {
   __shared__ __align__(16) float ws[27 * COUT];
   __shared__ float bs[COUT];
   __shared__ float lut[U8 ? 256 : 1];
   if constexpr (U8) lut[threadIdx.x] = u8_to_model_input(threadIdx.x);
+  pdl_launch_dependents();
+  pdl_wait();
   for (int i = threadIdx.x; i < 27 * COUT; i += 256) ws[i] = wgt[i];
   for (int i = threadIdx.x; i < COUT; i += 256) bs[i] = bias ? bias[i] : 0.f;
   __syncthreads();
@@ -307,27 +309,53 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
 #pragma unroll
     for (int j = 0; j < CPT; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(acc[p][j], acc[p][j + 1], acc[p][j + 2], acc[p][j + 3]);
   }
+  if (gn_part != nullptr) {
+    // GroupNorm(32) partial sums of the values just stored, in the layout of the tensor-core epilogue's partials ([slot][32
+    // groups][sum, sum of squares], one slot per warp = 32 consecutive pixels; H*W % 256 == 0 keeps a CTA inside one image):
+    // the first ResBlock's norm1 then needs no pass over this tensor.  A thread owns 4 pixels x CPT channels = CPT/2 groups of
+    // two channels (COUT = 64); the 8 lanes with the same channel slice are reduced in a fixed order.
+    static_assert(COUT == 64, "GroupNorm partials: two channels per group");
+    float gs[CPT / 2], gq[CPT / 2];
+#pragma unroll
+    for (int g = 0; g < CPT / 2; ++g) {
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        a += acc[p][2 * g] + acc[p][2 * g + 1];
+        b += fmaf(acc[p][2 * g], acc[p][2 * g], acc[p][2 * g + 1] * acc[p][2 * g + 1]);
+      }
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+      gs[g] = a; gq[g] = b;
+    }
+    if ((threadIdx.x & 31) < 4) {
+      const int64_t slot = pix0 / 32;                       // global slot index = n * (HW / 32) + slot within the image
+      float2* dst = reinterpret_cast<float2*>(gn_part) + slot * 32 + cg * (CPT / 2);
+#pragma unroll
+      for (int g = 0; g < CPT / 2; ++g) dst[g] = make_float2(gs[g], gq[g]);
+    }
+  }
 }
 
 int conv_first(const float* x, const float* wgt, const float* bias, float* out, int N, int H, int W, int Cout,
-               cudaStream_t st) {
+               cudaStream_t st, float* gn_part) {
   CFB_REQUIRE(Cout == 64, "conv_first: only nf=64 is built");
   CFB_REQUIRE(W % 4 == 0, "conv_first: W must be a multiple of 4");
   const int64_t quads = (int64_t)N * H * W / 4;
   if (quads == 0) return 0;
-  conv_first_kernel<64, false><<<(unsigned)((quads + 63) / 64), 256, 0, st>>>(x, wgt, bias, out, N, H, W);
-  CFB_LAUNCH_CHECK();
+  CFB_REQUIRE(gn_part == nullptr || ((int64_t)H * W) % 256 == 0, "conv_first: GroupNorm partials need H*W % 256 == 0");
+  CFB_LAUNCH_PDL((conv_first_kernel<64, false>), dim3((unsigned)((quads + 63) / 64)), dim3(256), 0, st, x, wgt, bias, out, N, H, W, gn_part);
   return 0;
 }
 int conv_first_u8(const unsigned char* x_bgr_hwc, const float* wgt, const float* bias, float* out, int N, int H, int W,
-                  int Cout, cudaStream_t st) {
+                  int Cout, cudaStream_t st, float* gn_part) {
   CFB_REQUIRE(Cout == 64, "conv_first: only nf=64 is built");
   CFB_REQUIRE(W % 4 == 0, "conv_first: W must be a multiple of 4");
   const int64_t quads = (int64_t)N * H * W / 4;
   if (quads == 0) return 0;
-  conv_first_kernel<64, true><<<(unsigned)((quads + 63) / 64), 256, 0, st>>>(reinterpret_cast<const float*>(x_bgr_hwc), wgt,
-                                                                             bias, out, N, H, W);
-  CFB_LAUNCH_CHECK();
+  CFB_REQUIRE(gn_part == nullptr || ((int64_t)H * W) % 256 == 0, "conv_first: GroupNorm partials need H*W % 256 == 0");
+  CFB_LAUNCH_PDL((conv_first_kernel<64, true>), dim3((unsigned)((quads + 63) / 64)), dim3(256), 0, st,
+                 reinterpret_cast<const float*>(x_bgr_hwc), wgt, bias, out, N, H, W, gn_part);
   return 0;
 }
 
@@ -344,6 +372,8 @@ __global__ void __launch_bounds__(256) conv_last_kernel(const float* __restrict_
   const int64_t HW = (int64_t)H * W;
   const int64_t pix0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
   const int n = (int)(((int64_t)blockIdx.x * 1024) / HW);  // HW % 1024 == 0: whole CTA in one image
+  pdl_launch_dependents();
+  pdl_wait();
   for (int i = threadIdx.x; i < 9 * Cin; i += 256) {
     ws[i * 4 + 0] = wgt[i * 3 + 0]; ws[i * 4 + 1] = wgt[i * 3 + 1]; ws[i * 4 + 2] = wgt[i * 3 + 2]; ws[i * 4 + 3] = 0.f;
   }
@@ -417,8 +447,8 @@ int conv_last(const float* in, const float* in_scale, const float* in_shift, con
   if (N == 0) return 0;
   const size_t smem = (size_t)(9 * Cin * 4 + 2 * Cin) * sizeof(float);
   CFB_REQUIRE(smem <= 48 * 1024, "conv_last: Cin too large");
-  conv_last_kernel<false><<<(unsigned)(N * HW / 1024), 256, smem, st>>>(in, in_scale, in_shift, wgt, bias, out, N, H, W, Cin);
-  CFB_LAUNCH_CHECK();
+  CFB_LAUNCH_PDL(conv_last_kernel<false>, dim3((unsigned)(N * HW / 1024)), dim3(256), smem, st, in, in_scale, in_shift, wgt, bias, out, N, H,
+                 W, Cin);
   return 0;
 }
 int conv_last_u8(const float* in, const float* in_scale, const float* in_shift, const float* wgt, const float* bias,
@@ -428,9 +458,8 @@ int conv_last_u8(const float* in, const float* in_scale, const float* in_shift, 
   if (N == 0) return 0;
   const size_t smem = (size_t)(9 * Cin * 4 + 2 * Cin) * sizeof(float);
   CFB_REQUIRE(smem <= 48 * 1024, "conv_last: Cin too large");
-  conv_last_kernel<true><<<(unsigned)(N * HW / 1024), 256, smem, st>>>(in, in_scale, in_shift, wgt, bias,
-                                                                        reinterpret_cast<float*>(out_bgr_hwc), N, H, W, Cin);
-  CFB_LAUNCH_CHECK();
+  CFB_LAUNCH_PDL(conv_last_kernel<true>, dim3((unsigned)(N * HW / 1024)), dim3(256), smem, st, in, in_scale, in_shift, wgt, bias,
+                 reinterpret_cast<float*>(out_bgr_hwc), N, H, W, Cin);
   return 0;
 }
 
@@ -591,6 +620,8 @@ __global__ void __launch_bounds__(256) gn_final_f32_kernel(const float* __restri
   __shared__ double ps[8][33], pq[8][33];
   __shared__ double gmean[32], grstd[32];
   __shared__ int is_last;
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = blockIdx.y, G = gridDim.x, blk = blockIdx.x, t = threadIdx.x;
   const int g = t & 31, stripe = t >> 5;
   const int per = (slots + G - 1) / G;
@@ -660,14 +691,16 @@ int gn_coef_from_partials(const float* part, int slots, const float* gamma, cons
   const int G = gn_final_split(slots);
   CFB_REQUIRE(G == 1 || (scratch && counters), "gn_coef_from_partials: scratch / counters missing");
   CFB_REQUIRE(N <= 65535, "gn_coef_from_partials: batch too large");
-  gn_final_f32_kernel<<<dim3(G, N), 256, 0, st>>>(part, gamma, beta, scale, shift, HW, C, slots, eps, (double*)scratch, counters);
-  CFB_LAUNCH_CHECK();
+  CFB_LAUNCH_PDL(gn_final_f32_kernel, dim3(G, N), dim3(256), 0, st, part, gamma, beta, scale, shift, HW, C, slots, eps, (double*)scratch,
+                 counters);
   return 0;
 }
 
 __global__ void gn_cat_partials_kernel(const float2* __restrict__ a, const float2* __restrict__ b, float2* __restrict__ out,
                                        int64_t total) {
   // group g of the concatenated tensor = two adjacent groups of one source: channels/group doubles, 32 groups stay
+  pdl_launch_dependents();
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int g = (int)(i & 31);
     const int64_t slot = i >> 5;
@@ -680,9 +713,8 @@ int gn_cat_partials(const float* a_part, const float* b_part, float* out_part, i
   const int64_t total = total_slots * 32;
   if (total == 0) return 0;
   const int64_t blocks = (total + 255) / 256;
-  gn_cat_partials_kernel<<<(unsigned)(blocks > 2048 ? 2048 : blocks), 256, 0, st>>>((const float2*)a_part, (const float2*)b_part,
-                                                                                     (float2*)out_part, total);
-  CFB_LAUNCH_CHECK();
+  CFB_LAUNCH_PDL(gn_cat_partials_kernel, dim3((unsigned)(blocks > 2048 ? 2048 : blocks)), dim3(256), 0, st, (const float2*)a_part,
+                 (const float2*)b_part, (float2*)out_part, total);
   return 0;
 }
 
@@ -889,6 +921,8 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const float* __restrict
                                                          float* __restrict__ y2, const float* __restrict__ pos,
                                                          int pos_rows, int rows, int64_t plane_elems) {
   constexpr int V = C / 128;  // float4 per lane
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int l = threadIdx.x & 31;
   if (row >= rows) return;
@@ -938,8 +972,8 @@ int layer_norm(const float* x, const float* gamma, const float* beta, float* y, 
                int pos_rows, int rows, int C, cudaStream_t st) {
   CFB_REQUIRE(C == 512, "layer_norm: only dim_embd=512 is built");
   if (rows == 0) return 0;
-  layer_norm_kernel<512, false><<<(rows + 7) / 8, 256, 0, st>>>(x, gamma, beta, y, y2, pos, pos_rows > 0 ? pos_rows : 1, rows, 0);
-  CFB_LAUNCH_CHECK();
+  CFB_LAUNCH_PDL((layer_norm_kernel<512, false>), dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, x, gamma, beta, y, y2, pos,
+                 pos_rows > 0 ? pos_rows : 1, rows, (int64_t)0);
   return 0;
 }
 // outputs as fp16 hi/lo operand planes: [hi plane | lo plane], each align1024(rows*C*2) bytes (the conv engine's layout)
@@ -948,9 +982,8 @@ int layer_norm_planes(const float* x, const float* gamma, const float* beta, voi
   CFB_REQUIRE(C == 512, "layer_norm: only dim_embd=512 is built");
   if (rows == 0) return 0;
   const int64_t plane_elems = (int64_t)((((size_t)rows * C * 2 + 1023) / 1024 * 1024) / 2);
-  layer_norm_kernel<512, true><<<(rows + 7) / 8, 256, 0, st>>>(x, gamma, beta, (float*)y_planes, (float*)y2_planes, pos,
-                                                              pos_rows > 0 ? pos_rows : 1, rows, plane_elems);
-  CFB_LAUNCH_CHECK();
+  CFB_LAUNCH_PDL((layer_norm_kernel<512, true>), dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, x, gamma, beta, (float*)y_planes,
+                 (float*)y2_planes, pos, pos_rows > 0 ? pos_rows : 1, rows, plane_elems);
   return 0;
 }
 
@@ -960,6 +993,8 @@ int layer_norm_planes(const float* x, const float* gamma, const float* beta, voi
 __global__ void __launch_bounds__(256) argmax_gather_kernel(const float* __restrict__ logits,
                                                             const float* __restrict__ codebook, int64_t* __restrict__ idx,
                                                             float* __restrict__ quant, int T, int K, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int tok = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int l = threadIdx.x & 31;
   if (tok >= T) return;
@@ -990,8 +1025,7 @@ int argmax_gather(const float* logits, const float* codebook, int64_t* idx, floa
                   cudaStream_t st) {
   CFB_REQUIRE(D % 4 == 0, "argmax_gather: D must be a multiple of 4");
   if (T == 0) return 0;
-  argmax_gather_kernel<<<(T + 7) / 8, 256, 0, st>>>(logits, codebook, idx, quant, T, K, D);
-  CFB_LAUNCH_CHECK();
+  CFB_LAUNCH_PDL(argmax_gather_kernel, dim3((unsigned)((T + 7) / 8)), dim3(256), 0, st, logits, codebook, idx, quant, T, K, D);
   return 0;
 }
 
@@ -1021,33 +1055,54 @@ int gather_rows(const int64_t* idx, const float* codebook, float* out, int T, in
 // code a content channel is nearly constant, (x - mean)/std then amplifies a 1e-7 error of the mean by 1/std
 // (observed 3e-5 relative on quant_feat with sequential fp32 sums); an accurately rounded mean reproduces the
 // reference's own fp32 value and the rest is IEEE-deterministic.
-__global__ void adain_kernel(const float* __restrict__ content, const float* __restrict__ style, float* __restrict__ out,
-                             int HW, int C) {
-  const int b = blockIdx.x;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float* cp = content + (int64_t)b * HW * C + c;
-    const float* sp = style + (int64_t)b * HW * C + c;
-    double cs = 0.0, ss = 0.0;
-    for (int p = 0; p < HW; ++p) { cs += (double)cp[(int64_t)p * C]; ss += (double)sp[(int64_t)p * C]; }
-    const double cmd = cs / HW, smd = ss / HW;
-    double cv = 0.0, sv = 0.0;
-    for (int p = 0; p < HW; ++p) {
-      const double a = (double)cp[(int64_t)p * C] - cmd, d = (double)sp[(int64_t)p * C] - smd;
+// One CTA = 32 channels of one image: lane = channel (128-byte coalesced rows), 8 warps = 8 token stripes; every stripe sum
+// and the 8-stripe combine run in a fixed order, so the result does not depend on the batch or the launch.
+__global__ void __launch_bounds__(256) adain_kernel(const float* __restrict__ content, const float* __restrict__ style,
+                                                    float* __restrict__ out, int HW, int C) {
+  __shared__ double red[2][8][33];
+  __shared__ float stat[4][32];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.y, c = blockIdx.x * 32 + (threadIdx.x & 31), stripe = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const bool ok = c < C;
+  const float* cp = content + (int64_t)b * HW * C + c;
+  const float* sp = style + (int64_t)b * HW * C + c;
+  double cs = 0.0, ss = 0.0;
+  if (ok)
+    for (int p = stripe; p < HW; p += 8) { cs += (double)__ldg(cp + (int64_t)p * C); ss += (double)__ldg(sp + (int64_t)p * C); }
+  red[0][stripe][l] = cs; red[1][stripe][l] = ss;
+  __syncthreads();
+  double cmd = 0.0, smd = 0.0;
+  for (int k = 0; k < 8; ++k) { cmd += red[0][k][l]; smd += red[1][k][l]; }
+  cmd /= HW; smd /= HW;
+  __syncthreads();
+  double cv = 0.0, sv = 0.0;
+  if (ok)
+    for (int p = stripe; p < HW; p += 8) {
+      const double a = (double)__ldg(cp + (int64_t)p * C) - cmd, d = (double)__ldg(sp + (int64_t)p * C) - smd;
       cv += a * a; sv += d * d;
     }
-    const float cm = (float)cmd, sm = (float)smd;
-    const float cstd = sqrtf(__fadd_rn((float)(cv / (HW - 1)), 1e-5f));    // calc_mean_std: var(unbiased) + eps, sqrt
-    const float sstd = sqrtf(__fadd_rn((float)(sv / (HW - 1)), 1e-5f));
-    for (int p = 0; p < HW; ++p) {
-      const float nrm = __fdiv_rn(__fsub_rn(cp[(int64_t)p * C], cm), cstd);   // (content - mean) / std
-      out[(int64_t)b * HW * C + (int64_t)p * C + c] = __fadd_rn(__fmul_rn(nrm, sstd), sm);   // * style_std + style_mean
-    }
+  red[0][stripe][l] = cv; red[1][stripe][l] = sv;
+  __syncthreads();
+  if (stripe == 0) {
+    double cvt = 0.0, svt = 0.0;
+    for (int k = 0; k < 8; ++k) { cvt += red[0][k][l]; svt += red[1][k][l]; }
+    stat[0][l] = (float)cmd; stat[1][l] = (float)smd;
+    stat[2][l] = sqrtf(__fadd_rn((float)(cvt / (HW - 1)), 1e-5f));    // calc_mean_std: var(unbiased) + eps, sqrt
+    stat[3][l] = sqrtf(__fadd_rn((float)(svt / (HW - 1)), 1e-5f));
+  }
+  __syncthreads();
+  if (!ok) return;
+  const float cm = stat[0][l], sm = stat[1][l], cstd = stat[2][l], sstd = stat[3][l];
+  for (int p = stripe; p < HW; p += 8) {
+    const float nrm = __fdiv_rn(__fsub_rn(__ldg(cp + (int64_t)p * C), cm), cstd);      // (content - mean) / std
+    out[(int64_t)b * HW * C + (int64_t)p * C + c] = __fadd_rn(__fmul_rn(nrm, sstd), sm);   // * style_std + style_mean
   }
 }
 int adain_nhwc(const float* content, const float* style, float* out, int B, int HW, int C, cudaStream_t st) {
   if (B == 0) return 0;
-  adain_kernel<<<B, 256, 0, st>>>(content, style, out, HW, C);
-  CFB_LAUNCH_CHECK();
+  CFB_REQUIRE(B <= 65535, "adain: batch too large");
+  CFB_LAUNCH_PDL(adain_kernel, dim3((unsigned)((C + 31) / 32), (unsigned)B), dim3(256), 0, st, content, style, out, HW, C);
   return 0;
 }
 
@@ -1057,6 +1112,8 @@ int adain_nhwc(const float* content, const float* style, float* out, int B, int 
 // in [n][R][Cc] -> out [n][Cc][R]  (32x32 smem tiles)
 __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int Cc) {
   __shared__ float tile[32][33];
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = blockIdx.z;
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   const float* ib = in + (int64_t)n * R * Cc;
@@ -1075,8 +1132,7 @@ static int transpose_batched(const float* in, float* out, int n, int R, int Cc, 
   if (n == 0 || R == 0 || Cc == 0) return 0;
   dim3 grid((Cc + 31) / 32, (R + 31) / 32, n);
   CFB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "transpose: tensor too large");
-  transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(in, out, R, Cc);
-  CFB_LAUNCH_CHECK();
+  CFB_LAUNCH_PDL(transpose_kernel, grid, dim3(32, 8), 0, st, in, out, R, Cc);
   return 0;
 }
 int nchw_to_nhwc(const float* in, float* out, int N, int C, int HW, cudaStream_t st) {
