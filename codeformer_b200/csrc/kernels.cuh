@@ -67,8 +67,16 @@ void reset_launch_count();
 // CFB_PDL=0 switches the attribute off (A/B timing).
 bool pdl_enabled();
 #ifdef __CUDACC__
+#ifndef CFB_PDL_DEVICE
+#define CFB_PDL_DEVICE 1
+#endif
+#if CFB_PDL_DEVICE
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#else      // A/B builds without the device side (the host side then never sets the attribute: pdl_enabled() is false)
+__device__ __forceinline__ void pdl_wait() {}
+__device__ __forceinline__ void pdl_launch_dependents() {}
+#endif
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};

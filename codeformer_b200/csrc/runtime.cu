@@ -32,6 +32,9 @@ const std::string& last_error() { return g_err; }
 static std::atomic<int64_t> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 bool pdl_enabled() {
+#if defined(CFB_PDL_DEVICE) && !CFB_PDL_DEVICE
+  return false;
+#endif
   static const bool v = [] { const char* e = getenv("CFB_PDL"); return !(e && atoi(e) == 0); }();
   return v;
 }

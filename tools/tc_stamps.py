@@ -1,5 +1,9 @@
 """Where does a small tcgen05 conv launch spend its time?  For each shape: back-to-back launch time (CUDA events, through
-cfb_debug_time_conv) and the phase stamps of CTA 0 of the last launch (cfb_debug_set_stamps, SM cycles)."""
+cfb_debug_time_conv) and the phase stamps of CTA 0 of the last launch (cfb_debug_set_stamps, SM cycles).
+
+The stamps are a BUILD option of the library (they cost 6-13 % of every conv kernel even when unused, see csrc/conv_tc.cu):
+    tools/build_ab.sh stamps -DCFB_TC_STAMPS=1 && CFB_LIB=$PWD/codeformer_b200/ab/lib_stamps.so python tools/tc_stamps.py
+With the production build the launch times are printed and every stamp reads zero."""
 import ctypes
 import sys
 
