@@ -86,6 +86,33 @@ def test_vqautoencoder_vs_reference_golden():
     assert st['min_encodings'].shape == (256, 1024)
 
 
+def test_vqautoencoder_batch64_properties():
+    """BASELINE.json configs[3] size (VQAutoEncoder.forward at batch 64): too large for an oracle run, so the size-independent
+    properties instead -- face 0 is the reference golden (indices bit-exact, out <= 1e-3), the run is deterministic, the faces
+    do not interact (prefix of 4 == a 4-face run, bit for bit), and the batch statistics are those of the 64 x 256 indices."""
+    g = golden('vqae.npz')
+    v = cb.ARCH_REGISTRY.get('VQAutoEncoder')(512, 64, [1, 2, 2, 4, 4, 8], 'nearest', 2, [16], 1024).cuda().eval()
+    v.load_state_dict(S.random_state_dict(S.vqae_spec(), 2), strict=True)
+    gen = torch.Generator().manual_seed(23)
+    x = torch.randn(64, 3, 512, 512, generator=gen).clamp_(-1, 1)
+    x[:4] = faces_input(slice(0, 4))
+    xd = x.cuda()
+    o1, loss1, st1 = v(xd, return_min_encodings=False)
+    o1 = o1.clone()
+    idx1 = st1['min_encoding_indices'].clone()
+    o2, loss2, st2 = v(xd, return_min_encodings=False)
+    assert torch.equal(o1, o2) and torch.equal(idx1, st2['min_encoding_indices']) and float(loss1) == float(loss2)
+    assert idx1.shape == (64 * 256, 1)
+    assert np.array_equal(idx1[:256].cpu().numpy(), g['idx']), 'face 0 of the batch must pick the golden codes'
+    assert maxabs(o1[:1, :, ::4, ::4].cpu(), g['out']) < TOL_OUT
+    o4, _, st4 = v(xd[:4], return_min_encodings=False)
+    assert torch.equal(o4, o1[:4]) and torch.equal(st4['min_encoding_indices'], idx1[:4 * 256]), 'faces must not interact'
+    counts = torch.bincount(idx1[:, 0], minlength=1024).float() / idx1.shape[0]
+    ppl = torch.exp(-(counts * torch.log(counts + 1e-10)).sum())
+    assert abs(float(ppl) - float(st1['perplexity'])) < 1e-3 * float(ppl)
+    assert bool(torch.isfinite(o1).all())
+
+
 def test_reload_weights_and_errors(net_main):
     x = faces_input(slice(2, 3)).cuda()
     a = net_main(x, w=0.5, adain=True)[0]
