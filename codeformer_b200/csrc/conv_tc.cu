@@ -26,9 +26,15 @@
 //     stages half of every B operand, commits are multicast to both CTAs, both CTAs' TMA bytes are counted on the leader's
 //     mbarrier; the (10x18) input patch of a 64-channel block is fetched ONCE and the taps read it through row-shifted
 //     128B-swizzled descriptors (see the comments at TcCfg and tc_geometry; probes in tools/umma_*.py);
-//   * optional in-kernel operand transform (XF): the patches arrive as RAW planes emitted by the producing conv's epilogue
-//     and four transform warps apply GroupNorm-affine + SiLU + the hi/lo re-split in place before the MMAs read them
-//     (tc_can_xform says where it is used); the same kernel also runs the AttnBlock score / P.V GEMMs (bmm_tc).
+//   * in-kernel operand transform (XF, the default for every GroupNorm(+SiLU) consumer): the patch of a 64-channel block
+//     arrives as the fp32 ACTIVATION itself (own loader warp, two 32-channel TMA boxes) and 4 (BN = 128) or 8 (BN = 64)
+//     transform warps apply GroupNorm-affine + SiLU + the fp16 hi/lo split in place before the MMAs read it -- no operand
+//     planes in HBM, no separate preparation pass (tc_can_xform says where it is used); GEN = the same for any H x W with
+//     reflection / replicate padding (ParseNet, RRDBNet); the kernel also runs the attention GEMMs (bmm_tc);
+//   * every kernel of the forward is launched with programmatic stream serialization (PDL, kernels.cuh); few-tile launches of
+//     wide layers use 64-wide n-tiles (conv_tc()); VectorQuantizer.forward is its own one-kernel pipeline (vq_fused_kernel).
+// Diagnostics are BUILD options (-DCFB_TC_STAMPS=1): measured on B200, stamp tests inside the role loops and even two unused
+// fields in the kernel parameter block slow every conv kernel by 10-25 % (profiles/round2_ab_builds.txt) -- keep TcParams compact.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -590,8 +596,9 @@ __device__ __forceinline__ void xf_patch(uint32_t src_base, uint32_t hi_base, ui
 // ------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------
-// Phase stamps (tools/tc_stamps.py) are a BUILD option: -DCFB_TC_STAMPS=1.  Measured on B200 (tools/gpu_ab3.sh): the stamp
-// tests inside the role loops cost 6-13 % of every conv kernel even with a null stamp buffer, so production builds omit them.
+// Phase stamps (tools/tc_stamps.py) are a BUILD option: -DCFB_TC_STAMPS=1.  Measured on B200 (profiles/round2_ab_builds.txt):
+// the stamp tests inside the role loops cost 6-13 % of every conv kernel even with a null stamp buffer, and the mere presence
+// of the stamp pointer (+ one more int) in this struct another 3-15 %, so production builds omit both.
 #ifndef CFB_TC_STAMPS
 #define CFB_TC_STAMPS 0
 #endif
@@ -696,8 +703,8 @@ struct TcCfg {
   static constexpr int HP_B_SLOT = P_BX_BYTES + P_BY_BYTES;
   static constexpr int HP_B_SLOTS = (BN == 64) ? 8 : 4;
   static constexpr int HP_SMEM_BYTES = H_A_SLOTS * H_A_SLOT + HP_B_SLOTS * HP_B_SLOT + 1024 + 512 + STG_BYTES;
-  // fused operand transform (XF, halo + pair only): the A patches arrive as RAW fp16 hi/lo planes of the producing conv's
-  // output and four transform warps apply GroupNorm-affine + SiLU + the hi/lo re-split in place before the MMAs read them;
+  // fused operand transform (XF, halo + pair only): the A patches arrive as the RAW fp32 activation (two 32-channel planes per
+  // slot) and 4 / 8 transform warps apply GroupNorm-affine + SiLU + the hi/lo split in place before the MMAs read them;
   // one more A slot for the short-K (Cin = 64) layers, whose MMA time per patch is below TMA + transform latency
   static constexpr int XF_WARPS = (BN == 64) ? 8 : 4;
   static constexpr int XF_THREADS = TC_THREADS + 32 * XF_WARPS + 32;
