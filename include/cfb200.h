@@ -253,7 +253,8 @@ int cfb_debug_inject_fault(int32_t kind);
 /* diagnostics (tools/tc_stamps.py): while `stamps` (device memory, >= 32 int64) is non-NULL, CTA 0 of every tcgen05 conv launch
  * writes the SM cycle counter at its role hand-offs ([0] entry, [1] set-up done, [2] first TMA, [3] first MMA, [4] last MMA
  * issued, [5]/[6] first/last accumulator seen by the epilogue, [7] epilogue K loop done, [13] epilogue done, [8]/[9] tear-down,
- * [10..12] transform roles, [14]/[15] %globaltimer at entry / exit).  NULL switches it off. */
+ * [10..12] transform roles, [14]/[15] %globaltimer at entry / exit).  NULL switches it off.  The stamps exist only in builds of the
+ * library with -DCFB_TC_STAMPS=1 (they cost 6-13 % of every conv kernel); the production build accepts the call and ignores it. */
 int cfb_debug_set_stamps(int64_t* stamps);
 /* layout plumbing */
 int cfb_nchw_to_nhwc(const float* in, float* out, int32_t n, int32_t c, int32_t hw, void* stream);
